@@ -1,0 +1,168 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE'S OWN torch modules (imported
+unmodified through oracle/ref_loader.py) on seeded inputs.  TEST INFRASTRUCTURE.
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.make_golden
+
+The reference ships no tests / golden vectors for this path, so these
+files are the pin for the oracle's leaf functions: tests/test_oracle_golden.py checks
+oracle/{leaf_math,dynamics,rewards,actor}.py against them on any machine.
+"""
+import os
+import math
+
+import numpy as np
+import torch
+
+from . import ref_loader
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _rand_quat(g, n, normalised=True):
+    q = torch.randn(n, 4, generator=g)
+    if normalised:
+        q = q / q.norm(dim=1, keepdim=True)
+    return q
+
+
+def leaf_math(ns):
+    g = torch.Generator().manual_seed(1001)
+    n = 257
+    tu, jit = ns.torch_utils, ns.jit_utils
+    a, b = _rand_quat(g, n), _rand_quat(g, n)
+    raw = _rand_quat(g, n, normalised=False) * 1.7
+    v = torch.randn(n, 3, generator=g) * 5
+    eul = (torch.rand(n, 3, generator=g) * 2 - 1) * math.pi
+    # gimbal / saturation corner cases for euler extraction
+    a[0] = torch.tensor([0.0, math.sqrt(0.5), 0.0, math.sqrt(0.5)])
+    a[1] = torch.tensor([0.0, -math.sqrt(0.5), 0.0, math.sqrt(0.5)])
+    a[2] = torch.tensor([0.0, 0.0, 0.0, 1.0])
+    a[3] = torch.tensor([1.0, 0.0, 0.0, 0.0])
+    r, p, y = tu.get_euler_xyz_v1(a)
+    out = dict(
+        a=a, b=b, raw=raw, v=v, eul=eul,
+        quat_mul=tu.quat_mul(a, b),
+        quat_conjugate=tu.quat_conjugate(a),
+        quat_rotate=tu.quat_rotate(a, v),
+        quat_rotate_conj=tu.quat_rotate(tu.quat_conjugate(a), v),
+        euler=torch.stack((r, p, y), dim=1),
+        quat_from_euler=tu.quat_from_euler_xyz(eul[:, 0], eul[:, 1], eul[:, 2]),
+        rotmat=jit.quaternion_to_matrix(raw).reshape(n, 9),
+        rotmat_unit=jit.quaternion_to_matrix(a).reshape(n, 9),
+        quat_diff_rad=jit.quat_diff_rad(a, b),
+        rand_float=tu.torch_rand_float(-math.pi, math.pi, (4, 3), "cpu"),  # shape/API check only
+    )
+    u = torch.rand(n, generator=g)
+    out["u"] = u
+    out["rand_range_pi"] = (math.pi - (-math.pi)) * u + (-math.pi)       # torch_utils.py:219 evaluated on given u
+    np.savez(os.path.join(OUT, "leaf_math.npz"), **{k: np.asarray(t) for k, t in out.items()})
+
+
+def dynamics(ns):
+    g = torch.Generator().manual_seed(2002)
+    n = 64
+    dt = float(np.float32(0.001))
+    out = {}
+    # ---- body-rate PID: 6 consecutive calls, with exact-zero errors mixed in (quirk 9)
+    pid = ns.angvel_control.angvel_control(1, 0, n, "cpu", dt)
+    sp = (torch.rand(6, n, 3, generator=g) * 2 - 1) * 20
+    w = torch.randn(6, n, 3, generator=g) * 8
+    w[0, :8] = sp[0, :8]                      # zero error on first call
+    w[2, 8:16, 1] = sp[2, 8:16, 1]
+    sp[3, 16:20] = 900.0                      # saturate the +-400 error clip
+    res, prev = [], []
+    for i in range(6):
+        res.append(pid.compute(sp[i], w[i]).clone())
+        prev.append(pid.previous_error.clone())
+    out.update(pid_sp=sp, pid_w=w, pid_out=torch.stack(res), pid_prev=torch.stack(prev))
+    # ---- allocator
+    alloc = ref_loader.make_allocator(ns)
+    u = torch.cat((torch.rand(n, 1, generator=g) * 1000, torch.randn(n, 3, generator=g) * 150), dim=1)
+    u[:6, 0] = torch.tensor([0.0, 1000.0, 1000.0, 50.0, 999.0, 500.0])
+    u[1, 1:] = torch.tensor([300.0, 300.0, 600.0])
+    out["alloc_u"] = u.clone()
+    out["alloc_thr"] = alloc.control_allocator(u.clone())
+    # ---- battery: 40 calls with time-varying power, random initial charge
+    bat = ns.battery_dynamics.Battery_Dynamics(n, "cpu", True, dt)
+    bat.E_c[:] = torch.rand(n, 1, generator=g) * 2.2
+    pm = torch.rand(40, n, 1, generator=g) * 1500
+    pm[0] = 0.0
+    out["bat_ec0"] = bat.E_c.clone()
+    volts = [bat.sim_process(pm[i]).clone() for i in range(40)]
+    out.update(bat_pm=pm, bat_volt=torch.stack(volts), bat_u1=bat.u_1.clone(), bat_ec=bat.E_c.clone(), bat_t=bat.time.clone())
+    bat_off = ns.battery_dynamics.Battery_Dynamics(n, "cpu", False, dt)
+    out["bat_off_volt"] = bat_off.sim_process(pm[1]).clone()
+    # ---- rotor lag with randomised per-env polynomial and response time
+    rot = ns.thrust_dynamics.RotorDynamics(n, "cpu", 0.017)
+    rot.omega_para = rot.omega_para_init * (0.95 + 0.1 * torch.rand(n, 5, generator=g))
+    rot.response_time = 0.016 + 0.002 * torch.rand(n, 4, generator=g)
+    volt = 20 + 6 * torch.rand(12, n, 1, generator=g)
+    thr = 100 + 900 * torch.rand(12, n, 4, generator=g)
+    om = torch.rand(n, 4, generator=g) * 400
+    out.update(rot_poly=rot.omega_para.clone(), rot_tau=rot.response_time.clone(), rot_volt=volt, rot_thr=thr, rot_om0=om.clone())
+    oms = []
+    for i in range(12):
+        om = rot.sim_process(volt[i], thr[i], om)
+        oms.append(om.clone())
+    out["rot_om"] = torch.stack(oms)
+    # ---- aero + remap + mechanical power
+    aero = ns.thrust_dynamics.AeroDynamics(n, "cpu")
+    aero.para_force_torque = aero.para_force_torque_init * (0.95 + 0.1 * torch.rand(n, 2, generator=g))
+    aero.para_d = aero.para_d_init * (0.95 + 0.1 * torch.rand(n, 2, generator=g))
+    aero.para_t = aero.para_t_init * (0.95 + 0.1 * torch.rand(n, 1, generator=g))
+    vb = torch.randn(n, 3, generator=g) * 4
+    om = torch.rand(n, 4, generator=g) * 800
+    f, tq, bf, bt = aero.sim_process(vb, om)
+    out.update(aero_par=torch.cat((aero.para_force_torque, aero.para_d, aero.para_t), dim=1), aero_vb=vb, aero_om=om,
+               aero_f=f.clone(), aero_tq=tq.clone(), aero_bf=bf.clone(), aero_bt=bt.clone())
+    fs, ts = alloc.sim_process(f.clone(), tq.clone())
+    out.update(remap_f=fs, remap_tq=ts)
+    out["mech_power"] = torch.sum(400 * (om * 2 * torch.pi / 4500) ** 3, dim=1).unsqueeze(1)   # fpv_asymmetry.py:614 verbatim expression
+    np.savez(os.path.join(OUT, "dynamics.npz"), **{k: np.asarray(t) for k, t in out.items()})
+
+
+def rewards(ns):
+    g = torch.Generator().manual_seed(3003)
+    n = 128
+    tr = ns.task_reward
+    rel_body = torch.randn(n, 3, generator=g) * 3
+    rel_body[:4] *= 10                                   # dist > 10 -> die
+    rel_world = torch.randn(n, 3, generator=g) * 2
+    rel_world[5] = torch.tensor([0.0, 0.0, 1.0])         # degenerate horizontal direction (eps path)
+    rel_vel = torch.randn(n, 3, generator=g) * 3
+    cpos = torch.randn(n, 3, generator=g) + torch.tensor([0.0, 0.0, 2.0])
+    cpos[6:10, 2] = torch.tensor([0.05, 0.1, 0.0999, -1.0])
+    cq, tq = _rand_quat(g, n), _rand_quat(g, n)
+    relq = _rand_quat(g, n)
+    cmd_rot = torch.stack((torch.ones(n), (torch.rand(n, generator=g) * 2 - 1) * 6), dim=1)
+    cmd_flip = torch.stack((-torch.ones(n), (torch.rand(n, generator=g) * 2 - 1) * 2 * math.pi), dim=1)
+    reset = torch.zeros(n, dtype=torch.long)
+    prog = torch.randint(0, 1000, (n,), generator=g)
+    prog[10:14] = torch.tensor([998, 999, 1000, 997])
+    max_len = 1000.0
+    rp, xp = tr.compute_pos_reward(rel_body, cpos, cq, tq, reset, prog, max_len)
+    rr, xr = tr.compute_rotating_reward(rel_world.clone(), rel_vel, cpos, cq, cmd_rot, reset, prog, max_len)
+    rf, xf = tr.compute_flip_reward(rel_body, relq, cpos, cmd_flip, reset, prog, max_len)
+    out = dict(rel_body=rel_body, rel_world=rel_world, rel_vel=rel_vel, cpos=cpos, cq=cq, tq=tq, relq=relq,
+               cmd_rot=cmd_rot, cmd_flip=cmd_flip, prog=prog, pos_rew=rp, pos_reset=xp, rot_rew=rr, rot_reset=xr,
+               flip_rew=rf, flip_reset=xf)
+    np.savez(os.path.join(OUT, "rewards.npz"), **{k: np.asarray(t) for k, t in out.items()})
+
+
+def main():
+    assert ref_loader.available(), "needs the reference tree (build container only)"
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(1)
+    ns = ref_loader.load()
+    leaf_math(ns)
+    dynamics(ns)
+    rewards(ns)
+    print("golden vectors written to", OUT)
+    for f in sorted(os.listdir(OUT)):
+        print("  ", f, os.path.getsize(os.path.join(OUT, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()
