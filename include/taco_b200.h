@@ -1,0 +1,160 @@
+/* taco_b200.h -- C ABI of the B200-native fused FPV environment step.
+ *
+ * Drop-in boundary for the hot path of yinzikang/taco: everything below
+ * VecTask.step(actions) (IsaacGymEnvs/isaacgymenvs/tasks/base/vec_task_asymmetry.py:290-334)
+ * for the fpv_asymmetry tasks (IsaacGymEnvs/isaacgymenvs/tasks/fpv_asymmetry.py:34-1112).
+ *
+ * The reference's only native boundary is gymtorch.wrap_tensor_impl(data_ptr, device, dtype,
+ * shape, ...) (python/isaacgym/_bindings/src/gymtorch/gymtorch.cpp:33-158): the simulator
+ * owns device memory and hands raw pointers + shapes to torch.  This library keeps that
+ * convention: it owns every state/output buffer, exposes raw device pointers + shapes
+ * (taco_env_buffers), takes caller-owned contiguous float32 device actions, and never
+ * synchronises the host inside taco_env_step.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative
+ * TACO_E_* code (message via taco_last_error, thread-local); `stream` is a cudaStream_t
+ * passed as void* (0 = legacy default stream); one handle per device, not re-entrant per
+ * handle; handles of different processes (one per GPU under torchrun) are independent.
+ */
+#ifndef TACO_B200_H
+#define TACO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TACO_ABI_VERSION 1
+
+/* task_mode: isaacgym_task_map keys Fpv_pos / Fpv_rotate / Fpv_flip / Fpv_mix
+ * (IsaacGymEnvs/isaacgymenvs/tasks/__init__.py:33-39) */
+#define TACO_TASK_POS 0
+#define TACO_TASK_ROTATE 1
+#define TACO_TASK_FLIP 2
+#define TACO_TASK_MIX 3
+
+/* cfg switches, fpv_asymmetry.py:63-112 (names keep the upstream spelling) */
+#define TACO_F_RANDOM_COPTER_POS (1u << 0)
+#define TACO_F_RANDOM_COPTER_QUAT (1u << 1)
+#define TACO_F_RANDOM_COPTER_VEL (1u << 2)
+#define TACO_F_RANDOM_TARGET_POS (1u << 3)
+#define TACO_F_RANDOM_TARGET_YAW (1u << 4)
+#define TACO_F_BATTERY_CONSUMPTION (1u << 5)
+#define TACO_F_RANDOM_VOLTAGE (1u << 6)
+#define TACO_F_ROTOR_NOISE (1u << 7)
+#define TACO_F_ROTOR_RESPONSE (1u << 8)
+#define TACO_F_RANDOM_ROTORDYNAMIC_COE (1u << 9)
+#define TACO_F_RANDOM_ROTOR_RESPONSE (1u << 10)
+#define TACO_F_RANDOM_ROTOR_SPEED (1u << 11)
+#define TACO_F_RANDOM_AERODYNAMIC_COE (1u << 12)
+#define TACO_F_RAMDOM_DELAY_TIME (1u << 13)
+#define TACO_F_RAMDOM_DEPLOY_TIME (1u << 14)
+#define TACO_F_RANDOM_COMMAND (1u << 15)
+#define TACO_F_OBSERVATION_NOISE (1u << 16)
+/* library-only switches */
+#define TACO_F_STRICT_FP (1u << 24)   /* kernels compiled with -fmad=false: op-for-op float32 like eager torch */
+#define TACO_F_DEBUG_DELAY (1u << 25) /* record the delayed action of every control sub-step (taco_env_debug_delay) */
+
+#define TACO_OK 0
+#define TACO_E_INVALID (-1) /* bad argument / unsupported configuration */
+#define TACO_E_CUDA (-2)    /* CUDA runtime error, see taco_last_error */
+#define TACO_E_NOMEM (-3)
+
+#define TACO_NUM_OBS 26   /* fpv_asymmetry.py:107 */
+#define TACO_NUM_ACTS 4   /* fpv_asymmetry.py:102 */
+#define TACO_NUM_STATS 8
+#define TACO_STATE_WORDS 64 /* floats per env in taco_env_export_state */
+
+typedef struct TacoCfg {
+    int32_t abi_version;        /* TACO_ABI_VERSION */
+    int32_t num_envs;           /* envs simulated by this handle (cfg["env"]["numEnvs"] of the shard) */
+    int64_t env_offset;         /* global id of local env 0 (rank * num_envs under torchrun) */
+    int64_t num_envs_global;    /* total envs of the job; mix task groups are thirds of this range (fpv_asymmetry.py:924-926) */
+    int32_t task_mode;          /* TACO_TASK_* */
+    int32_t len_obs;            /* cfg["env"]["lenObservations"] */
+    int32_t len_states;         /* cfg["env"]["lenStates"] */
+    int32_t max_episode_length; /* cfg["env"]["maxEpisodeLength"] */
+    int32_t control_freq_inv;   /* cfg["env"]["controlFrequencyInv"]; the delay buffer pins it to 10 */
+    int32_t substeps;           /* cfg["sim"]["substeps"] */
+    int32_t delay_time;         /* cfg["delay_time"], ms, 0..100 */
+    uint32_t flags;             /* TACO_F_* */
+    float dt;                   /* cfg["sim"]["dt"]; rotor model pins 0.001 */
+    float rotor_response_time;  /* cfg["rotor_response_time"] */
+    float difficulty;           /* cfg["difficulty"] */
+    float clip_actions;         /* cfg["env"]["clipActions"] (inf allowed) */
+    uint64_t seed;              /* Philox key */
+} TacoCfg;
+
+/* Device pointers of the buffers VecTask exposes (vec_task_asymmetry.py:231-254).  obs and
+ * states are double-buffered: the pointers change on every step; call taco_env_buffers
+ * again after each taco_env_step (the two alternating addresses are obs_ab / states_ab). */
+typedef struct TacoBuffers {
+    float* obs;          /* (num_envs, len_obs, 26) f32, newest frame last */
+    float* states;       /* (num_envs, len_states, 26) f32 */
+    float* rew;          /* (num_envs) f32 */
+    int64_t* reset;      /* (num_envs) i64, read at the start of step (lazy reset), written at the end */
+    uint8_t* time_outs;  /* (num_envs) bool */
+    int32_t* progress;   /* (num_envs) i32 (reference: i64 progress_buf) */
+    float* obs_ab[2];
+    float* states_ab[2];
+    int32_t num_envs, len_obs, len_states, num_obs;
+} TacoBuffers;
+
+typedef struct TacoEnv TacoEnv;
+
+/* -- lifecycle: FpvBase.__init__ + VecTask.allocate_buffers (fpv_asymmetry.py:54-211, vec_task_asymmetry.py:231-254) */
+int taco_env_create(const TacoCfg* cfg, int device, TacoEnv** out);
+int taco_env_destroy(TacoEnv* env);
+int taco_env_buffers(TacoEnv* env, TacoBuffers* out);
+
+/* -- VecTask.step (vec_task_asymmetry.py:290-334): actions_dev = (num_envs,4) contiguous f32 on the env's
+ * device.  Asynchronous on `stream`, no host sync. */
+int taco_env_step(TacoEnv* env, const float* actions_dev, void* stream);
+/* Same step through HOST buffers: copies actions H2D, steps, copies rew/reset/time_outs D2H and
+ * synchronises the stream.  Any output pointer may be NULL.  Pinned host memory recommended. */
+int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host, int64_t* reset_host,
+                       uint8_t* time_outs_host, void* stream);
+/* -- VecTask.reset (vec_task_asymmetry.py:352-361) does not simulate; this additionally marks every env for
+ * reset on the next step and zeroes the observation history, i.e. restores the freshly-constructed state. */
+int taco_env_reset_all(TacoEnv* env, void* stream);
+/* -- env.difficulty is written by the trainer every epoch (algorithms/ppo_asymmetry.py:173-175) */
+int taco_env_set_difficulty(TacoEnv* env, float difficulty);
+int taco_env_set_seed(TacoEnv* env, uint64_t seed);
+
+/* -- rollout statistics accumulated on the device since the last call (ppo_asymmetry.py:313-339):
+ * [sum_reward, n_done, n_timeout, sum_episode_return, sum_episode_length, n_nonfinite, n_delay_overflow, n_env_steps]
+ * written as 8 doubles to out_dev (device) and/or out_host; clears the accumulators.  This is the vector a
+ * multi-GPU job all-reduces once per rollout. */
+int taco_env_stats(TacoEnv* env, double* out_dev, double* out_host, void* stream);
+
+/* -- synthetic U(-1,1) actions from the Philox action stream (benchmarks, tests): (num_envs,4) f32 */
+int taco_env_fill_random_actions(TacoEnv* env, float* actions_dev, uint32_t step_index, void* stream);
+
+/* -- test / checkpoint access: TACO_STATE_WORDS floats per env, layout in DESIGN.md (host pointers) */
+int taco_env_export_state(TacoEnv* env, float* out_host);
+int taco_env_import_state(TacoEnv* env, const float* in_host);
+/* delayed action read at each control sub-step of the last step: (num_envs, control_freq_inv, 4) f32, host */
+int taco_env_debug_delay(TacoEnv* env, float* out_host);
+
+/* -- actor MLP inference (algorithms/nets_asymmetry.py:23-39,326-346): see taco_actor.h section below */
+typedef struct TacoActor TacoActor;
+/* sizes = [in, h1, ..., hL, out] (n_sizes entries); weights/biases are host float32, row-major (out,in) per
+ * layer like nn.Linear; spectral projection (ppo_asymmetry.py:398-404) with lipschitz_const > 0 is applied
+ * once here ("pre-normalised once per update"). */
+int taco_actor_create(int device, const int32_t* sizes, int32_t n_sizes, TacoActor** out);
+int taco_actor_destroy(TacoActor* actor);
+int taco_actor_load(TacoActor* actor, const float* const* weights_host, const float* const* biases_host,
+                    float lipschitz_const, void* stream);
+/* mean = tanh(MLP(obs)); obs_dev (n, in) f32, mean_dev (n, out) f32.  use_tensor_cores = 0 selects the FP32
+ * CUDA-core path (parity), 1 the tcgen05 bf16 path. */
+int taco_actor_forward(TacoActor* actor, const float* obs_dev, float* mean_dev, int32_t n, int32_t use_tensor_cores,
+                       void* stream);
+
+const char* taco_last_error(void);
+int taco_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TACO_B200_H */

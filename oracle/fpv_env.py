@@ -322,7 +322,7 @@ class RefFpvEnv:
         self.overflow = self.overflow | ((self.delay_len + T) > 100)
         self.delay_len = self.delay_len + T
         rows = torch.arange(N)
-        delay_idx_log = []
+        delay_idx_log, delay_act_log = [], []
         # ---- control_freq_inv x (mid_physics_step + simulate), VT:309-313
         for k in range(self.cfi):
             self._refresh()                                            # FPV:363
@@ -330,6 +330,7 @@ class RefFpvEnv:
             idx = torch.where(idx < 0, idx + 100, idx)
             delay_idx_log.append(idx.clone())
             da = self.delay_buf[rows, :, idx]
+            delay_act_log.append(da.clone())
             # angular_vel_control, FPV:637-650
             u0 = (da[:, 0] + 1) / 2 * 1000
             sp = da[:, 1:] * 20
@@ -353,6 +354,7 @@ class RefFpvEnv:
             self.pos, self.quat, self.linvel, self.angvel = rb.integrate(                          # VT:313
                 self.pos, self.quat, self.linvel, self.angvel, force_b, torque_b, self.dt, self.substeps)
         self.last_delay_index = torch.stack(delay_idx_log, dim=1)
+        self.last_delayed_actions = torch.stack(delay_act_log, dim=1)          # (N, cfi, 4)
         # ---- post_physics_step, FPV:374-388
         self.progress_buf = self.progress_buf + 1
         self.delay_buf[:, :, 0:-10] = self.delay_buf[:, :, 10:].clone()                             # memmove semantics

@@ -1,0 +1,95 @@
+// Quaternion / vector leaf math of the fused step kernel.  Operation order follows the
+// reference's torch expressions (python/isaacgym/torch_utils.py = TU,
+// isaacgymenvs/utils/torch_jit_utils.py = JIT) so that the -fmad=false build rounds like
+// eager torch float32.  Quaternions are xyzw.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace taco {
+
+struct V3 { float x, y, z; };
+struct Q4 { float x, y, z, w; };
+
+constexpr float kPi = 3.14159265358979323846f;
+constexpr float kTwoPi = 6.28318530717958647692f;
+constexpr float kHalfPi = 1.57079632679489661923f;
+
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 neg(V3 a) { return v3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+    return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ Q4 conj(Q4 q) { Q4 r; r.x = -q.x; r.y = -q.y; r.z = -q.z; r.w = q.w; return r; }
+
+// TU:58-68 quat_rotate: v(2w^2-1) + 2w(u x v) + 2u(u.v)
+__device__ __forceinline__ V3 qrot(Q4 q, V3 v) {
+    const float s = 2.0f * q.w * q.w - 1.0f;
+    const V3 u = v3(q.x, q.y, q.z);
+    const V3 c = cross(u, v);
+    const float d = (u.x * v.x + u.y * v.y) + u.z * v.z;
+    V3 r;
+    r.x = (v.x * s + c.x * q.w * 2.0f) + u.x * d * 2.0f;
+    r.y = (v.y * s + c.y * q.w * 2.0f) + u.y * d * 2.0f;
+    r.z = (v.z * s + c.z * q.w * 2.0f) + u.z * d * 2.0f;
+    return r;
+}
+
+// TU:19-40 quat_mul (8-multiply factored form)
+__device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
+    const float ww = (a.z + a.x) * (b.x + b.y);
+    const float yy = (a.w - a.y) * (b.w + b.z);
+    const float zz = (a.w + a.y) * (b.w - b.z);
+    const float xx = ww + yy + zz;
+    const float qq = 0.5f * (xx + (a.z - a.x) * (b.x - b.y));
+    Q4 r;
+    r.w = qq - ww + (a.z - a.y) * (b.y - b.z);
+    r.x = qq - xx + (a.x + a.w) * (b.x + b.w);
+    r.y = qq - yy + (a.w - a.x) * (b.y + b.z);
+    r.z = qq - zz + (a.z + a.y) * (b.w - b.x);
+    return r;
+}
+
+// TU:175-196 get_euler_xyz_v1, roll component (the only one the hot path consumes)
+__device__ __forceinline__ float roll_of(Q4 q) {
+    const float sinr = 2.0f * (q.w * q.x + q.y * q.z);
+    const float cosr = q.w * q.w - q.x * q.x - q.y * q.y + q.z * q.z;
+    return atan2f(sinr, cosr);
+}
+
+// TU:199-213 quat_from_euler_xyz
+__device__ __forceinline__ Q4 quat_from_euler(float roll, float pitch, float yaw) {
+    float sy, cy, sr, cr, sp, cp;
+    sincosf(yaw * 0.5f, &sy, &cy);
+    sincosf(roll * 0.5f, &sr, &cr);
+    sincosf(pitch * 0.5f, &sp, &cp);
+    Q4 q;
+    q.w = cy * cr * cp + sy * sr * sp;
+    q.x = cy * sr * cp - sy * cr * sp;
+    q.y = cy * cr * sp + sy * sr * cp;
+    q.z = sy * cr * cp - cy * sr * sp;
+    return q;
+}
+
+// JIT:389-416 quaternion_to_matrix, row-major m[9]
+__device__ __forceinline__ void rotmat9(Q4 q, float* m) {
+    const float i = q.x, j = q.y, k = q.z, r = q.w;
+    const float two_s = 2.0f / (((i * i + j * j) + k * k) + r * r);
+    m[0] = 1.0f - two_s * (j * j + k * k);
+    m[1] = two_s * (i * j - k * r);
+    m[2] = two_s * (i * k + j * r);
+    m[3] = two_s * (i * j + k * r);
+    m[4] = 1.0f - two_s * (i * i + k * k);
+    m[5] = two_s * (j * k - i * r);
+    m[6] = two_s * (i * k - j * r);
+    m[7] = two_s * (j * k + i * r);
+    m[8] = 1.0f - two_s * (i * i + j * j);
+}
+
+// (hi-lo)*u + lo, TU:216-219 torch_rand_float; rng/lo are the float32 casts of the python doubles
+__device__ __forceinline__ float rr(float rng, float lo, float u) { return rng * u + lo; }
+
+// 1/(1+d^2) + 1/(1+10 d^2), task_reward.py:26-28 (note (10*d)*d)
+__device__ __forceinline__ float two_scale(float d) { return 1.0f / (1.0f + d * d) + 1.0f / (1.0f + 10.0f * d * d); }
+
+}  // namespace taco

@@ -1,0 +1,611 @@
+// Fused FPV environment step: one thread = one env, whole RL step in registers.
+//
+// Replaces, for the fpv_asymmetry tasks of yinzikang/taco (paths under IsaacGymEnvs/isaacgymenvs/):
+//   VecTask.step                      tasks/base/vec_task_asymmetry.py:290-334
+//   FpvBase.pre/mid/post_physics_step tasks/fpv_asymmetry.py:317-388
+//   refresh_state                     tasks/fpv_asymmetry.py:334-360
+//   angvel_control.compute            tasks/control/angvel_control.py:67-88
+//   control_allocator / sim_process   tasks/control/fpv_dynamics.py:35-56
+//   Battery_Dynamics.sim_process      tasks/control/battery_dynamics.py:47-75
+//   RotorDynamics / AeroDynamics      tasks/control/thrust_dynamics.py:52-104,173-199
+//   gym.simulate (PhysX, closed)      -> our documented free-body integrator (oracle/rigid_body.py)
+//   compute_observation_state         tasks/fpv_asymmetry.py:390-421 (+ :711-714,:766-771,:830-838,:929-946)
+//   compute_{pos,rotating,flip}_reward tasks/control/task_reward.py:20-143
+//   reset_idx and friends             tasks/fpv_asymmetry.py:475-603,:725-759,:783-821,:850-917,:981-1112
+//
+// This header is compiled twice: fpv_step_fast.cu (FMA contraction on) and
+// fpv_step_strict.cu (-fmad=false: every multiply/add rounds separately, like eager torch).
+#pragma once
+#include "fpv_math.cuh"
+#include "philox.cuh"
+#include "step_params.h"
+#include "../../include/taco_b200.h"
+
+namespace taco {
+
+// nominal model parameters (thrust_dynamics.py:46-47,156-167)
+__device__ constexpr float kPolyNom[5] = {0.0f, 12.9466f, 0.1872f, -5.1220f, 0.5906f};
+__device__ constexpr float kAeroNom[5] = {1.13e-05f, 0.05f, -0.386f, -0.53f, 0.009f};
+__device__ constexpr float kTurns[8] = {-3.f, -2.f, -1.f, 0.f, 0.f, 1.f, 2.f, 3.f};   // fpv_asymmetry.py:892-901
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+template <int TASK>
+__global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p) {
+    __shared__ float s_clean[kBlock * kFramePad];
+    __shared__ float s_noisy[kBlock * kFramePad];
+    __shared__ double s_stats[kNumStats];
+
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * kBlock + tid;
+    const bool valid = i < p.n;
+    const uint32_t flags = p.flags;
+    const bool obs_noise = (flags & TACO_F_OBSERVATION_NOISE) != 0;
+    if (tid < kNumStats) s_stats[tid] = 0.0;
+    __syncthreads();
+
+    float st_rew = 0.f, st_done = 0.f, st_tout = 0.f, st_epret = 0.f, st_eplen = 0.f, st_nonfin = 0.f, st_ovf = 0.f;
+    float* fc = s_clean + tid * kFramePad;
+    float* fn = s_noisy + tid * kFramePad;
+
+    if (valid) {
+        // ------------------------------------------------------------------ load
+        const float4 s0 = p.S[0][i], s1 = p.S[1][i], s2 = p.S[2][i], s3 = p.S[3][i];
+        const float4 s4 = p.S[4][i], s5 = p.S[5][i], s6 = p.S[6][i], s7 = p.S[7][i];
+        float4 act = ldg4(p.actions + i);
+        int progress = p.progress[i];
+        uint32_t qm = p.qmeta[i];
+        const bool R = p.reset_buf[i] != 0;                    // latched for the whole RL step (fpv_asymmetry.py:318)
+        float poly[5], aero[5], lag[4];
+        if (p.has_dr) {
+            const float4 d0 = p.D[0][i], d1 = p.D[1][i], d2 = p.D[2][i], d3 = p.D[3][i];
+            poly[0] = d0.x; poly[1] = d0.y; poly[2] = d0.z; poly[3] = d0.w; poly[4] = d1.x;
+            aero[0] = d1.y; aero[1] = d1.z; aero[2] = d1.w; aero[3] = d2.x; aero[4] = d2.y;
+            lag[0] = d3.x; lag[1] = d3.y; lag[2] = d3.z; lag[3] = d3.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) { poly[j] = kPolyNom[j]; aero[j] = kAeroNom[j]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) lag[j] = p.lag_gain_fixed;
+        }
+        V3 pos = v3(s0.x, s0.y, s0.z);
+        Q4 q; q.x = s0.w; q.y = s1.x; q.z = s1.y; q.w = s1.z;
+        V3 vel = v3(s1.w, s2.x, s2.y);
+        V3 wld = v3(s2.z, s2.w, s3.x);                          // angular velocity, world frame
+        V3 tpos = v3(s3.y, s3.z, s3.w);
+        Q4 tq; tq.x = 0.f; tq.y = 0.f; tq.z = s4.x; tq.w = s4.y; // target attitude is yaw-only (fpv_asymmetry.py:539-546)
+        float roll_old = s4.z, roll_cont = s4.w;
+        float om[4] = {s5.x, s5.y, s5.z, s5.w};
+        float pe[3] = {s6.x, s6.y, s6.z};
+        float cmd = s6.w;                                       // rotate: speed command; flip: flip_radian
+        float bu1 = s7.x, bec = s7.y, bt = s7.z, ep_ret = s7.w;
+
+        const float ca = p.clip_actions;                        // vec_task_asymmetry.py:304
+        act.x = clampf(act.x, -ca, ca); act.y = clampf(act.y, -ca, ca);
+        act.z = clampf(act.z, -ca, ca); act.w = clampf(act.w, -ca, ca);
+
+        const uint32_t g = (uint32_t)(p.env_offset + i);        // global env id = Philox counter word 0
+        const uint32_t k0 = p.seed_lo, k1 = p.seed_hi, t_rl = p.step_index;
+        int task = TASK;
+        const bool is_mix = (TASK == TACO_TASK_MIX);
+        if (is_mix) {
+            const long long gg = p.env_offset + i;
+            task = gg < p.mix_n1 ? TACO_TASK_POS : (gg < p.mix_n2 ? TACO_TASK_ROTATE : TACO_TASK_FLIP);
+        }
+        const float d = p.difficulty;
+        const bool at500 = (progress == 500);                   // fpv_asymmetry.py:152,597 (before counters clear)
+
+        uint32_t q_head = (qm >> QM_HEAD_SHIFT) & 15u, q_n = (qm >> QM_N_SHIFT) & 31u;
+        int q_len = (int)((qm >> QM_LEN_SHIFT) & 2047u);
+        uint32_t q_ovf = (qm >> QM_OVF_SHIFT) & 1u;
+
+        // ------------------------------------------------------------------ lazy reset (fpv_asymmetry.py:475-517)
+        if (R) {
+            const uint4 b0 = philox4x32_10(g, t_rl, 0, STREAM_RESET, k0, k1);
+            const uint4 b1 = philox4x32_10(g, t_rl, 1, STREAM_RESET, k0, k1);
+            const uint4 b2 = philox4x32_10(g, t_rl, 2, STREAM_RESET, k0, k1);
+            const uint4 b3 = philox4x32_10(g, t_rl, 3, STREAM_RESET, k0, k1);
+            const uint4 b4 = philox4x32_10(g, t_rl, 4, STREAM_RESET, k0, k1);
+            const bool flip_env = (task == TACO_TASK_FLIP);
+            // copter position (:730-737, :788-793, :855-861, :993-1036)
+            if (flags & TACO_F_RANDOM_COPTER_POS) {
+                if (flip_env && !is_mix) {
+                    pos.x = rr(p.flip_xy_rng, p.flip_xy_lo, u01(b0.x));
+                    pos.y = rr(p.flip_xy_rng, p.flip_xy_lo, u01(b0.y));
+                    pos.z = 3.0f + d * rr(4.0f, -2.0f, u01(b0.z));
+                } else {
+                    pos.x = rr(4.0f, -2.0f, u01(b0.x));
+                    pos.y = rr(4.0f, -2.0f, u01(b0.y));
+                    pos.z = 2.5f + rr(4.0f, -2.0f, u01(b0.z));
+                }
+            } else {
+                if (is_mix || task == TACO_TASK_POS) { pos.x = 0.f; pos.y = 0.f; pos.z = 2.5f; }
+                else {
+                    pos.x = rr(1.0f, -0.5f, u01(b0.x));
+                    pos.y = rr(1.0f, -0.5f, u01(b0.y));
+                    pos.z = flip_env ? 3.0f : 2.5f;
+                }
+            }
+            // attitude: rand_quat feeds its "pitch" draw into the ROLL slot (:698-704); flip is roll-only (:864,:1038)
+            if (flags & TACO_F_RANDOM_COPTER_QUAT) {
+                const float ea = rr(kTwoPi, -kPi, u01(b1.x));
+                if (flip_env) q = quat_from_euler(ea, 0.0f, 0.0f);
+                else q = quat_from_euler(ea, rr(kTwoPi, -kPi, u01(b1.y)), rr(kTwoPi, -kPi, u01(b1.z)));
+            } else { q.x = 0.f; q.y = 0.f; q.z = 0.f; q.w = 1.f; }
+            // velocities (:745-750, :869-878, :1042-1050): flip keeps stale w_y, w_z
+            if (flags & TACO_F_RANDOM_COPTER_VEL) {
+                if (flip_env) {
+                    vel = v3(rr(p.flip_lin_rng, p.flip_lin_lo, u01(b2.x)), rr(p.flip_lin_rng, p.flip_lin_lo, u01(b2.y)),
+                             rr(p.flip_lin_rng, p.flip_lin_lo, u01(b2.z)));
+                    wld.x = 10.0f * ((b0.w >> 31) ? 1.0f : -1.0f);
+                } else {
+                    vel = v3(3.0f * rr(2.0f, -1.0f, u01(b2.x)), 3.0f * rr(2.0f, -1.0f, u01(b2.y)), 3.0f * rr(2.0f, -1.0f, u01(b2.z)));
+                    wld = v3(3.0f * rr(2.0f, -1.0f, u01(b3.x)), 3.0f * rr(2.0f, -1.0f, u01(b3.y)), 3.0f * rr(2.0f, -1.0f, u01(b3.z)));
+                }
+            } else {
+                vel = v3(0.f, 0.f, 0.f);
+                if (!(flip_env && !is_mix)) wld = v3(0.f, 0.f, 0.f);   // FpvFlip leaves angvel untouched (:877-878)
+            }
+            roll_old = roll_cont = roll_of(q);                   // :752-754
+            // controllers (:550-558)
+            pe[0] = pe[1] = pe[2] = 0.f;
+            bu1 = 0.f; bt = 0.f;
+            bec = (flags & TACO_F_RANDOM_VOLTAGE) ? rr(2.2f, 0.0f, u01(b2.w)) : 0.f;
+            if (p.has_dr) {
+                const uint4 b5 = philox4x32_10(g, t_rl, 5, STREAM_RESET, k0, k1);
+                const uint4 b6 = philox4x32_10(g, t_rl, 6, STREAM_RESET, k0, k1);
+                const uint4 b7 = philox4x32_10(g, t_rl, 7, STREAM_RESET, k0, k1);
+                const uint4 b8 = philox4x32_10(g, t_rl, 8, STREAM_RESET, k0, k1);
+                if (flags & TACO_F_RANDOM_ROTORDYNAMIC_COE) {     // thrust_dynamics.py:117-122
+                    poly[0] = kPolyNom[0] * rr(p.dr_rng, p.dr_lo, u01(b5.x));
+                    poly[1] = kPolyNom[1] * rr(p.dr_rng, p.dr_lo, u01(b5.y));
+                    poly[2] = kPolyNom[2] * rr(p.dr_rng, p.dr_lo, u01(b5.z));
+                    poly[3] = kPolyNom[3] * rr(p.dr_rng, p.dr_lo, u01(b5.w));
+                    poly[4] = kPolyNom[4] * rr(p.dr_rng, p.dr_lo, u01(b6.x));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) poly[j] = kPolyNom[j];
+                }
+                if ((flags & TACO_F_ROTOR_RESPONSE) && (flags & TACO_F_RANDOM_ROTOR_RESPONSE)) {   // thrust_dynamics.py:134-137
+                    lag[0] = 0.001f / rr(p.tau_rng, p.tau_lo, u01(b8.x));
+                    lag[1] = 0.001f / rr(p.tau_rng, p.tau_lo, u01(b8.y));
+                    lag[2] = 0.001f / rr(p.tau_rng, p.tau_lo, u01(b8.z));
+                    lag[3] = 0.001f / rr(p.tau_rng, p.tau_lo, u01(b8.w));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) lag[j] = p.lag_gain_fixed;
+                }
+                if (flags & TACO_F_RANDOM_AERODYNAMIC_COE) {      // thrust_dynamics.py:201-210
+                    aero[0] = kAeroNom[0] * rr(p.dr_rng, p.dr_lo, u01(b6.y));
+                    aero[1] = kAeroNom[1] * rr(p.dr_rng, p.dr_lo, u01(b6.z));
+                    aero[2] = kAeroNom[2] * rr(p.dr_rng, p.dr_lo, u01(b6.w));
+                    aero[3] = kAeroNom[3] * rr(p.dr_rng, p.dr_lo, u01(b7.x));
+                    aero[4] = kAeroNom[4] * rr(p.dr_rng, p.dr_lo, u01(b7.y));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) aero[j] = kAeroNom[j];
+                }
+                p.D[0][i] = make_float4(poly[0], poly[1], poly[2], poly[3]);
+                p.D[1][i] = make_float4(poly[4], aero[0], aero[1], aero[2]);
+                p.D[2][i] = make_float4(aero[3], aero[4], 0.f, 0.f);
+                p.D[3][i] = make_float4(lag[0], lag[1], lag[2], lag[3]);
+            }
+            if (flags & TACO_F_RANDOM_ROTOR_SPEED) {              // thrust_dynamics.py:143-146
+                const uint4 b9 = philox4x32_10(g, t_rl, 9, STREAM_RESET, k0, k1);
+                om[0] = rr(400.0f, 0.0f, u01(b9.x)); om[1] = rr(400.0f, 0.0f, u01(b9.y));
+                om[2] = rr(400.0f, 0.0f, u01(b9.z)); om[3] = rr(400.0f, 0.0f, u01(b9.w));
+            } else { om[0] = om[1] = om[2] = om[3] = 0.f; }
+            // pending-action queue (:574-578): `delay` slots of zero action
+            q_len = p.delay_time;
+            if (flags & TACO_F_RAMDOM_DELAY_TIME) q_len = max(p.delay_time - round_normal(b1.w, 3), 0);
+            q_head = 0; q_n = 0; q_ovf = 0;
+            if (q_len > 0) {
+                p.qact[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                p.qend[i] = (uint16_t)q_len;
+                q_n = 1;
+            }
+            // target (:523-548)
+            if (flags & TACO_F_RANDOM_TARGET_POS) {
+                tpos.x = d * rr(4.0f, -2.0f, u01(b4.x));
+                tpos.y = d * rr(4.0f, -2.0f, u01(b4.y));
+                tpos.z = 3.0f + d * rr(4.0f, -2.0f, u01(b4.z));
+            } else tpos = v3(0.f, 0.f, 3.f);
+            const float yaw = (flags & TACO_F_RANDOM_TARGET_YAW) ? rr(kTwoPi, -kPi, u01(b3.w)) : 0.0f;
+            sincosf(yaw * 0.5f, &tq.z, &tq.w);
+        }
+        // ------------------------------------------------------------------ command (:587-603, :758, :814-821, :886-917, :1058-1112)
+        if (R || at500) {
+            const uint4 cb = philox4x32_10(g, t_rl, 0, STREAM_COMMAND, k0, k1);
+            if (task == TACO_TASK_POS) cmd = 0.f;
+            else if (task == TACO_TASK_ROTATE) cmd = (flags & TACO_F_RANDOM_COMMAND) ? rr(12.0f, -6.0f, u01(cb.y)) : 1.0f;
+            else {
+                if (at500) cmd = cmd + kTwoPi * kTurns[cb.x >> 29];
+                if (R) cmd = (wld.x > 5.0f) ? kTwoPi : -kTwoPi;
+            }
+        }
+        if (R) progress = 0;                                       // :510-511
+
+        // ------------------------------------------------------------------ pre_physics_step (:321-332): enqueue the action
+        int T = 10;
+        if (flags & TACO_F_RAMDOM_DEPLOY_TIME) {
+            const uint4 db = philox4x32_10(g, t_rl, 0, STREAM_DEPLOY, k0, k1);
+            T = 10 - round_normal(db.x, 1);
+        }
+        const int clk = 10 * progress;                              // absolute slot clock of buffer position 0
+        if (q_len + T <= 100 && q_n < (uint32_t)kQueueCap) {
+            const uint32_t slot = (q_head + q_n) & 15u;
+            p.qact[(size_t)slot * p.n_pad + i] = act;
+            p.qend[(size_t)slot * p.n_pad + i] = (uint16_t)(clk + q_len + T);
+            q_n += 1;
+        } else {
+            q_ovf = 1;      // reference truncates the write at slot 100 (:329): outside delay_time_max, flagged + counted
+        }
+        q_len += T;
+        // head run
+        uint32_t q_cur = q_head, q_left = q_n;
+        float4 dact = make_float4(0.f, 0.f, 0.f, 0.f);
+        int run_end = 0;
+        if (q_left > 0) {
+            dact = p.qact[(size_t)q_cur * p.n_pad + i];
+            run_end = p.qend[(size_t)q_cur * p.n_pad + i];
+        }
+
+        const float dt = p.dt, h = p.h;
+        const bool battery_on = (flags & TACO_F_BATTERY_CONSUMPTION) != 0;
+        const bool track_roll = (task == TACO_TASK_FLIP);
+        float volt = 4.35f * 6.0f;                                  // battery_dynamics.py:75
+        const Q4 qc0 = conj(q);
+        V3 vb = qrot(qc0, vel), wb = qrot(qc0, wld);
+
+        // ------------------------------------------------------------------ control_freq_inv x (mid_physics_step + simulate)
+        for (int k = 0; k < p.cfi; ++k) {
+            // refresh_state (:334-360): roll unwrap with the 1 rad threshold; body-frame velocities
+            if (track_roll) {
+                const float roll = roll_of(q);
+                float dl = roll - roll_old;
+                if (dl > 1.0f) dl = dl - kTwoPi;
+                if (dl < -1.0f) dl = dl + kTwoPi;
+                roll_cont += dl;
+                roll_old = roll;
+            }
+            if (k > 0) { const Q4 qc = conj(q); vb = qrot(qc, vel); wb = qrot(qc, wld); }
+            // delayed action (:366-368): buffer position min(len-1, k)
+            {
+                const int slot_abs = clk + min(q_len - 1, k);
+                while (slot_abs >= run_end && q_left > 1) {
+                    q_cur = (q_cur + 1) & 15u; q_left -= 1;
+                    dact = p.qact[(size_t)q_cur * p.n_pad + i];
+                    run_end = p.qend[(size_t)q_cur * p.n_pad + i];
+                }
+                if (p.dbg_delay) p.dbg_delay[(size_t)k * p.n_pad + i] = dact;
+            }
+            // angular_vel_control (:637-650) + rate PID (angvel_control.py:67-88)
+            const float u0 = (dact.x + 1.0f) / 2.0f * 1000.0f;
+            float uu[3];
+            {
+                const float sp[3] = {dact.y * 20.0f, dact.z * 20.0f, dact.w * 20.0f};
+                const float wbv[3] = {wb.x, wb.y, wb.z};
+                const float kp[3] = {27.5f, 50.0f, 200.0f};
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const float e = clampf(sp[a] - wbv[a], -400.0f, 400.0f);
+                    const float prev = (pe[a] == 0.0f) ? e : pe[a];
+                    const float pt = kp[a] * e;
+                    const float dv = clampf(0.5f * ((e - prev) / dt), -150.0f, 150.0f);
+                    uu[a] = 0.4f * (pt + dv);
+                    pe[a] = e;
+                }
+            }
+            // control_allocator (fpv_dynamics.py:35-46)
+            float thr[4];
+            {
+                const float u1 = uu[0], u2 = uu[1];
+                const float u3 = fminf(fmaxf(uu[2], -u0 / 2.0f), u0 / 2.0f);
+                thr[0] = u0 - u1 + u2 - u3;
+                thr[1] = u0 - u1 - u2 + u3;
+                thr[2] = u0 + u1 - u2 - u3;
+                thr[3] = u0 + u1 + u2 + u3;
+                const float mx = fmaxf(fmaxf(thr[0], thr[1]), fmaxf(thr[2], thr[3])) - 1000.0f;
+                const float sat = fmaxf(mx, 0.0f);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) thr[r] = clampf(thr[r] - sat, 100.0f, 1000.0f);
+            }
+            // mechanical power of the previous rotor speeds (fpv_asymmetry.py:614)
+            float pm;
+            {
+                float c[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { const float x = om[r] * 2.0f * kPi / 4500.0f; c[r] = 400.0f * (x * x * x); }
+                pm = ((c[0] + c[1]) + c[2]) + c[3];
+            }
+            // battery sag (battery_dynamics.py:47-75)
+            if (battery_on) {
+                bt = bt + dt;
+                const float pc = pm / 0.75f / 9000.0f;
+                bec = bec + pc * dt;
+                const float pavg = bec / bt;
+                float r0 = (0.0015778f + -7.7608e-5f * pavg) + (float)(0.0069498 * 1500.0);   // b0 + b1*P_avg + b2*C_c (python folds b2*C_c in double)
+                r0 = (r0 > 4.5f) ? r0 : 4.5f;
+                const float v0 = ((4.35f + -0.1102178f * bec) + 0.0103368f * (bec * bec)) + -4.3778e-4f * (bec * bec * bec);
+                bu1 = bu1 + ((0.00104846f * pc - bu1) / 3.3f) * dt;
+                const float df = v0 - bu1;
+                volt = 0.5f * (df + sqrtf(df * df - 4.0f * r0 * pc)) * 6.0f;
+            }
+            // rotor lag (thrust_dynamics.py:52-66,80-86) + optional speed noise (:68-78)
+            {
+                const float y = (volt - 23.0f) / 3.0f;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float x = thr[r] / 1000.0f;
+                    const float tgt = ((((poly[0] + poly[1] * x) + poly[2] * y) + poly[3] * (x * x)) + poly[4] * x * y) * 100.0f;
+                    om[r] = om[r] + lag[r] * (tgt - om[r]);
+                }
+                if (flags & TACO_F_ROTOR_NOISE) {
+                    const uint4 nb = philox4x32_10(g, t_rl, (uint32_t)k, STREAM_ROTOR_NOISE, k0, k1);
+                    const float rng = (float)((1.0 + 10.0 / 700.0) - (1.0 - 10.0 / 700.0)), lo = (float)(1.0 - 10.0 / 700.0);
+                    om[0] = om[0] * rr(rng, lo, u01(nb.x)); om[1] = om[1] * rr(rng, lo, u01(nb.y));
+                    om[2] = om[2] * rr(rng, lo, u01(nb.z)); om[3] = om[3] * rr(rng, lo, u01(nb.w));
+                }
+            }
+            // aerodynamics (thrust_dynamics.py:173-199), real->sim remap (fpv_dynamics.py:48-56), body wrench
+            V3 fb, tb;
+            {
+                float f[4], tqr[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { f[r] = aero[0] * om[r] * om[r]; tqr[r] = aero[1] * f[r]; }
+                const float vxy = sqrtf(vb.x * vb.x + vb.y * vb.y);
+                const float f0 = f[2], f1 = f[3], f2 = f[0], f3 = f[1];           // sim rotor (0,1,2,3) <- real (2,3,0,1)
+                const float t0 = -tqr[2], t1 = tqr[3], t2 = -tqr[0], t3 = tqr[1];
+                fb.x = aero[2] * vb.x;
+                fb.y = aero[3] * vb.y;
+                fb.z = aero[4] * vxy * vxy + (((f0 + f1) + f2) + f3);
+                tb.x = 0.059f * (((f0 + f1) - f2) - f3);
+                tb.y = 0.047f * (((f1 + f2) - f0) - f3);
+                tb.z = ((t0 + t1) + t2) + t3;
+                if (R) { fb = v3(0.f, 0.f, 0.f); tb = v3(0.f, 0.f, 0.f); }        // fpv_asymmetry.py:629-630
+            }
+            // free rigid body, `substeps` x h (DESIGN.md "integrator"; oracle/rigid_body.py)
+            {
+                const V3 fw = qrot(q, fb);
+                V3 tw = tb;
+                if (p.substeps > 1) tw = qrot(q, tb);
+                const V3 acc = v3(fw.x * p.inv_mass + 0.0f, fw.y * p.inv_mass + 0.0f, fw.z * p.inv_mass + -9.81f);
+                V3 w = wb;
+                for (int s = 0; s < p.substeps; ++s) {
+                    vel.x = vel.x + h * acc.x; vel.y = vel.y + h * acc.y; vel.z = vel.z + h * acc.z;
+                    const V3 ts = (s == 0) ? tb : qrot(conj(q), tw);
+                    const V3 iw = v3(5e-4f * w.x, 7e-4f * w.y, 8e-4f * w.z);
+                    const V3 gy = cross(w, iw);
+                    w.x = w.x + h * ((ts.x - gy.x) * 2000.0f);
+                    w.y = w.y + h * ((ts.y - gy.y) * (float)(1.0 / 7e-4));
+                    w.z = w.z + h * ((ts.z - gy.z) * 1250.0f);
+                    pos.x = pos.x + h * vel.x; pos.y = pos.y + h * vel.y; pos.z = pos.z + h * vel.z;
+                    const float wn = sqrtf((w.x * w.x + w.y * w.y) + w.z * w.z);
+                    const float half = wn * p.half_h;
+                    float sn, cs;
+                    sincosf(half, &sn, &cs);
+                    const float kk = (wn > 0.0f) ? sn / wn : p.half_h;
+                    Q4 dq; dq.x = w.x * kk; dq.y = w.y * kk; dq.z = w.z * kk; dq.w = cs;
+                    q = qmul(q, dq);
+                    const float qn = sqrtf(((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w);
+                    q.x = q.x / qn; q.y = q.y / qn; q.z = q.z / qn; q.w = q.w / qn;
+                }
+                wld = qrot(q, w);
+            }
+        }
+
+        // ------------------------------------------------------------------ post_physics_step (:374-388)
+        progress += 1;
+        {   // shift the delay buffer by 10 slots = advance the slot clock; drop exhausted runs
+            const int clk2 = clk + 10;
+            q_n = q_left; q_head = q_cur;
+            while (q_n > 0 && run_end <= clk2) {
+                q_head = (q_head + 1) & 15u; q_n -= 1;
+                if (q_n > 0) run_end = p.qend[(size_t)q_head * p.n_pad + i];
+            }
+            q_len = max(q_len - 10, 0);
+        }
+        // refresh_state
+        if (track_roll) {
+            const float roll = roll_of(q);
+            float dl = roll - roll_old;
+            if (dl > 1.0f) dl = dl - kTwoPi;
+            if (dl < -1.0f) dl = dl + kTwoPi;
+            roll_cont += dl;
+            roll_old = roll;
+        }
+        const Q4 qc = conj(q);
+        vb = qrot(qc, vel);
+        wb = qrot(qc, wld);
+        const V3 rel = v3(tpos.x - pos.x, tpos.y - pos.y, tpos.z - pos.z);
+        const V3 relb = qrot(qc, rel);
+        const Q4 rq = qmul(qc, tq);
+        float m[9];
+        rotmat9(rq, m);
+        // newest frame (:394-400) + task id / command (:713-714,:768-771,:835-838)
+        float c1 = cmd;                                              // command[:,1]
+        float o24 = 0.f, o25;
+        if (task == TACO_TASK_FLIP) {
+            c1 = clampf(cmd - roll_cont, -kTwoPi, kTwoPi);           // :831-832
+            o24 = -1.f; o25 = c1 / 2.0f / kPi;
+        } else if (task == TACO_TASK_ROTATE) { o24 = 1.f; o25 = c1 / 6.0f; }
+        else { c1 = 0.f; o25 = 0.f; }
+        fc[0] = relb.x / 3.0f; fc[1] = relb.y / 3.0f; fc[2] = relb.z / 3.0f;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) fc[3 + j] = m[j];
+        fc[12] = -vb.x / 2.0f; fc[13] = -vb.y / 2.0f; fc[14] = -vb.z / 2.0f;         // relative velocity = -(own), target is static (:147-148,:357-360)
+        fc[15] = -wb.x / kPi; fc[16] = -wb.y / kPi; fc[17] = -wb.z / kPi;
+        fc[18] = (volt - 23.0f) / 3.0f;
+        fc[19] = act.x; fc[20] = act.y; fc[21] = act.z; fc[22] = act.w;
+        fc[23] = 4.0f * clampf(pos.z, 0.0f, 0.5f) - 1.0f;
+        fc[24] = o24; fc[25] = o25;
+        bool finite = true;
+#pragma unroll
+        for (int j = 0; j < 24; ++j) finite = finite && isfinite(fc[j]);
+        finite = finite && isfinite(o25);
+        if (obs_noise) {                                              // :402-410
+            float z[12];
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const uint4 nb = philox4x32_10(g, t_rl, (uint32_t)s, STREAM_OBS_NOISE, k0, k1);
+                box_muller(nb.x, nb.y, z[4 * s + 0], z[4 * s + 1]);
+                box_muller(nb.z, nb.w, z[4 * s + 2], z[4 * s + 3]);
+            }
+            const uint4 ub = philox4x32_10(g, t_rl, 3, STREAM_OBS_NOISE, k0, k1);
+            const float sp_ = (float)(0.06 / 3 / 3), sv_ = (float)(0.1 / 3 / 2), sw_ = (float)(60.0 / 3 / 180), su_ = (float)(0.06 / 3), sh_ = (float)(0.06 / 3 / 3);
+#pragma unroll
+            for (int j = 0; j < 26; ++j) fn[j] = fc[j];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                fn[a] = fc[a] + d * (z[a] * sp_);
+                fn[12 + a] = fc[12 + a] + d * (z[3 + a] * sv_);
+                fn[15 + a] = fc[15 + a] + d * (z[6 + a] * sw_);
+            }
+            fn[18] = fc[18] + d * (z[9] * su_);
+            fn[23] = fc[23] + d * (z[10] * sh_);
+            const Q4 nq = quat_from_euler(rr(p.noise_rng, p.noise_lo, u01(ub.x)), rr(p.noise_rng, p.noise_lo, u01(ub.y)),
+                                          rr(p.noise_rng, p.noise_lo, u01(ub.z)));
+            float mn[9];
+            rotmat9(qmul(rq, nq), mn);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) fn[3 + j] = mn[j];
+        }
+        // ------------------------------------------------------------------ reward + termination (task_reward.py)
+        float rew, dist;
+        if (task == TACO_TASK_POS) {                                  // :20-47
+            dist = sqrtf((relb.x * relb.x + relb.y * relb.y) + relb.z * relb.z);
+            const Q4 mq = qmul(q, conj(tq));                          // quat_diff_rad, torch_jit_utils.py:146-164
+            const float nv = sqrtf((mq.x * mq.x + mq.y * mq.y) + mq.z * mq.z);
+            const float ang = 2.0f * asinf(fminf(nv, 1.0f));
+            rew = two_scale(dist) * two_scale(ang) / 100.0f;
+        } else if (task == TACO_TASK_ROTATE) {                        // :50-104
+            float ex = -rel.x, ey = -rel.y;
+            const float en = sqrtf(ex * ex + ey * ey) + 1e-8f;
+            ex = ex / en; ey = ey / en;
+            float yx = -ey, yy = ex;                                  // e_z x e_x
+            const float yn = sqrtf(yx * yx + yy * yy) + 1e-8f;
+            yx = yx / yn; yy = yy / yn;
+            const float hori = sqrtf(rel.x * rel.x + rel.y * rel.y) - 1.2f;
+            const float vert = fabsf(rel.z);
+            dist = sqrtf(hori * hori + vert * vert);
+            const float rvx = -vel.x, rvy = -vel.y, rvz = -vel.z;     // relative_linvel = 0 - v
+            const float vn = rvx * ex + rvy * ey;
+            const float vt = (rvx * yx + rvy * yy) - c1;
+            const float verr = sqrtf((vn * vn + vt * vt) + rvz * rvz);
+            const float two_s = 2.0f / (((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w);
+            const float hx = 1.0f - two_s * (q.y * q.y + q.z * q.z);
+            const float hy = two_s * (q.x * q.y + q.z * q.w);
+            const float ddir = 1.0f + (ex * hx + ey * hy) / sqrtf(hx * hx + hy * hy);
+            rew = two_scale(dist) * two_scale(verr) * two_scale(ddir) / 100.0f;
+        } else {                                                      // :107-143
+            dist = sqrtf((relb.x * relb.x + relb.y * relb.y) + relb.z * relb.z);
+            const float rp = 1.0f / (1.0f + 1.0f * dist) + 1.0f / (1.0f + 10.0f * dist);
+            const float rt = 1.0f / (1.0f + 10.0f * (1.0f - m[0]));
+            const float turns = c1 / 2.0f / kPi;
+            rew = rp * rt * two_scale(turns) / 100.0f;
+        }
+        const bool die = (pos.z < 0.1f) || (dist > 10.0f);
+        const bool tmax = progress >= p.max_len - 1;
+        const bool done = tmax || die;
+        const bool tout = tmax && done;                               // vec_task_asymmetry.py:323
+        // episode statistics (ppo_asymmetry.py:313-339)
+        ep_ret += rew;
+        st_rew = rew; st_done = done ? 1.f : 0.f; st_tout = tout ? 1.f : 0.f;
+        st_epret = done ? ep_ret : 0.f; st_eplen = done ? (float)progress : 0.f;
+        st_nonfin = finite ? 0.f : 1.f; st_ovf = q_ovf ? 1.f : 0.f;
+        if (done) ep_ret = 0.f;
+        // ------------------------------------------------------------------ store
+        p.S[0][i] = make_float4(pos.x, pos.y, pos.z, q.x);
+        p.S[1][i] = make_float4(q.y, q.z, q.w, vel.x);
+        p.S[2][i] = make_float4(vel.y, vel.z, wld.x, wld.y);
+        p.S[3][i] = make_float4(wld.z, tpos.x, tpos.y, tpos.z);
+        p.S[4][i] = make_float4(tq.z, tq.w, roll_old, roll_cont);
+        p.S[5][i] = make_float4(om[0], om[1], om[2], om[3]);
+        p.S[6][i] = make_float4(pe[0], pe[1], pe[2], cmd);
+        p.S[7][i] = make_float4(bu1, bec, bt, ep_ret);
+        p.progress[i] = progress;
+        p.qmeta[i] = (q_head << QM_HEAD_SHIFT) | (q_n << QM_N_SHIFT) | ((uint32_t)min(q_len, 2047) << QM_LEN_SHIFT) | (q_ovf << QM_OVF_SHIFT);
+        p.reset_buf[i] = done ? 1ll : 0ll;
+        p.time_outs[i] = tout ? 1 : 0;
+        p.rew[i] = rew;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 26; ++j) { fc[j] = 0.f; fn[j] = 0.f; }
+    }
+
+    // ---------------------------------------------------------------------- rollout statistics: warp shuffle -> smem -> 1 atomic / block / stat
+    {
+        float sv[7] = {st_rew, st_done, st_tout, st_epret, st_eplen, st_nonfin, st_ovf};
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            float v = sv[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s_stats[j], (double)v);
+        }
+    }
+    __syncthreads();   // frames + stats visible
+    if (tid < 7) {
+        const double v = s_stats[tid];
+        if (v != 0.0) atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * kStatStride + tid, v);
+    } else if (tid == 7) {
+        const int nv = min(kBlock, p.n - blockIdx.x * kBlock);
+        atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * kStatStride + 7, (double)nv);
+    }
+
+    // ---------------------------------------------------------------------- history shift + newest frame, coalesced 64-bit rows
+    // out[e][f][:] = in[e][f+1][:] for f < L-1, newest frame last (:392,:413); ping-pong buffers, so no in-place hazard.
+    const size_t blk_env0 = (size_t)blockIdx.x * kBlock;
+    {
+        const int L = p.len_states;
+        const int row2 = 13 * L, keep2 = 13 * (L - 1);
+        const float2* in2 = reinterpret_cast<const float2*>(p.states_in) + blk_env0 * row2;
+        float2* out2 = reinterpret_cast<float2*>(p.states_out) + blk_env0 * row2;
+        const int total = kBlock * row2;
+        int e = tid / row2, j2 = tid % row2;
+        const int de = kBlock / row2, dj = kBlock % row2;
+        for (int idx = tid; idx < total; idx += kBlock) {
+            float2 v;
+            if (j2 < keep2) v = __ldg(in2 + idx + 13);
+            else { const float* fr = s_clean + e * kFramePad + 2 * (j2 - keep2); v = make_float2(fr[0], fr[1]); }
+            out2[idx] = v;
+            e += de; j2 += dj;
+            if (j2 >= row2) { j2 -= row2; e += 1; }
+        }
+    }
+    {
+        const float* sf = obs_noise ? s_noisy : s_clean;
+        const int L = p.len_obs;
+        const int row2 = 13 * L, keep2 = 13 * (L - 1);
+        const float2* in2 = reinterpret_cast<const float2*>(p.obs_in) + blk_env0 * row2;
+        float2* out2 = reinterpret_cast<float2*>(p.obs_out) + blk_env0 * row2;
+        const int total = kBlock * row2;
+        int e = tid / row2, j2 = tid % row2;
+        const int de = kBlock / row2, dj = kBlock % row2;
+        for (int idx = tid; idx < total; idx += kBlock) {
+            float2 v;
+            if (j2 < keep2) v = __ldg(in2 + idx + 13);
+            else { const float* fr = sf + e * kFramePad + 2 * (j2 - keep2); v = make_float2(fr[0], fr[1]); }
+            out2[idx] = v;
+            e += de; j2 += dj;
+            if (j2 >= row2) { j2 -= row2; e += 1; }
+        }
+    }
+}
+
+template <int TASK>
+static void launch_task(const StepParams& p, cudaStream_t stream) {
+    const int grid = p.n_pad / kBlock;
+    fpv_step_kernel<TASK><<<grid, kBlock, 0, stream>>>(p);
+}
+
+static inline void launch_any(const StepParams& p, cudaStream_t stream) {
+    switch (p.task_mode) {
+        case TACO_TASK_POS: launch_task<TACO_TASK_POS>(p, stream); break;
+        case TACO_TASK_ROTATE: launch_task<TACO_TASK_ROTATE>(p, stream); break;
+        case TACO_TASK_FLIP: launch_task<TACO_TASK_FLIP>(p, stream); break;
+        default: launch_task<TACO_TASK_MIX>(p, stream); break;
+    }
+}
+
+}  // namespace taco

@@ -1,0 +1,53 @@
+// Kernel parameter block shared by the host library (taco_env.cu) and the two compiled
+// variants of the fused step kernel (fpv_step_fast.cu / fpv_step_strict.cu).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace taco {
+
+constexpr int kBlock = 128;       // envs (threads) per CTA
+constexpr int kQueueCap = 16;     // pending-action runs per env (in-domain max is 13)
+constexpr int kObs = 26;          // values per frame, fpv_asymmetry.py:107
+constexpr int kFramePad = 27;     // smem row stride (odd -> conflict-free column writes)
+constexpr int kStatSlots = 64;    // spread of the per-block stats atomics
+constexpr int kStatStride = 16;   // doubles per slot (128 B)
+constexpr int kNumStats = 8;
+
+// qmeta bit layout
+constexpr uint32_t QM_HEAD_SHIFT = 0, QM_N_SHIFT = 4, QM_LEN_SHIFT = 9, QM_OVF_SHIFT = 20;
+
+struct StepParams {
+    int n, n_pad;
+    long long env_offset;
+    long long mix_n1, mix_n2;      // global task-group boundaries (fpv_asymmetry.py:924-926)
+    int task_mode, len_obs, len_states, max_len, cfi, substeps, delay_time;
+    uint32_t flags, seed_lo, seed_hi, step_index;
+    float dt, h, half_h, inv_mass, difficulty, clip_actions;
+    // host-precomputed (double -> float) bounds of the difficulty-dependent uniform draws
+    float flip_xy_rng, flip_xy_lo, flip_lin_rng, flip_lin_lo, dr_rng, dr_lo, tau_rng, tau_lo, noise_rng, noise_lo;
+    float lag_gain_fixed;          // 0.001 / rotor_response_time (or 1.0 when rotor_response is off)
+    int has_dr;                    // per-env DR planes are live
+    // inputs / state / outputs (device)
+    const float4* actions;
+    float4* S[8];
+    int* progress;
+    uint32_t* qmeta;
+    float4* qact;                  // [kQueueCap][n_pad]
+    uint16_t* qend;                // [kQueueCap][n_pad]
+    float4* D[4];
+    long long* reset_buf;
+    uint8_t* time_outs;
+    float* rew;
+    const float* obs_in;
+    float* obs_out;
+    const float* states_in;
+    float* states_out;
+    double* stats;                 // [kStatSlots][kStatStride]
+    float4* dbg_delay;             // [cfi][n_pad] or null
+};
+
+void launch_fpv_step_fast(const StepParams& p, cudaStream_t stream);
+void launch_fpv_step_strict(const StepParams& p, cudaStream_t stream);
+
+}  // namespace taco

@@ -1,0 +1,432 @@
+// Host side of the C ABI (include/taco_b200.h): owns every device buffer of one env shard and
+// launches the fused step kernel.  No torch types, no exceptions across the boundary.
+//
+// Mirrors, for buffer ownership and layout, VecTask.allocate_buffers
+// (IsaacGymEnvs/isaacgymenvs/tasks/base/vec_task_asymmetry.py:231-254) and the state tensors of
+// FpvBase.__init__ (IsaacGymEnvs/isaacgymenvs/tasks/fpv_asymmetry.py:124-200).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/taco_b200.h"
+#include "philox.cuh"
+#include "step_params.h"
+
+namespace taco {
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define TACO_CUDA(expr)                                                                          \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return fail(TACO_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace taco
+
+struct TacoEnv {
+    TacoCfg cfg;
+    int device;
+    int n, n_pad;
+    taco::StepParams p;          // pointers + constants (step_index / ping-pong patched per step)
+    void* arena = nullptr;       // one cudaMalloc for everything
+    size_t arena_bytes = 0;
+    float* obs_ab[2] = {nullptr, nullptr};
+    float* states_ab[2] = {nullptr, nullptr};
+    int cur = 0;                 // index of the buffers holding the latest obs/states
+    float4* actions_stage = nullptr;   // device staging for taco_env_step_host
+    double* stats_out = nullptr;       // 8 doubles, device
+    float* export_stage = nullptr;     // n * TACO_STATE_WORDS floats, device
+    float4* dbg_delay = nullptr;
+    uint32_t step_index = 0;
+};
+
+namespace taco {
+
+static void refresh_derived(TacoEnv* e) {
+    // bounds of the difficulty-dependent uniform draws, evaluated in double like the python
+    // expressions they replace (fpv_asymmetry.py:856,870,405; thrust_dynamics.py:118,136), then cast to f32
+    StepParams& p = e->p;
+    const double d = (double)e->cfg.difficulty;
+    const double lim = 0.5 + 1.5 * d;
+    p.flip_xy_rng = (float)(lim - (-lim)); p.flip_xy_lo = (float)(-lim);
+    p.flip_lin_rng = (float)(3 * d - (-3 * d)); p.flip_lin_lo = (float)(-3 * d);
+    const double lo = 1 - 0.05 * d, hi = 1 + 0.05 * d;
+    p.dr_rng = (float)(hi - lo); p.dr_lo = (float)lo;
+    const double tau0 = (double)e->cfg.rotor_response_time;
+    p.tau_rng = (float)((tau0 + 0.001) - (tau0 - 0.001)); p.tau_lo = (float)(tau0 - 0.001);
+    const double nl = d * 0.05;
+    p.noise_rng = (float)(nl - (-nl)); p.noise_lo = (float)(-nl);
+    p.difficulty = e->cfg.difficulty;
+}
+
+// ---- small utility kernels -----------------------------------------------------------------
+__global__ void init_state_kernel(StepParams p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_pad) return;
+    // default pose (0,0,4), identity attitude, at rest (fpv_asymmetry.py:264-266); reset_buf = 1 (vec_task_asymmetry.py:246-247)
+    p.S[0][i] = make_float4(0.f, 0.f, 4.f, 0.f);
+    p.S[1][i] = make_float4(0.f, 0.f, 1.f, 0.f);
+    p.S[2][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    p.S[3][i] = make_float4(0.f, 0.f, 0.f, 4.f);
+    p.S[4][i] = make_float4(0.f, 1.f, 0.f, 0.f);
+    p.S[5][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    p.S[6][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    p.S[7][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    p.progress[i] = 0;
+    p.qmeta[i] = ((uint32_t)p.delay_time << QM_LEN_SHIFT);
+    p.reset_buf[i] = 1;
+    p.time_outs[i] = 0;
+    p.rew[i] = 0.f;
+    if (p.has_dr) {
+        p.D[0][i] = make_float4(0.0f, 12.9466f, 0.1872f, -5.1220f);
+        p.D[1][i] = make_float4(0.5906f, 1.13e-05f, 0.05f, -0.386f);
+        p.D[2][i] = make_float4(-0.53f, 0.009f, 0.f, 0.f);
+        p.D[3][i] = make_float4(p.lag_gain_fixed, p.lag_gain_fixed, p.lag_gain_fixed, p.lag_gain_fixed);
+    }
+}
+
+__global__ void fill_actions_kernel(float4* out, int n, long long env_offset, uint32_t step, uint32_t k0, uint32_t k1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 r = philox4x32_10((uint32_t)(env_offset + i), step, 0, STREAM_ACTIONS, k0, k1);
+    out[i] = make_float4(2.0f * u01(r.x) - 1.0f, 2.0f * u01(r.y) - 1.0f, 2.0f * u01(r.z) - 1.0f, 2.0f * u01(r.w) - 1.0f);
+}
+
+__global__ void reduce_stats_kernel(double* partial, double* out) {
+    // kStatSlots x kNumStats partial sums -> out[kNumStats]; clears the partials
+    const int j = threadIdx.x;
+    if (j >= kNumStats) return;
+    double acc = 0.0;
+    for (int s = 0; s < kStatSlots; ++s) { acc += partial[s * kStatStride + j]; partial[s * kStatStride + j] = 0.0; }
+    out[j] = acc;
+}
+
+// SoA planes <-> TACO_STATE_WORDS floats per env (layout documented in DESIGN.md "state export")
+__global__ void export_state_kernel(StepParams p, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    float* o = out + (size_t)i * TACO_STATE_WORDS;
+    const float4 s0 = p.S[0][i], s1 = p.S[1][i], s2 = p.S[2][i], s3 = p.S[3][i], s4 = p.S[4][i], s5 = p.S[5][i], s6 = p.S[6][i], s7 = p.S[7][i];
+    o[0] = s0.x; o[1] = s0.y; o[2] = s0.z;                    // pos
+    o[3] = s0.w; o[4] = s1.x; o[5] = s1.y; o[6] = s1.z;       // quat xyzw
+    o[7] = s1.w; o[8] = s2.x; o[9] = s2.y;                    // linvel (world)
+    o[10] = s2.z; o[11] = s2.w; o[12] = s3.x;                 // angvel (world)
+    o[13] = s3.y; o[14] = s3.z; o[15] = s3.w;                 // target pos
+    o[16] = 0.f; o[17] = 0.f; o[18] = s4.x; o[19] = s4.y;     // target quat
+    o[20] = s4.z; o[21] = s4.w;                               // roll_old, roll_continuous
+    o[22] = s5.x; o[23] = s5.y; o[24] = s5.z; o[25] = s5.w;   // rotor speed
+    o[26] = s6.x; o[27] = s6.y; o[28] = s6.z;                 // PID previous error
+    o[29] = s6.w;                                             // command state (rotate speed / flip_radian)
+    o[30] = s7.x; o[31] = s7.y; o[32] = s7.z;                 // battery u_1, E_c, time
+    o[33] = s7.w;                                             // running episode return
+    const uint32_t qm = p.qmeta[i];
+    o[34] = (float)p.progress[i];
+    o[35] = (float)((qm >> QM_LEN_SHIFT) & 2047u);            // actions_remained_length
+    o[36] = (float)((qm >> QM_N_SHIFT) & 31u);                // live runs in the action queue
+    o[37] = (float)((qm >> QM_OVF_SHIFT) & 1u);               // delay overflow flag
+    o[38] = (float)p.reset_buf[i];
+    o[39] = (float)((qm >> QM_HEAD_SHIFT) & 15u);
+    if (p.has_dr) {
+        const float4 d0 = p.D[0][i], d1 = p.D[1][i], d2 = p.D[2][i], d3 = p.D[3][i];
+        o[40] = d0.x; o[41] = d0.y; o[42] = d0.z; o[43] = d0.w; o[44] = d1.x;             // omega polynomial
+        o[45] = d1.y; o[46] = d1.z; o[47] = d1.w; o[48] = d2.x; o[49] = d2.y;             // aero k_f,k_tau,d_x,d_y,k_th
+        o[50] = d3.x; o[51] = d3.y; o[52] = d3.z; o[53] = d3.w;                           // lag gains
+    } else {
+        o[40] = 0.0f; o[41] = 12.9466f; o[42] = 0.1872f; o[43] = -5.1220f; o[44] = 0.5906f;
+        o[45] = 1.13e-05f; o[46] = 0.05f; o[47] = -0.386f; o[48] = -0.53f; o[49] = 0.009f;
+        o[50] = o[51] = o[52] = o[53] = p.lag_gain_fixed;
+    }
+    for (int j = 54; j < TACO_STATE_WORDS; ++j) o[j] = 0.f;
+}
+
+__global__ void import_state_kernel(StepParams p, const float* in) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const float* o = in + (size_t)i * TACO_STATE_WORDS;
+    p.S[0][i] = make_float4(o[0], o[1], o[2], o[3]);
+    p.S[1][i] = make_float4(o[4], o[5], o[6], o[7]);
+    p.S[2][i] = make_float4(o[8], o[9], o[10], o[11]);
+    p.S[3][i] = make_float4(o[12], o[13], o[14], o[15]);
+    p.S[4][i] = make_float4(o[18], o[19], o[20], o[21]);
+    p.S[5][i] = make_float4(o[22], o[23], o[24], o[25]);
+    p.S[6][i] = make_float4(o[26], o[27], o[28], o[29]);
+    p.S[7][i] = make_float4(o[30], o[31], o[32], o[33]);
+    p.progress[i] = (int)o[34];
+    p.reset_buf[i] = (long long)o[38];
+    // the pending-action queue itself is not imported: only its scalar meta (length / counts) is restored
+    p.qmeta[i] = (((uint32_t)o[39] & 15u) << QM_HEAD_SHIFT) | (((uint32_t)o[36] & 31u) << QM_N_SHIFT) |
+                 (((uint32_t)o[35] & 2047u) << QM_LEN_SHIFT) | (((uint32_t)o[37] & 1u) << QM_OVF_SHIFT);
+    if (p.has_dr) {
+        p.D[0][i] = make_float4(o[40], o[41], o[42], o[43]);
+        p.D[1][i] = make_float4(o[44], o[45], o[46], o[47]);
+        p.D[2][i] = make_float4(o[48], o[49], 0.f, 0.f);
+        p.D[3][i] = make_float4(o[50], o[51], o[52], o[53]);
+    }
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace taco
+
+using namespace taco;
+
+extern "C" {
+
+const char* taco_last_error(void) { return g_err.c_str(); }
+int taco_abi_version(void) { return TACO_ABI_VERSION; }
+
+int taco_env_create(const TacoCfg* cfg, int device, TacoEnv** out) {
+    if (!cfg || !out) return fail(TACO_E_INVALID, "taco_env_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != TACO_ABI_VERSION) return fail(TACO_E_INVALID, "taco_env_create: ABI version mismatch");
+    if (cfg->num_envs <= 0) return fail(TACO_E_INVALID, "num_envs must be positive");
+    if (cfg->task_mode < TACO_TASK_POS || cfg->task_mode > TACO_TASK_MIX) return fail(TACO_E_INVALID, "unknown task_mode");
+    if (cfg->len_obs < 1 || cfg->len_states < 1 || cfg->len_obs > 64 || cfg->len_states > 64)
+        return fail(TACO_E_INVALID, "len_obs / len_states must be in [1, 64]");
+    if (cfg->control_freq_inv < 1) return fail(TACO_E_INVALID, "control_freq_inv must be >= 1");
+    if (cfg->control_freq_inv != 10)
+        return fail(TACO_E_INVALID, "control_freq_inv must be 10: the delay buffer advances 10 slots per RL step (fpv_asymmetry.py:326,378)");
+    if (cfg->substeps < 1 || cfg->substeps > 16) return fail(TACO_E_INVALID, "substeps must be in [1, 16]");
+    if (cfg->delay_time < 0 || cfg->delay_time > 100) return fail(TACO_E_INVALID, "delay_time must be in [0, 100] ms (delay_time_max is 100, fpv_asymmetry.py:329)");
+    if (cfg->max_episode_length < 2 || (long long)cfg->max_episode_length * 10 + 200 >= 65536)
+        return fail(TACO_E_INVALID, "max_episode_length must be in [2, 6500]");
+    if (!(cfg->dt > 0.f) || !(cfg->rotor_response_time > 0.f)) return fail(TACO_E_INVALID, "dt and rotor_response_time must be positive");
+    if (cfg->env_offset < 0 || cfg->num_envs_global < cfg->env_offset + cfg->num_envs || cfg->num_envs_global > 0xFFFFFFFFll)
+        return fail(TACO_E_INVALID, "env_offset / num_envs_global inconsistent");
+    int ndev = 0;
+    TACO_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(TACO_E_INVALID, "no such CUDA device");
+    DeviceGuard guard(device);
+
+    TacoEnv* e = new (std::nothrow) TacoEnv();
+    if (!e) return fail(TACO_E_NOMEM, "host allocation failed");
+    e->cfg = *cfg;
+    e->device = device;
+    e->n = cfg->num_envs;
+    e->n_pad = (int)align_up((size_t)cfg->num_envs, kBlock);
+    const size_t np = (size_t)e->n_pad;
+    StepParams& p = e->p;
+    memset(&p, 0, sizeof(p));
+    p.n = e->n; p.n_pad = e->n_pad;
+    p.env_offset = cfg->env_offset;
+    // python: int(num_envs / 3 * 1), int(num_envs / 3 * 2) in double (fpv_asymmetry.py:924-925)
+    p.mix_n1 = (long long)((double)cfg->num_envs_global / 3 * 1);
+    p.mix_n2 = (long long)((double)cfg->num_envs_global / 3 * 2);
+    p.task_mode = cfg->task_mode; p.len_obs = cfg->len_obs; p.len_states = cfg->len_states;
+    p.max_len = cfg->max_episode_length; p.cfi = cfg->control_freq_inv; p.substeps = cfg->substeps; p.delay_time = cfg->delay_time;
+    p.flags = cfg->flags;
+    p.seed_lo = (uint32_t)(cfg->seed & 0xFFFFFFFFull); p.seed_hi = (uint32_t)(cfg->seed >> 32);
+    p.dt = cfg->dt;
+    p.h = (float)((double)cfg->dt / cfg->substeps);
+    p.half_h = (float)(0.5 * ((double)cfg->dt / cfg->substeps));
+    p.inv_mass = (float)(1.0 / (0.46 + 8 * 1e-7));            // fpv_without_duct.xml:6,11-13
+    p.clip_actions = cfg->clip_actions;
+    p.lag_gain_fixed = (cfg->flags & TACO_F_ROTOR_RESPONSE) ? 0.001f / cfg->rotor_response_time : 0.001f / 0.001f;
+    p.has_dr = (cfg->flags & (TACO_F_RANDOM_ROTORDYNAMIC_COE | TACO_F_RANDOM_ROTOR_RESPONSE | TACO_F_RANDOM_AERODYNAMIC_COE)) ? 1 : 0;
+    refresh_derived(e);
+
+    // ---- one arena, every plane 512-byte aligned
+    const size_t A = 512;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, A); return o; };
+    size_t oS[8], oD[4];
+    for (int k = 0; k < 8; ++k) oS[k] = take(np * sizeof(float4));
+    for (int k = 0; k < 4; ++k) oD[k] = p.has_dr ? take(np * sizeof(float4)) : 0;
+    const size_t oProg = take(np * sizeof(int)), oMeta = take(np * sizeof(uint32_t));
+    const size_t oQact = take((size_t)kQueueCap * np * sizeof(float4)), oQend = take((size_t)kQueueCap * np * sizeof(uint16_t));
+    const size_t oReset = take(np * sizeof(long long)), oTout = take(np), oRew = take(np * sizeof(float));
+    const size_t obs_bytes = np * cfg->len_obs * kObs * sizeof(float), st_bytes = np * cfg->len_states * kObs * sizeof(float);
+    const size_t oObs0 = take(obs_bytes), oObs1 = take(obs_bytes), oSt0 = take(st_bytes), oSt1 = take(st_bytes);
+    const size_t oStats = take((size_t)kStatSlots * kStatStride * sizeof(double)), oStatsOut = take(kNumStats * sizeof(double));
+    const size_t oStage = take(np * sizeof(float4));
+    const size_t oDbg = (cfg->flags & TACO_F_DEBUG_DELAY) ? take((size_t)cfg->control_freq_inv * np * sizeof(float4)) : 0;
+    e->arena_bytes = off;
+    cudaError_t ce = cudaMalloc(&e->arena, e->arena_bytes);
+    if (ce != cudaSuccess) { delete e; return fail(TACO_E_NOMEM, std::string("cudaMalloc of env arena failed: ") + cudaGetErrorString(ce)); }
+    char* base = (char*)e->arena;
+    ce = cudaMemset(base, 0, e->arena_bytes);
+    if (ce != cudaSuccess) { cudaFree(e->arena); delete e; return fail(TACO_E_CUDA, cudaGetErrorString(ce)); }
+    for (int k = 0; k < 8; ++k) p.S[k] = (float4*)(base + oS[k]);
+    for (int k = 0; k < 4; ++k) p.D[k] = p.has_dr ? (float4*)(base + oD[k]) : nullptr;
+    p.progress = (int*)(base + oProg); p.qmeta = (uint32_t*)(base + oMeta);
+    p.qact = (float4*)(base + oQact); p.qend = (uint16_t*)(base + oQend);
+    p.reset_buf = (long long*)(base + oReset); p.time_outs = (uint8_t*)(base + oTout); p.rew = (float*)(base + oRew);
+    e->obs_ab[0] = (float*)(base + oObs0); e->obs_ab[1] = (float*)(base + oObs1);
+    e->states_ab[0] = (float*)(base + oSt0); e->states_ab[1] = (float*)(base + oSt1);
+    p.stats = (double*)(base + oStats); e->stats_out = (double*)(base + oStatsOut);
+    e->actions_stage = (float4*)(base + oStage);
+    e->dbg_delay = (cfg->flags & TACO_F_DEBUG_DELAY) ? (float4*)(base + oDbg) : nullptr;
+    p.dbg_delay = e->dbg_delay;
+    e->cur = 0;
+    e->step_index = 0;
+    init_state_kernel<<<(e->n_pad + 255) / 256, 256>>>(p);
+    ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) { cudaFree(e->arena); delete e; return fail(TACO_E_CUDA, std::string("init kernel: ") + cudaGetErrorString(ce)); }
+    *out = e;
+    return TACO_OK;
+}
+
+int taco_env_destroy(TacoEnv* env) {
+    if (!env) return TACO_OK;
+    DeviceGuard guard(env->device);
+    if (env->export_stage) cudaFree(env->export_stage);
+    if (env->arena) cudaFree(env->arena);
+    delete env;
+    return TACO_OK;
+}
+
+int taco_env_buffers(TacoEnv* env, TacoBuffers* out) {
+    if (!env || !out) return fail(TACO_E_INVALID, "taco_env_buffers: null argument");
+    out->obs = env->obs_ab[env->cur];
+    out->states = env->states_ab[env->cur];
+    out->rew = env->p.rew;
+    out->reset = (int64_t*)env->p.reset_buf;
+    out->time_outs = env->p.time_outs;
+    out->progress = env->p.progress;
+    for (int k = 0; k < 2; ++k) { out->obs_ab[k] = env->obs_ab[k]; out->states_ab[k] = env->states_ab[k]; }
+    out->num_envs = env->n; out->len_obs = env->cfg.len_obs; out->len_states = env->cfg.len_states; out->num_obs = kObs;
+    return TACO_OK;
+}
+
+int taco_env_step(TacoEnv* env, const float* actions_dev, void* stream) {
+    if (!env || !actions_dev) return fail(TACO_E_INVALID, "taco_env_step: null argument");
+    if (((uintptr_t)actions_dev & 15u) != 0) return fail(TACO_E_INVALID, "actions must be 16-byte aligned (contiguous (N,4) float32)");
+    DeviceGuard guard(env->device);
+    StepParams& p = env->p;
+    const int nxt = env->cur ^ 1;
+    p.actions = (const float4*)actions_dev;
+    p.obs_in = env->obs_ab[env->cur]; p.obs_out = env->obs_ab[nxt];
+    p.states_in = env->states_ab[env->cur]; p.states_out = env->states_ab[nxt];
+    p.step_index = env->step_index;
+    if (env->cfg.flags & TACO_F_STRICT_FP) launch_fpv_step_strict(p, (cudaStream_t)stream);
+    else launch_fpv_step_fast(p, (cudaStream_t)stream);
+    TACO_CUDA(cudaGetLastError());
+    env->cur = nxt;
+    env->step_index += 1;
+    return TACO_OK;
+}
+
+int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host, int64_t* reset_host, uint8_t* time_outs_host,
+                       void* stream) {
+    if (!env || !actions_host) return fail(TACO_E_INVALID, "taco_env_step_host: null argument");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)env->n;
+    TACO_CUDA(cudaMemcpyAsync(env->actions_stage, actions_host, n * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = taco_env_step(env, (const float*)env->actions_stage, stream);
+    if (rc != TACO_OK) return rc;
+    if (rew_host) TACO_CUDA(cudaMemcpyAsync(rew_host, env->p.rew, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (reset_host) TACO_CUDA(cudaMemcpyAsync(reset_host, env->p.reset_buf, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    if (time_outs_host) TACO_CUDA(cudaMemcpyAsync(time_outs_host, env->p.time_outs, n, cudaMemcpyDeviceToHost, s));
+    TACO_CUDA(cudaStreamSynchronize(s));
+    return TACO_OK;
+}
+
+int taco_env_reset_all(TacoEnv* env, void* stream) {
+    if (!env) return fail(TACO_E_INVALID, "taco_env_reset_all: null argument");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t np = (size_t)env->n_pad;
+    for (int k = 0; k < 2; ++k) {
+        TACO_CUDA(cudaMemsetAsync(env->obs_ab[k], 0, np * env->cfg.len_obs * kObs * sizeof(float), s));
+        TACO_CUDA(cudaMemsetAsync(env->states_ab[k], 0, np * env->cfg.len_states * kObs * sizeof(float), s));
+    }
+    TACO_CUDA(cudaMemsetAsync(env->p.stats, 0, (size_t)kStatSlots * kStatStride * sizeof(double), s));
+    init_state_kernel<<<(env->n_pad + 255) / 256, 256, 0, s>>>(env->p);
+    TACO_CUDA(cudaGetLastError());
+    env->step_index = 0;
+    return TACO_OK;
+}
+
+int taco_env_set_difficulty(TacoEnv* env, float difficulty) {
+    if (!env) return fail(TACO_E_INVALID, "taco_env_set_difficulty: null argument");
+    env->cfg.difficulty = difficulty;
+    refresh_derived(env);
+    return TACO_OK;
+}
+
+int taco_env_set_seed(TacoEnv* env, uint64_t seed) {
+    if (!env) return fail(TACO_E_INVALID, "taco_env_set_seed: null argument");
+    env->cfg.seed = seed;
+    env->p.seed_lo = (uint32_t)(seed & 0xFFFFFFFFull); env->p.seed_hi = (uint32_t)(seed >> 32);
+    return TACO_OK;
+}
+
+int taco_env_stats(TacoEnv* env, double* out_dev, double* out_host, void* stream) {
+    if (!env) return fail(TACO_E_INVALID, "taco_env_stats: null argument");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    double* dst = out_dev ? out_dev : env->stats_out;
+    reduce_stats_kernel<<<1, 32, 0, s>>>(env->p.stats, dst);
+    TACO_CUDA(cudaGetLastError());
+    if (out_host) {
+        TACO_CUDA(cudaMemcpyAsync(out_host, dst, kNumStats * sizeof(double), cudaMemcpyDeviceToHost, s));
+        TACO_CUDA(cudaStreamSynchronize(s));
+    }
+    return TACO_OK;
+}
+
+int taco_env_fill_random_actions(TacoEnv* env, float* actions_dev, uint32_t step_index, void* stream) {
+    if (!env || !actions_dev) return fail(TACO_E_INVALID, "taco_env_fill_random_actions: null argument");
+    DeviceGuard guard(env->device);
+    fill_actions_kernel<<<(env->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float4*)actions_dev, env->n, env->p.env_offset, step_index,
+                                                                               env->p.seed_lo, env->p.seed_hi);
+    TACO_CUDA(cudaGetLastError());
+    return TACO_OK;
+}
+
+int taco_env_export_state(TacoEnv* env, float* out_host) {
+    if (!env || !out_host) return fail(TACO_E_INVALID, "taco_env_export_state: null argument");
+    DeviceGuard guard(env->device);
+    const size_t bytes = (size_t)env->n * TACO_STATE_WORDS * sizeof(float);
+    if (!env->export_stage) TACO_CUDA(cudaMalloc(&env->export_stage, bytes));
+    TACO_CUDA(cudaDeviceSynchronize());
+    export_state_kernel<<<(env->n + 255) / 256, 256>>>(env->p, env->export_stage);
+    TACO_CUDA(cudaGetLastError());
+    TACO_CUDA(cudaMemcpy(out_host, env->export_stage, bytes, cudaMemcpyDeviceToHost));
+    return TACO_OK;
+}
+
+int taco_env_import_state(TacoEnv* env, const float* in_host) {
+    if (!env || !in_host) return fail(TACO_E_INVALID, "taco_env_import_state: null argument");
+    DeviceGuard guard(env->device);
+    const size_t bytes = (size_t)env->n * TACO_STATE_WORDS * sizeof(float);
+    if (!env->export_stage) TACO_CUDA(cudaMalloc(&env->export_stage, bytes));
+    TACO_CUDA(cudaDeviceSynchronize());
+    TACO_CUDA(cudaMemcpy(env->export_stage, in_host, bytes, cudaMemcpyHostToDevice));
+    import_state_kernel<<<(env->n + 255) / 256, 256>>>(env->p, env->export_stage);
+    TACO_CUDA(cudaGetLastError());
+    TACO_CUDA(cudaDeviceSynchronize());
+    return TACO_OK;
+}
+
+int taco_env_debug_delay(TacoEnv* env, float* out_host) {
+    if (!env || !out_host) return fail(TACO_E_INVALID, "taco_env_debug_delay: null argument");
+    if (!env->dbg_delay) return fail(TACO_E_INVALID, "env was not created with TACO_F_DEBUG_DELAY");
+    DeviceGuard guard(env->device);
+    TACO_CUDA(cudaDeviceSynchronize());
+    // device layout [cfi][n_pad] float4 -> host (n, cfi, 4)
+    const int cfi = env->cfg.control_freq_inv;
+    std::vector<float4> tmp((size_t)cfi * env->n_pad);
+    TACO_CUDA(cudaMemcpy(tmp.data(), env->dbg_delay, tmp.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < env->n; ++i)
+        for (int k = 0; k < cfi; ++k) {
+            const float4 v = tmp[(size_t)k * env->n_pad + i];
+            float* o = out_host + ((size_t)i * cfi + k) * 4;
+            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        }
+    return TACO_OK;
+}
+
+}  // extern "C"
