@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--envs-per-gpu", type=int, default=2 * 1024 * 1024)
     ap.add_argument("--task", default=TASK, choices=["pos", "rotate", "flip", "mix"])
     ap.add_argument("--dr", action="store_true", help="per-env domain randomisation (BASELINE config 5)")
-    ap.add_argument("--strict-fp", action="store_true", help="time the -fmad=false kernel build")
+    ap.add_argument("--fast-fp", action="store_true", help="time the FMA-contracted kernel build instead of the default strict (-fmad=false) one")
     ap.add_argument("--cpu-envs", type=int, default=4096)
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -204,7 +204,7 @@ def main():
     n = args.envs_per_gpu
     cfg = taco_b200.make_cfg(args.task, n, domain_randomization=args.dr)
     dev = f"cuda:{local_rank}"
-    env = taco_b200.FpvVecTask(cfg, dev, dev, -1, True, env_offset=rank * n, num_envs_global=world * n, seed=SEED, strict_fp=args.strict_fp)
+    env = taco_b200.FpvVecTask(cfg, dev, dev, -1, True, env_offset=rank * n, num_envs_global=world * n, seed=SEED, strict_fp=not args.fast_fp)
     n_act = 4
     actions = [env.random_actions(t) for t in range(n_act)]     # synthetic U(-1,1), resident in HBM before timing
     sampler = ClockSampler(local_rank)
@@ -251,7 +251,7 @@ def main():
     small = None
     if not args.no_small and world == 1:
         cfg_s = taco_b200.make_cfg(args.task, 4096)
-        env_s = taco_b200.FpvVecTask(cfg_s, dev, dev, -1, True, seed=SEED, strict_fp=args.strict_fp)
+        env_s = taco_b200.FpvVecTask(cfg_s, dev, dev, -1, True, seed=SEED, strict_fp=not args.fast_fp)
         acts_s = [env_s.random_actions(t) for t in range(n_act)]
         for t in range(10):
             env_s.step(acts_s[t % n_act])
@@ -284,7 +284,7 @@ def main():
                                    f"{'per-env DR on' if args.dr else 'no per-env DR'}, U(-1,1) Philox actions",
                        "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-sharded x{world}",
                        "l2": "inputs larger than L2 (working set ~%.1f GB/GPU)" % (n * 1900 / 1e9),
-                       "fp_mode": "strict (-fmad=false)" if args.strict_fp else "fast (FMA contraction)"},
+                       "fp_mode": "fast (FMA contraction)" if args.fast_fp else "strict (-fmad=false, the parity-tested build)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "fpv_step_kernel", "algorithmic_bytes_per_env_step": algo, "peak_source": peak_src,
                          "kernel_ms": kernel_ms},

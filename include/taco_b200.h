@@ -151,6 +151,10 @@ int taco_actor_load(TacoActor* actor, const float* const* weights_host, const fl
 int taco_actor_forward(TacoActor* actor, const float* obs_dev, float* mean_dev, int32_t n, int32_t use_tensor_cores,
                        void* stream);
 
+/* -- self-test: exhaustive comparison (all float bit patterns with |x| in [2^-60, 2^60]) of the kernel's 3-instruction
+ * division-by-constant against IEEE division, for every divisor the step kernel uses; writes the mismatch count. */
+int taco_selftest_divc(int device, float dt, uint64_t* n_mismatch);
+
 const char* taco_last_error(void);
 int taco_abi_version(void);
 

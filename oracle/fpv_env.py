@@ -27,7 +27,7 @@ from . import philox as px
 from . import dynamics as dyn
 from . import rewards as rw
 from . import rigid_body as rb
-from .leaf_math import (qmul, qconj, qrot, euler_xyz, quat_from_euler, rotmat9, rand_range)
+from .leaf_math import (qmul, qconj, qrot, euler_xyz, quat_from_euler, rotmat9, rand_range, sincos_draw)
 
 TASK_POS, TASK_ROTATE, TASK_FLIP, TASK_MIX = 0, 1, 2, 3
 TASK_BY_NAME = {"pos": TASK_POS, "rotate": TASK_ROTATE, "flip": TASK_FLIP, "mix": TASK_MIX}
@@ -169,9 +169,9 @@ class RefFpvEnv:
             if self.random_copter_quat:
                 # rand_quat(n, pitch_lim, roll_lim, yaw_lim): the "pitch" draw lands in the ROLL slot (FPV:698-704)
                 full = quat_from_euler(rand_range(-math.pi, math.pi, U(1, 0)), rand_range(-math.pi, math.pi, U(1, 1)),
-                                       rand_range(-math.pi, math.pi, U(1, 2)))
+                                       rand_range(-math.pi, math.pi, U(1, 2)), sincos_draw)
                 zero = torch.zeros(N)
-                roll_only = quat_from_euler(rand_range(-math.pi, math.pi, U(1, 0)), zero, zero)      # FPV:864,1038
+                roll_only = quat_from_euler(rand_range(-math.pi, math.pi, U(1, 0)), zero, zero, sincos_draw)      # FPV:864,1038
                 new_q = torch.where(is_flip.unsqueeze(1), roll_only, full)
             else:
                 new_q = torch.tensor([0.0, 0.0, 0.0, 1.0]).repeat(N, 1)
@@ -250,7 +250,7 @@ class RefFpvEnv:
             self.tpos = torch.where(Rc, torch.cat((txy, tz.unsqueeze(1)), dim=1), self.tpos)
             yaw = rand_range(-math.pi, math.pi, U(3, 3)) if self.random_target_yaw else torch.zeros(N)
             zero = torch.zeros(N)
-            self.tquat = torch.where(Rc, quat_from_euler(zero, zero, yaw), self.tquat)
+            self.tquat = torch.where(Rc, quat_from_euler(zero, zero, yaw, sincos_draw), self.tquat)
         # ---- command (FPV:758-759, :814-821, :886-917, :1058-1112)
         if bool(cmd_mask.any()):
             cblk = self._block(0, px.STREAM_COMMAND)
@@ -409,7 +409,7 @@ class RefFpvEnv:
                 noisy[:, i] = noisy[:, i] + d * (nrm[i] * sig_p)
             lim = d * 0.05
             nq = quat_from_euler(rand_range(-lim, lim, f32(px.u01(ub[:, 0]))), rand_range(-lim, lim, f32(px.u01(ub[:, 1]))),
-                                 rand_range(-lim, lim, f32(px.u01(ub[:, 2]))))
+                                 rand_range(-lim, lim, f32(px.u01(ub[:, 2]))), sincos_draw)
             noisy[:, 3:12] = rotmat9(qmul(self.rel_quat_body, nq))
             for i in range(3):
                 noisy[:, 12 + i] = noisy[:, 12 + i] + d * (nrm[3 + i] * sig_v)

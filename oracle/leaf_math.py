@@ -77,11 +77,37 @@ def roll_of(q):
     return torch.atan2(2.0 * (w * x + y * z), w * w - x * x - y * y + z * z)
 
 
-def quat_from_euler(roll, pitch, yaw):
-    """TU:199-213 (quat_from_euler_xyz)."""
-    cy, sy = torch.cos(yaw * 0.5), torch.sin(yaw * 0.5)
-    cr, sr = torch.cos(roll * 0.5), torch.sin(roll * 0.5)
-    cp, sp = torch.cos(pitch * 0.5), torch.sin(pitch * 0.5)
+_SIN_C = (-1.0 / 6, 1.0 / 120, -1.0 / 5040, 1.0 / 362880, -1.0 / 39916800, 1.0 / 6227020800)
+_COS_C = (-1.0 / 2, 1.0 / 24, -1.0 / 720, 1.0 / 40320, -1.0 / 3628800, 1.0 / 479001600, -1.0 / 87178291200)
+
+
+def sincos_draw(x):
+    """sin(x), cos(x) for |x| <= pi/2 by Horner evaluation of the degree-13 / degree-14 Taylor
+    polynomials (truncation < 7e-10 relative).  Used ONLY for the random attitude draws of a reset
+    (copter attitude, target yaw, observation-noise quaternion), which are our own Philox-driven
+    draws: built from + and * alone, the -fmad=false CUDA kernel reproduces it bit for bit, so
+    oracle and kernel start every episode from identical float32 quaternions (libm sin/cos differ
+    by 1 ulp between vendors, which decorrelates the subsequent float32 rounding)."""
+    z = x * x
+    s = torch.full_like(x, _SIN_C[-1])
+    for c in reversed(_SIN_C[:-1]):
+        s = c + z * s
+    s = x * (1.0 + z * s)
+    c_ = torch.full_like(x, _COS_C[-1])
+    for c in reversed(_COS_C[:-1]):
+        c_ = c + z * c_
+    c_ = 1.0 + z * c_
+    return s, c_
+
+
+def quat_from_euler(roll, pitch, yaw, sincos=None):
+    """TU:199-213 (quat_from_euler_xyz).  ``sincos`` replaces torch.sin/torch.cos of the half
+    angles (see sincos_draw); default = torch, as in the reference."""
+    if sincos is None:
+        sincos = lambda a: (torch.sin(a), torch.cos(a))
+    sy, cy = sincos(yaw * 0.5)
+    sr, cr = sincos(roll * 0.5)
+    sp, cp = sincos(pitch * 0.5)
     qw = cy * cr * cp + sy * sr * sp
     qx = cy * sr * cp - sy * cr * sp
     qy = cy * cr * sp + sy * sr * cp

@@ -18,16 +18,21 @@ Model facts taken from the reference:
   * root state = pos, quat xyzw, linear velocity (world), angular velocity (world)
     (docs/programming/tensors: actor root state layout).
 
-Step (semi-implicit Euler, closed-form quaternion exponential):
+Step (semi-implicit Euler; quaternion exponential by its 4th-order series -- with
+theta = |w_b| h/2 <= 0.02 rad for |w_b| <= 80 rad/s the truncation error theta^6/720 is < 1e-13,
+far below float32 resolution, and the form needs only + and *, so a -fmad=false CUDA build
+reproduces the torch float32 result bit for bit; no sqrt / sin / cos / division):
+    exp(h/2 w_b) ~ ( w_b * (h/2)(1 - t/6 + t^2/120),  1 - t/2 + t^2/24 ),  t = theta^2
     F_w = R(q) F_b ; tau_w = R(q) tau_b ; w_b = R(q)^T w        (once per simulate call)
     per sub-step s:
         v    += h * (F_w / m + g)
         tau_s = tau_b if s == 0 else R(q)^T tau_w
         w_b  += h * I^-1 (tau_s - w_b x (I w_b))
         p    += h * v
-        q     = normalize(q * exp(h/2 * w_b))   (body-frame increment, right-multiplied;
+        q     = renorm(q * exp(h/2 * w_b))      (body-frame increment, right-multiplied;
                                                  it rotates about w_b, so w_b is unchanged)
     w = R(q) w_b                                                  (once, at the end)
+    renorm(q) = q * (1.5 - 0.5 |q|^2)    (one Newton step of 1/sqrt: no sqrt, no division)
 """
 import torch
 
@@ -66,13 +71,16 @@ def integrate(pos, quat, linvel, angvel, force_b, torque_b, dt, substeps):
         tau_b = torque_b if s == 0 else qrot(qconj(quat), torque_w)
         w_b = w_b + h * ((tau_b - cross3(w_b, inertia * w_b)) * inv_inertia)
         pos = pos + h * linvel
-        wn = torch.sqrt((w_b[:, 0:1] * w_b[:, 0:1] + w_b[:, 1:2] * w_b[:, 1:2]) + w_b[:, 2:3] * w_b[:, 2:3])
-        half = wn * (0.5 * h)
-        k = torch.where(wn > 0, torch.sin(half) / wn, torch.full_like(wn, 0.5 * h))
-        dq = torch.cat((w_b * k, torch.cos(half)), dim=1)
+        hh = 0.5 * h
+        w2 = (w_b[:, 0:1] * w_b[:, 0:1] + w_b[:, 1:2] * w_b[:, 1:2]) + w_b[:, 2:3] * w_b[:, 2:3]
+        t = w2 * (hh * hh)                                   # theta^2
+        k = hh * (1.0 + t * (-1.0 / 6.0 + t * (1.0 / 120.0)))  # sin(theta)/|w|
+        c = 1.0 + t * (-0.5 + t * (1.0 / 24.0))                # cos(theta)
+        dq = torch.cat((w_b * k, c), dim=1)
         quat = qmul(quat, dq)
-        qn = torch.sqrt(((quat[:, 0:1] * quat[:, 0:1] + quat[:, 1:2] * quat[:, 1:2]) + quat[:, 2:3] * quat[:, 2:3])
-                        + quat[:, 3:4] * quat[:, 3:4])
-        quat = quat / qn
+        # renormalise with one Newton step of 1/sqrt about 1: |q|^2 = 1 + e with |e| ~ 1e-7 after a
+        # float32 product of unit quaternions, so q * (1.5 - 0.5 |q|^2) is unit to O(e^2) ~ 1e-14
+        n2 = ((quat[:, 0:1] * quat[:, 0:1] + quat[:, 1:2] * quat[:, 1:2]) + quat[:, 2:3] * quat[:, 2:3]) + quat[:, 3:4] * quat[:, 3:4]
+        quat = quat * (1.5 - 0.5 * n2)
     angvel = qrot(quat, w_b)
     return pos, quat, linvel, angvel

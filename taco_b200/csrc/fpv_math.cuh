@@ -57,12 +57,34 @@ __device__ __forceinline__ float roll_of(Q4 q) {
     return atan2f(sinr, cosr);
 }
 
-// TU:199-213 quat_from_euler_xyz
+// sin/cos for |x| <= pi/2 by Horner evaluation of the degree-13/14 Taylor polynomials (oracle/leaf_math.py
+// sincos_draw): + and * only, so the -fmad=false build matches the torch oracle bit for bit.  Used for the
+// random attitude draws of a reset, which are our own Philox-driven draws.
+__device__ __forceinline__ void sincos_draw(float x, float* s, float* c) {
+    const float z = x * x;
+    float a = (float)(1.0 / 6227020800);
+    a = (float)(-1.0 / 39916800) + z * a;
+    a = (float)(1.0 / 362880) + z * a;
+    a = (float)(-1.0 / 5040) + z * a;
+    a = (float)(1.0 / 120) + z * a;
+    a = (float)(-1.0 / 6) + z * a;
+    *s = x * (1.0f + z * a);
+    float b = (float)(-1.0 / 87178291200);
+    b = (float)(1.0 / 479001600) + z * b;
+    b = (float)(-1.0 / 3628800) + z * b;
+    b = (float)(1.0 / 40320) + z * b;
+    b = (float)(-1.0 / 720) + z * b;
+    b = (float)(1.0 / 24) + z * b;
+    b = (float)(-1.0 / 2) + z * b;
+    *c = 1.0f + z * b;
+}
+
+// TU:199-213 quat_from_euler_xyz with sincos_draw for the half angles
 __device__ __forceinline__ Q4 quat_from_euler(float roll, float pitch, float yaw) {
     float sy, cy, sr, cr, sp, cp;
-    sincosf(yaw * 0.5f, &sy, &cy);
-    sincosf(roll * 0.5f, &sr, &cr);
-    sincosf(pitch * 0.5f, &sp, &cp);
+    sincos_draw(yaw * 0.5f, &sy, &cy);
+    sincos_draw(roll * 0.5f, &sr, &cr);
+    sincos_draw(pitch * 0.5f, &sp, &cp);
     Q4 q;
     q.w = cy * cr * cp + sy * sr * sp;
     q.x = cy * sr * cp - sy * cr * sp;
@@ -84,6 +106,22 @@ __device__ __forceinline__ void rotmat9(Q4 q, float* m) {
     m[6] = two_s * (i * k - j * r);
     m[7] = two_s * (j * k + i * r);
     m[8] = 1.0f - two_s * (i * i + j * j);
+}
+
+// torch.norm(p=2) on CPU accumulates acc = fma(x_i, x_i, acc) in order and takes one sqrt (verified against
+// torch 2.11 in tests/test_oracle_semantics.py); the reference's norms must be formed the same way in BOTH builds.
+__device__ __forceinline__ float norm2(float x, float y) { return sqrtf(__fmaf_rn(y, y, x * x)); }
+__device__ __forceinline__ float norm3(float x, float y, float z) { return sqrtf(__fmaf_rn(z, z, __fmaf_rn(y, y, x * x))); }
+
+// x / C for a compile-time constant C, correctly rounded (== IEEE x / C) with three FMA-class instructions instead of
+// the ~12-instruction IEEE division sequence: q = RN(x*rc), r = x - C*q (exact, one FMA), q' = RN(q + r*rc), rc = RN(1/C)
+// (Markstein 1990; valid while x/C neither overflows nor underflows and C's significand is not all ones -- checked
+// exhaustively on the GPU by taco_selftest_divc / tests/test_kernel_selftest_gpu.py).  Non-finite x gives NaN.
+#define TACO_DIVC(x, C) ::taco::divc_impl((x), (C), 1.0f / (C))
+__device__ __forceinline__ float divc_impl(float x, float c, float rc) {
+    const float q = x * rc;
+    const float r = __fmaf_rn(-c, q, x);
+    return __fmaf_rn(r, rc, q);
 }
 
 // (hi-lo)*u + lo, TU:216-219 torch_rand_float; rng/lo are the float32 casts of the python doubles

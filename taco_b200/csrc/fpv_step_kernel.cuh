@@ -35,7 +35,46 @@ __device__ constexpr float kTurns[8] = {-3.f, -2.f, -1.f, 0.f, 0.f, 1.f, 2.f, 3.
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
-template <int TASK>
+// One CTA writes its 128 rows of an (N, L, 26) history buffer: frames 1..L-1 of the previous buffer shifted down by one
+// (coalesced 64-bit copies: a row is 13*L float2, the shift is 13 float2) and the newest frame from shared memory.
+// LC = compile-time L (fast paths for the README shapes L=5 / L=1), 0 = runtime L.
+template <int LC>
+__device__ __forceinline__ void write_rows(const float* __restrict__ in, float* __restrict__ out, const float* frames,
+                                           int L_rt, size_t blk_env0, int tid) {
+    const int L = LC ? LC : L_rt;
+    const int row2 = 13 * L, keep2 = 13 * (L - 1);
+    const float2* in2 = reinterpret_cast<const float2*>(in) + blk_env0 * row2;
+    float2* out2 = reinterpret_cast<float2*>(out) + blk_env0 * row2;
+    if (keep2 > 0) {
+        const int total = kBlock * keep2;                       // multiple of kBlock
+        constexpr int U = 13;                                   // loads in flight per thread
+        for (int k0 = tid; k0 < total; k0 += kBlock * U) {
+            float2 v[U];
+            int dst[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = k0 + u * kBlock;
+                const int e = k / keep2, j = k - e * keep2;
+                dst[u] = e * row2 + j;
+                v[u] = (k < total) ? __ldg(in2 + dst[u] + 13) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (k0 + u * kBlock < total) out2[dst[u]] = v[u];
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 13; ++u) {                               // 128 rows x 13 float2 of the newest frame
+        const int k = tid + u * kBlock;
+        const int e = k / 13, j = k - e * 13;
+        const float* fr = frames + e * kFramePad + 2 * j;
+        out2[e * row2 + keep2 + j] = make_float2(fr[0], fr[1]);
+    }
+}
+
+// TASK: task_mode (mix = per-env task from the global env id).  DR: per-env randomised model parameters live in the
+// D planes; when false the rotor polynomial / aero coefficients fold into instruction immediates.
+template <int TASK, bool DR>
 __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p) {
     __shared__ float s_clean[kBlock * kFramePad];
     __shared__ float s_noisy[kBlock * kFramePad];
@@ -62,7 +101,7 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
         uint32_t qm = p.qmeta[i];
         const bool R = p.reset_buf[i] != 0;                    // latched for the whole RL step (fpv_asymmetry.py:318)
         float poly[5], aero[5], lag[4];
-        if (p.has_dr) {
+        if (DR) {
             const float4 d0 = p.D[0][i], d1 = p.D[1][i], d2 = p.D[2][i], d3 = p.D[3][i];
             poly[0] = d0.x; poly[1] = d0.y; poly[2] = d0.z; poly[3] = d0.w; poly[4] = d1.x;
             aero[0] = d1.y; aero[1] = d1.z; aero[2] = d1.w; aero[3] = d2.x; aero[4] = d2.y;
@@ -156,7 +195,7 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
             pe[0] = pe[1] = pe[2] = 0.f;
             bu1 = 0.f; bt = 0.f;
             bec = (flags & TACO_F_RANDOM_VOLTAGE) ? rr(2.2f, 0.0f, u01(b2.w)) : 0.f;
-            if (p.has_dr) {
+            if (DR) {
                 const uint4 b5 = philox4x32_10(g, t_rl, 5, STREAM_RESET, k0, k1);
                 const uint4 b6 = philox4x32_10(g, t_rl, 6, STREAM_RESET, k0, k1);
                 const uint4 b7 = philox4x32_10(g, t_rl, 7, STREAM_RESET, k0, k1);
@@ -172,10 +211,10 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
                     for (int j = 0; j < 5; ++j) poly[j] = kPolyNom[j];
                 }
                 if ((flags & TACO_F_ROTOR_RESPONSE) && (flags & TACO_F_RANDOM_ROTOR_RESPONSE)) {   // thrust_dynamics.py:134-137
-                    lag[0] = 0.001f / rr(p.tau_rng, p.tau_lo, u01(b8.x));
-                    lag[1] = 0.001f / rr(p.tau_rng, p.tau_lo, u01(b8.y));
-                    lag[2] = 0.001f / rr(p.tau_rng, p.tau_lo, u01(b8.z));
-                    lag[3] = 0.001f / rr(p.tau_rng, p.tau_lo, u01(b8.w));
+                    lag[0] = (1.0f / rr(p.tau_rng, p.tau_lo, u01(b8.x))) * 0.001f;   // python scalar / tensor = tensor.reciprocal() * scalar
+                    lag[1] = (1.0f / rr(p.tau_rng, p.tau_lo, u01(b8.y))) * 0.001f;
+                    lag[2] = (1.0f / rr(p.tau_rng, p.tau_lo, u01(b8.z))) * 0.001f;
+                    lag[3] = (1.0f / rr(p.tau_rng, p.tau_lo, u01(b8.w))) * 0.001f;
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) lag[j] = p.lag_gain_fixed;
@@ -216,7 +255,7 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
                 tpos.z = 3.0f + d * rr(4.0f, -2.0f, u01(b4.z));
             } else tpos = v3(0.f, 0.f, 3.f);
             const float yaw = (flags & TACO_F_RANDOM_TARGET_YAW) ? rr(kTwoPi, -kPi, u01(b3.w)) : 0.0f;
-            sincosf(yaw * 0.5f, &tq.z, &tq.w);
+            sincos_draw(yaw * 0.5f, &tq.z, &tq.w);
         }
         // ------------------------------------------------------------------ command (:587-603, :758, :814-821, :886-917, :1058-1112)
         if (R || at500) {
@@ -256,6 +295,8 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
         }
 
         const float dt = p.dt, h = p.h;
+        const float rdt = p.inv_dt;
+        auto fdiv_dt = [dt, rdt](float x) { return divc_impl(x, dt, rdt); };   // x / dt, correctly rounded (dt = sim dt)
         const bool battery_on = (flags & TACO_F_BATTERY_CONSUMPTION) != 0;
         const bool track_roll = (task == TACO_TASK_FLIP);
         float volt = 4.35f * 6.0f;                                  // battery_dynamics.py:75
@@ -296,7 +337,7 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
                     const float e = clampf(sp[a] - wbv[a], -400.0f, 400.0f);
                     const float prev = (pe[a] == 0.0f) ? e : pe[a];
                     const float pt = kp[a] * e;
-                    const float dv = clampf(0.5f * ((e - prev) / dt), -150.0f, 150.0f);
+                    const float dv = clampf(0.5f * fdiv_dt(e - prev), -150.0f, 150.0f);
                     uu[a] = 0.4f * (pt + dv);
                     pe[a] = e;
                 }
@@ -320,28 +361,28 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
             {
                 float c[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) { const float x = om[r] * 2.0f * kPi / 4500.0f; c[r] = 400.0f * (x * x * x); }
+                for (int r = 0; r < 4; ++r) { const float x = TACO_DIVC(om[r] * 2.0f * kPi, 4500.0f); c[r] = 400.0f * (x * x * x); }
                 pm = ((c[0] + c[1]) + c[2]) + c[3];
             }
             // battery sag (battery_dynamics.py:47-75)
             if (battery_on) {
                 bt = bt + dt;
-                const float pc = pm / 0.75f / 9000.0f;
+                const float pc = TACO_DIVC(TACO_DIVC(pm, 0.75f), 9000.0f);
                 bec = bec + pc * dt;
                 const float pavg = bec / bt;
                 float r0 = (0.0015778f + -7.7608e-5f * pavg) + (float)(0.0069498 * 1500.0);   // b0 + b1*P_avg + b2*C_c (python folds b2*C_c in double)
                 r0 = (r0 > 4.5f) ? r0 : 4.5f;
                 const float v0 = ((4.35f + -0.1102178f * bec) + 0.0103368f * (bec * bec)) + -4.3778e-4f * (bec * bec * bec);
-                bu1 = bu1 + ((0.00104846f * pc - bu1) / 3.3f) * dt;
+                bu1 = bu1 + TACO_DIVC(0.00104846f * pc - bu1, 3.3f) * dt;
                 const float df = v0 - bu1;
                 volt = 0.5f * (df + sqrtf(df * df - 4.0f * r0 * pc)) * 6.0f;
             }
             // rotor lag (thrust_dynamics.py:52-66,80-86) + optional speed noise (:68-78)
             {
-                const float y = (volt - 23.0f) / 3.0f;
+                const float y = TACO_DIVC(volt - 23.0f, 3.0f);
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
-                    const float x = thr[r] / 1000.0f;
+                    const float x = TACO_DIVC(thr[r], 1000.0f);
                     const float tgt = ((((poly[0] + poly[1] * x) + poly[2] * y) + poly[3] * (x * x)) + poly[4] * x * y) * 100.0f;
                     om[r] = om[r] + lag[r] * (tgt - om[r]);
                 }
@@ -358,7 +399,7 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
                 float f[4], tqr[4];
 #pragma unroll
                 for (int r = 0; r < 4; ++r) { f[r] = aero[0] * om[r] * om[r]; tqr[r] = aero[1] * f[r]; }
-                const float vxy = sqrtf(vb.x * vb.x + vb.y * vb.y);
+                const float vxy = norm2(vb.x, vb.y);                                // torch.norm, thrust_dynamics.py:193
                 const float f0 = f[2], f1 = f[3], f2 = f[0], f3 = f[1];           // sim rotor (0,1,2,3) <- real (2,3,0,1)
                 const float t0 = -tqr[2], t1 = tqr[3], t2 = -tqr[0], t3 = tqr[1];
                 fb.x = aero[2] * vb.x;
@@ -385,15 +426,16 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
                     w.y = w.y + h * ((ts.y - gy.y) * (float)(1.0 / 7e-4));
                     w.z = w.z + h * ((ts.z - gy.z) * 1250.0f);
                     pos.x = pos.x + h * vel.x; pos.y = pos.y + h * vel.y; pos.z = pos.z + h * vel.z;
-                    const float wn = sqrtf((w.x * w.x + w.y * w.y) + w.z * w.z);
-                    const float half = wn * p.half_h;
-                    float sn, cs;
-                    sincosf(half, &sn, &cs);
-                    const float kk = (wn > 0.0f) ? sn / wn : p.half_h;
+                    // exp(h/2 w) by its 4th-order series (exact to float32 for |w| h/2 < 0.1 rad), DESIGN.md "integrator"
+                    const float w2 = (w.x * w.x + w.y * w.y) + w.z * w.z;
+                    const float th2 = w2 * p.half_h2;
+                    const float kk = p.half_h * (1.0f + th2 * (p.c_sin3 + th2 * p.c_sin5));
+                    const float cs = 1.0f + th2 * (-0.5f + th2 * p.c_cos4);
                     Q4 dq; dq.x = w.x * kk; dq.y = w.y * kk; dq.z = w.z * kk; dq.w = cs;
                     q = qmul(q, dq);
-                    const float qn = sqrtf(((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w);
-                    q.x = q.x / qn; q.y = q.y / qn; q.z = q.z / qn; q.w = q.w / qn;
+                    const float n2 = ((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w;
+                    const float rn = 1.5f - 0.5f * n2;                                   // one Newton step of 1/sqrt about 1
+                    q.x = q.x * rn; q.y = q.y * rn; q.z = q.z * rn; q.w = q.w * rn;
                 }
                 wld = qrot(q, w);
             }
@@ -432,15 +474,15 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
         float o24 = 0.f, o25;
         if (task == TACO_TASK_FLIP) {
             c1 = clampf(cmd - roll_cont, -kTwoPi, kTwoPi);           // :831-832
-            o24 = -1.f; o25 = c1 / 2.0f / kPi;
-        } else if (task == TACO_TASK_ROTATE) { o24 = 1.f; o25 = c1 / 6.0f; }
+            o24 = -1.f; o25 = TACO_DIVC(c1 / 2.0f, kPi);
+        } else if (task == TACO_TASK_ROTATE) { o24 = 1.f; o25 = TACO_DIVC(c1, 6.0f); }
         else { c1 = 0.f; o25 = 0.f; }
-        fc[0] = relb.x / 3.0f; fc[1] = relb.y / 3.0f; fc[2] = relb.z / 3.0f;
+        fc[0] = TACO_DIVC(relb.x, 3.0f); fc[1] = TACO_DIVC(relb.y, 3.0f); fc[2] = TACO_DIVC(relb.z, 3.0f);
 #pragma unroll
         for (int j = 0; j < 9; ++j) fc[3 + j] = m[j];
         fc[12] = -vb.x / 2.0f; fc[13] = -vb.y / 2.0f; fc[14] = -vb.z / 2.0f;         // relative velocity = -(own), target is static (:147-148,:357-360)
-        fc[15] = -wb.x / kPi; fc[16] = -wb.y / kPi; fc[17] = -wb.z / kPi;
-        fc[18] = (volt - 23.0f) / 3.0f;
+        fc[15] = TACO_DIVC(-wb.x, kPi); fc[16] = TACO_DIVC(-wb.y, kPi); fc[17] = TACO_DIVC(-wb.z, kPi);
+        fc[18] = TACO_DIVC(volt - 23.0f, 3.0f);
         fc[19] = act.x; fc[20] = act.y; fc[21] = act.z; fc[22] = act.w;
         fc[23] = 4.0f * clampf(pos.z, 0.0f, 0.5f) - 1.0f;
         fc[24] = o24; fc[25] = o25;
@@ -478,36 +520,36 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
         // ------------------------------------------------------------------ reward + termination (task_reward.py)
         float rew, dist;
         if (task == TACO_TASK_POS) {                                  // :20-47
-            dist = sqrtf((relb.x * relb.x + relb.y * relb.y) + relb.z * relb.z);
+            dist = norm3(relb.x, relb.y, relb.z);
             const Q4 mq = qmul(q, conj(tq));                          // quat_diff_rad, torch_jit_utils.py:146-164
-            const float nv = sqrtf((mq.x * mq.x + mq.y * mq.y) + mq.z * mq.z);
+            const float nv = norm3(mq.x, mq.y, mq.z);
             const float ang = 2.0f * asinf(fminf(nv, 1.0f));
-            rew = two_scale(dist) * two_scale(ang) / 100.0f;
+            rew = TACO_DIVC(two_scale(dist) * two_scale(ang), 100.0f);
         } else if (task == TACO_TASK_ROTATE) {                        // :50-104
             float ex = -rel.x, ey = -rel.y;
-            const float en = sqrtf(ex * ex + ey * ey) + 1e-8f;
+            const float en = norm3(ex, ey, 0.0f) + 1e-8f;
             ex = ex / en; ey = ey / en;
             float yx = -ey, yy = ex;                                  // e_z x e_x
-            const float yn = sqrtf(yx * yx + yy * yy) + 1e-8f;
+            const float yn = norm3(yx, yy, 0.0f) + 1e-8f;
             yx = yx / yn; yy = yy / yn;
-            const float hori = sqrtf(rel.x * rel.x + rel.y * rel.y) - 1.2f;
+            const float hori = norm2(rel.x, rel.y) - 1.2f;
             const float vert = fabsf(rel.z);
             dist = sqrtf(hori * hori + vert * vert);
             const float rvx = -vel.x, rvy = -vel.y, rvz = -vel.z;     // relative_linvel = 0 - v
             const float vn = rvx * ex + rvy * ey;
             const float vt = (rvx * yx + rvy * yy) - c1;
-            const float verr = sqrtf((vn * vn + vt * vt) + rvz * rvz);
+            const float verr = norm3(vn, vt, rvz);
             const float two_s = 2.0f / (((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w);
             const float hx = 1.0f - two_s * (q.y * q.y + q.z * q.z);
             const float hy = two_s * (q.x * q.y + q.z * q.w);
-            const float ddir = 1.0f + (ex * hx + ey * hy) / sqrtf(hx * hx + hy * hy);
-            rew = two_scale(dist) * two_scale(verr) * two_scale(ddir) / 100.0f;
+            const float ddir = 1.0f + (ex * hx + ey * hy) / norm2(hx, hy);
+            rew = TACO_DIVC(two_scale(dist) * two_scale(verr) * two_scale(ddir), 100.0f);
         } else {                                                      // :107-143
-            dist = sqrtf((relb.x * relb.x + relb.y * relb.y) + relb.z * relb.z);
+            dist = norm3(relb.x, relb.y, relb.z);
             const float rp = 1.0f / (1.0f + 1.0f * dist) + 1.0f / (1.0f + 10.0f * dist);
             const float rt = 1.0f / (1.0f + 10.0f * (1.0f - m[0]));
-            const float turns = c1 / 2.0f / kPi;
-            rew = rp * rt * two_scale(turns) / 100.0f;
+            const float turns = TACO_DIVC(c1 / 2.0f, kPi);
+            rew = TACO_DIVC(rp * rt * two_scale(turns), 100.0f);
         }
         const bool die = (pos.z < 0.1f) || (dist > 10.0f);
         const bool tmax = progress >= p.max_len - 1;
@@ -558,50 +600,21 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
         atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * kStatStride + 7, (double)nv);
     }
 
-    // ---------------------------------------------------------------------- history shift + newest frame, coalesced 64-bit rows
-    // out[e][f][:] = in[e][f+1][:] for f < L-1, newest frame last (:392,:413); ping-pong buffers, so no in-place hazard.
+    // ---------------------------------------------------------------------- history shift + newest frame (:392,:413)
+    // out[e][f][:] = in[e][f+1][:] for f < L-1, newest frame last; ping-pong buffers, so no in-place hazard.
     const size_t blk_env0 = (size_t)blockIdx.x * kBlock;
-    {
-        const int L = p.len_states;
-        const int row2 = 13 * L, keep2 = 13 * (L - 1);
-        const float2* in2 = reinterpret_cast<const float2*>(p.states_in) + blk_env0 * row2;
-        float2* out2 = reinterpret_cast<float2*>(p.states_out) + blk_env0 * row2;
-        const int total = kBlock * row2;
-        int e = tid / row2, j2 = tid % row2;
-        const int de = kBlock / row2, dj = kBlock % row2;
-        for (int idx = tid; idx < total; idx += kBlock) {
-            float2 v;
-            if (j2 < keep2) v = __ldg(in2 + idx + 13);
-            else { const float* fr = s_clean + e * kFramePad + 2 * (j2 - keep2); v = make_float2(fr[0], fr[1]); }
-            out2[idx] = v;
-            e += de; j2 += dj;
-            if (j2 >= row2) { j2 -= row2; e += 1; }
-        }
-    }
-    {
-        const float* sf = obs_noise ? s_noisy : s_clean;
-        const int L = p.len_obs;
-        const int row2 = 13 * L, keep2 = 13 * (L - 1);
-        const float2* in2 = reinterpret_cast<const float2*>(p.obs_in) + blk_env0 * row2;
-        float2* out2 = reinterpret_cast<float2*>(p.obs_out) + blk_env0 * row2;
-        const int total = kBlock * row2;
-        int e = tid / row2, j2 = tid % row2;
-        const int de = kBlock / row2, dj = kBlock % row2;
-        for (int idx = tid; idx < total; idx += kBlock) {
-            float2 v;
-            if (j2 < keep2) v = __ldg(in2 + idx + 13);
-            else { const float* fr = sf + e * kFramePad + 2 * (j2 - keep2); v = make_float2(fr[0], fr[1]); }
-            out2[idx] = v;
-            e += de; j2 += dj;
-            if (j2 >= row2) { j2 -= row2; e += 1; }
-        }
-    }
+    if (p.len_states == 5) write_rows<5>(p.states_in, p.states_out, s_clean, 5, blk_env0, tid);
+    else write_rows<0>(p.states_in, p.states_out, s_clean, p.len_states, blk_env0, tid);
+    const float* sf = obs_noise ? s_noisy : s_clean;
+    if (p.len_obs == 1) write_rows<1>(p.obs_in, p.obs_out, sf, 1, blk_env0, tid);
+    else write_rows<0>(p.obs_in, p.obs_out, sf, p.len_obs, blk_env0, tid);
 }
 
 template <int TASK>
 static void launch_task(const StepParams& p, cudaStream_t stream) {
     const int grid = p.n_pad / kBlock;
-    fpv_step_kernel<TASK><<<grid, kBlock, 0, stream>>>(p);
+    if (p.has_dr) fpv_step_kernel<TASK, true><<<grid, kBlock, 0, stream>>>(p);
+    else fpv_step_kernel<TASK, false><<<grid, kBlock, 0, stream>>>(p);
 }
 
 static inline void launch_any(const StepParams& p, cudaStream_t stream) {

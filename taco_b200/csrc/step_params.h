@@ -23,7 +23,7 @@ struct StepParams {
     long long mix_n1, mix_n2;      // global task-group boundaries (fpv_asymmetry.py:924-926)
     int task_mode, len_obs, len_states, max_len, cfi, substeps, delay_time;
     uint32_t flags, seed_lo, seed_hi, step_index;
-    float dt, h, half_h, inv_mass, difficulty, clip_actions;
+    float dt, inv_dt, h, half_h, half_h2, c_sin3, c_sin5, c_cos4, inv_mass, difficulty, clip_actions;
     // host-precomputed (double -> float) bounds of the difficulty-dependent uniform draws
     float flip_xy_rng, flip_xy_lo, flip_lin_rng, flip_lin_lo, dr_rng, dr_lo, tau_rng, tau_lo, noise_rng, noise_lo;
     float lag_gain_fixed;          // 0.001 / rotor_response_time (or 1.0 when rotor_response is off)

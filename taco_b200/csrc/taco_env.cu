@@ -13,6 +13,7 @@
 
 #include "../../include/taco_b200.h"
 #include "philox.cuh"
+#include "fpv_math.cuh"
 #include "step_params.h"
 
 namespace taco {
@@ -175,6 +176,26 @@ __global__ void import_state_kernel(StepParams p, const float* in) {
     }
 }
 
+// exhaustive check of the constant-division sequence against IEEE division: every float bit pattern whose magnitude
+// is in [2^-60, 2^60] (and +-0), for every divisor the step kernel uses
+template <int K>
+__device__ __forceinline__ bool divc_case(float x, float c) {
+    const float a = divc_impl(x, c, 1.0f / c), b = x / c;
+    return __float_as_uint(a) == __float_as_uint(b);
+}
+__global__ void selftest_divc_kernel(unsigned long long* bad, float dt) {
+    const float cs[11] = {4500.0f, 0.75f, 9000.0f, 3.3f, 3.0f, 1000.0f, kPi, 6.0f, 100.0f, dt, 2.0f};
+    unsigned long long local = 0;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32); b += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((uint32_t)b);
+        const float ax = fabsf(x);
+        if (!(ax == 0.0f || (ax >= 8.673617379884035e-19f && ax <= 1.152921504606847e18f))) continue;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) local += divc_case<0>(x, cs[k]) ? 0 : 1;
+    }
+    if (local) atomicAdd(bad, local);
+}
+
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace taco
@@ -184,6 +205,21 @@ using namespace taco;
 extern "C" {
 
 const char* taco_last_error(void) { return g_err.c_str(); }
+
+int taco_selftest_divc(int device, float dt, uint64_t* n_mismatch) {
+    if (!n_mismatch) return fail(TACO_E_INVALID, "taco_selftest_divc: null argument");
+    DeviceGuard guard(device);
+    unsigned long long* d = nullptr;
+    TACO_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+    TACO_CUDA(cudaMemset(d, 0, sizeof(unsigned long long)));
+    selftest_divc_kernel<<<148 * 8, 256>>>(d, dt);
+    TACO_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    TACO_CUDA(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *n_mismatch = h;
+    return TACO_OK;
+}
 int taco_abi_version(void) { return TACO_ABI_VERSION; }
 
 int taco_env_create(const TacoCfg* cfg, int device, TacoEnv** out) {
@@ -228,11 +264,17 @@ int taco_env_create(const TacoCfg* cfg, int device, TacoEnv** out) {
     p.flags = cfg->flags;
     p.seed_lo = (uint32_t)(cfg->seed & 0xFFFFFFFFull); p.seed_hi = (uint32_t)(cfg->seed >> 32);
     p.dt = cfg->dt;
+    p.inv_dt = 1.0f / cfg->dt;
     p.h = (float)((double)cfg->dt / cfg->substeps);
     p.half_h = (float)(0.5 * ((double)cfg->dt / cfg->substeps));
+    {   // python evaluates hh*hh, -1/6, 1/120, 1/24 in double and casts at the tensor op (oracle/rigid_body.py)
+        const double hh = 0.5 * ((double)cfg->dt / cfg->substeps);
+        p.half_h2 = (float)(hh * hh); p.c_sin3 = (float)(-1.0 / 6.0); p.c_sin5 = (float)(1.0 / 120.0); p.c_cos4 = (float)(1.0 / 24.0);
+    }
     p.inv_mass = (float)(1.0 / (0.46 + 8 * 1e-7));            // fpv_without_duct.xml:6,11-13
     p.clip_actions = cfg->clip_actions;
-    p.lag_gain_fixed = (cfg->flags & TACO_F_ROTOR_RESPONSE) ? 0.001f / cfg->rotor_response_time : 0.001f / 0.001f;
+    // thrust_dynamics.py:84 `sample_time / response_time` is python-float / tensor = tensor.reciprocal() * float
+    p.lag_gain_fixed = (cfg->flags & TACO_F_ROTOR_RESPONSE) ? (1.0f / cfg->rotor_response_time) * 0.001f : (1.0f / 0.001f) * 0.001f;
     p.has_dr = (cfg->flags & (TACO_F_RANDOM_ROTORDYNAMIC_COE | TACO_F_RANDOM_ROTOR_RESPONSE | TACO_F_RANDOM_AERODYNAMIC_COE)) ? 1 : 0;
     refresh_derived(e);
 

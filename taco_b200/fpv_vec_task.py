@@ -49,7 +49,9 @@ class FpvVecTask:
 
     def __init__(self, cfg, rl_device="cuda:0", sim_device="cuda:0", graphics_device_id=-1, headless=True,
                  virtual_screen_capture=False, force_render=False, *, env_offset=0, num_envs_global=None, seed=None,
-                 strict_fp=False, debug_delay=False):
+                 strict_fp=True, debug_delay=False):
+        # strict_fp=True (default): the -fmad=false kernel build, op-for-op float32 like eager torch -- the build
+        # every parity claim is made for and the one bench.py times.  strict_fp=False selects the FMA-contracted build.
         if not torch.cuda.is_available():
             raise RuntimeError("CUDA is not available: the fused FPV step has no CPU fallback")
         self.cfg = cfg

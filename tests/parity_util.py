@@ -40,10 +40,14 @@ def oracle_state(env):
 
 
 def rel_err(a, b, scale):
+    """Relative error of a field: per env, max_i |a_i - b_i| / max(||b||_2, scale) where b is the
+    env's whole vector for that field (3-vector, quaternion, 4 rotor speeds, one 26-value frame...),
+    so that a small component of a large vector is measured against the vector, not against itself."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     both_nan = np.isnan(a) & np.isnan(b)
-    err = np.abs(a - b) / np.maximum(np.abs(b), scale)
+    norm = np.sqrt(np.sum(np.where(np.isfinite(b), b, 0.0) ** 2, axis=-1, keepdims=True)) if b.ndim > 1 else np.abs(b)
+    err = np.abs(a - b) / np.maximum(norm, scale)
     err = np.where(both_nan, 0.0, err)
     return np.where(np.isnan(err), np.inf, err)
 

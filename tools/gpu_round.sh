@@ -3,12 +3,13 @@
 # usage (under gpurun): bash tools/gpu_round.sh <tag>
 TAG=${1:-r01}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu_$TAG.log
+python tools/parity_report.py 50 2>&1 | grep -E "==|step 1 |step 2 |step 50|mismatch" | cut -c1-700 > gpurun_out/parity_$TAG.log
+python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu_$TAG.log
 tail -5 gpurun_out/pytest_gpu_$TAG.log
 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
 cat gpurun_out/bench_$TAG.json
-python bench.py --strict-fp --no-cpu-baseline > gpurun_out/bench_strict_$TAG.json 2>> gpurun_out/bench_$TAG.err
-cat gpurun_out/bench_strict_$TAG.json
+python bench.py --fast-fp --no-cpu-baseline > gpurun_out/bench_fast_$TAG.json 2>> gpurun_out/bench_$TAG.err
+cat gpurun_out/bench_fast_$TAG.json
 BENCH_SMALL="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-small"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv $BENCH_SMALL > gpurun_out/ncu_launch_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:fpv_step_kernel -s 3 -c 2 -f -o gpurun_out/prof_$TAG $BENCH_SMALL > gpurun_out/ncu_full_$TAG.log 2>&1
