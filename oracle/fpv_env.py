@@ -278,8 +278,10 @@ class RefFpvEnv:
         self.progress_buf = torch.where(R, torch.zeros_like(self.progress_buf), self.progress_buf)
 
     # ------------------------------------------------------------------ state refresh
-    def _refresh(self):
-        """FPV:334-360."""
+    def _refresh(self, w_body=None):
+        """FPV:334-360.  ``w_body``: body-frame angular velocity carried by the simulator stand-in between the
+        control sub-steps of one RL step (oracle/rigid_body.py); None = derive it from the world-frame root
+        state exactly as FPV:350 does (first sub-step and post_physics_step)."""
         self.rpy = torch.stack(euler_xyz(self.quat), dim=1)
         delta = self.rpy - self.rpy_old
         if self.first_reset:
@@ -291,7 +293,7 @@ class RefFpvEnv:
         self.rpy_old = self.rpy.clone()
         qc = qconj(self.quat)
         self.linvel_body = qrot(qc, self.linvel)
-        self.angvel_body = qrot(qc, self.angvel)
+        self.angvel_body = qrot(qc, self.angvel) if w_body is None else w_body
         self.rel_pos = self.tpos - self.pos
         self.rel_pos_body = qrot(qc, self.rel_pos)
         self.rel_quat_body = qmul(qc, self.tquat)
@@ -324,8 +326,9 @@ class RefFpvEnv:
         rows = torch.arange(N)
         delay_idx_log, delay_act_log = [], []
         # ---- control_freq_inv x (mid_physics_step + simulate), VT:309-313
+        w_b = None
         for k in range(self.cfi):
-            self._refresh()                                            # FPV:363
+            self._refresh(w_b)                                         # FPV:363
             idx = torch.clamp(self.delay_len - 1, max=k)               # FPV:366 (negative wraps like python)
             idx = torch.where(idx < 0, idx + 100, idx)
             delay_idx_log.append(idx.clone())
@@ -351,8 +354,10 @@ class RefFpvEnv:
             force_b, torque_b = rb.body_wrench(fs, ts, body_f)
             force_b = torch.where(R.unsqueeze(1), torch.zeros(N, 3), force_b)                      # FPV:629-630
             torque_b = torch.where(R.unsqueeze(1), torch.zeros(N, 3), torque_b)
-            self.pos, self.quat, self.linvel, self.angvel = rb.integrate(                          # VT:313
-                self.pos, self.quat, self.linvel, self.angvel, force_b, torque_b, self.dt, self.substeps)
+            self.pos, self.quat, self.linvel, w_b = rb.integrate(                                  # VT:313
+                self.pos, self.quat, self.linvel, self.angvel_body, force_b, torque_b, self.dt, self.substeps)
+        if w_b is not None:
+            self.angvel = qrot(self.quat, w_b)                         # world-frame root state at the end of the RL step
         self.last_delay_index = torch.stack(delay_idx_log, dim=1)
         self.last_delayed_actions = torch.stack(delay_act_log, dim=1)          # (N, cfi, 4)
         # ---- post_physics_step, FPV:374-388

@@ -12,27 +12,29 @@ Model facts taken from the reference:
   * gravity (0,0,-9.81) (fpv_asymmetry.py:215-217); no damping, no velocity limits
     (fpv_asymmetry.py:250-256); gyroscopic forces on (docs release notes: enabled by default)
   * forces/torques are given in the BODY frame and applied with LOCAL_SPACE
-    (fpv_asymmetry.py:620-635): converted to the world frame with the pose at apply time
-    and held constant for the whole simulate() call, over ``substeps`` sub-steps of
+    (fpv_asymmetry.py:620-635); the simulate() call runs ``substeps`` sub-steps of
     h = dt/substeps (vec_task_asymmetry.py:432).
   * root state = pos, quat xyzw, linear velocity (world), angular velocity (world)
     (docs/programming/tensors: actor root state layout).
 
-Step (semi-implicit Euler; quaternion exponential by its 4th-order series -- with
-theta = |w_b| h/2 <= 0.02 rad for |w_b| <= 80 rad/s the truncation error theta^6/720 is < 1e-13,
-far below float32 resolution, and the form needs only + and *, so a -fmad=false CUDA build
-reproduces the torch float32 result bit for bit; no sqrt / sin / cos / division):
-    exp(h/2 w_b) ~ ( w_b * (h/2)(1 - t/6 + t^2/120),  1 - t/2 + t^2/24 ),  t = theta^2
-    F_w = R(q) F_b ; tau_w = R(q) tau_b ; w_b = R(q)^T w        (once per simulate call)
-    per sub-step s:
-        v    += h * (F_w / m + g)
-        tau_s = tau_b if s == 0 else R(q)^T tau_w
-        w_b  += h * I^-1 (tau_s - w_b x (I w_b))
-        p    += h * v
-        q     = renorm(q * exp(h/2 * w_b))      (body-frame increment, right-multiplied;
-                                                 it rotates about w_b, so w_b is unchanged)
-    w = R(q) w_b                                                  (once, at the end)
-    renorm(q) = q * (1.5 - 0.5 |q|^2)    (one Newton step of 1/sqrt: no sqrt, no division)
+Our specification (semi-implicit Euler, body-frame rotational dynamics):
+    F_w = R(q) F_b                        once per simulate call: the FORCE is held constant in the world
+                                          frame over the sub-steps (what PhysX does with an applied force)
+    per sub-step:
+        v   += h * (F_w / m + g)
+        w_b += h * I^-1 (tau_b - w_b x (I w_b))      the TORQUE is held constant in the BODY frame (rotor
+                                          thrust differentials and reaction torques are body-fixed; PhysX would
+                                          hold it in the world frame -- an O(h^2) difference at h = 0.5 ms)
+        p   += h * v
+        q    = renorm(q * exp(h/2 * w_b))            body-frame increment, right-multiplied
+    exp(h/2 w_b) ~ ( w_b * (h/2)(1 - t/6 + t^2/120),  1 - t/2 + t^2/24 ),  t = |w_b|^2 (h/2)^2
+        4th-order series: truncation theta^6/720 < 1e-13 for |w_b| <= 80 rad/s, needs only + and *
+    renorm(q) = q * (1.5 - 0.5 |q|^2)     one Newton step of 1/sqrt about 1 (|q|^2 = 1 + O(1e-7)): no sqrt, no division
+The angular velocity is carried in BODY coordinates (w_b) for the whole VecTask.step; the world-frame
+root-state value w = R(q) w_b is materialised by the caller at the end of the RL step and converted back
+with w_b = R(q)^T w at the start of the next one (fpv_asymmetry.py:350), so the flip-reset quirk that leaves
+the world-frame w_y, w_z stale (fpv_asymmetry.py:876) keeps its meaning.  Every operation is +, * on float32,
+so a -fmad=false CUDA build reproduces the torch result bit for bit.
 """
 import torch
 
@@ -56,31 +58,25 @@ def body_wrench(rotor_force_sim, rotor_torque_sim, body_force):
     return force, torch.stack((tx, ty, tz), dim=1)
 
 
-def integrate(pos, quat, linvel, angvel, force_b, torque_b, dt, substeps):
-    """One simulate(dt) call.  All tensors (N,3|4) float32; returns the new root state."""
+def integrate(pos, quat, linvel, w_b, force_b, torque_b, dt, substeps):
+    """One simulate(dt) call.  All tensors (N,3|4) float32; w_b is the body-frame angular velocity.
+    Returns the new (pos, quat, linvel, w_b)."""
     inertia = torch.tensor(INERTIA, dtype=torch.float32)
     inv_inertia = torch.tensor([1.0 / i for i in INERTIA], dtype=torch.float32)
     inv_mass = 1.0 / MASS
     h = dt / substeps
+    hh = 0.5 * h
     grav = torch.tensor([0.0, 0.0, GRAVITY_Z], dtype=torch.float32)
-    force_w = qrot(quat, force_b)
-    torque_w = qrot(quat, torque_b)
-    w_b = qrot(qconj(quat), angvel)
-    for s in range(substeps):
-        linvel = linvel + h * (force_w * inv_mass + grav)
-        tau_b = torque_b if s == 0 else qrot(qconj(quat), torque_w)
-        w_b = w_b + h * ((tau_b - cross3(w_b, inertia * w_b)) * inv_inertia)
+    acc = qrot(quat, force_b) * inv_mass + grav
+    for _ in range(substeps):
+        linvel = linvel + h * acc
+        w_b = w_b + h * ((torque_b - cross3(w_b, inertia * w_b)) * inv_inertia)
         pos = pos + h * linvel
-        hh = 0.5 * h
         w2 = (w_b[:, 0:1] * w_b[:, 0:1] + w_b[:, 1:2] * w_b[:, 1:2]) + w_b[:, 2:3] * w_b[:, 2:3]
-        t = w2 * (hh * hh)                                   # theta^2
+        t = w2 * (hh * hh)                                     # theta^2
         k = hh * (1.0 + t * (-1.0 / 6.0 + t * (1.0 / 120.0)))  # sin(theta)/|w|
         c = 1.0 + t * (-0.5 + t * (1.0 / 24.0))                # cos(theta)
-        dq = torch.cat((w_b * k, c), dim=1)
-        quat = qmul(quat, dq)
-        # renormalise with one Newton step of 1/sqrt about 1: |q|^2 = 1 + e with |e| ~ 1e-7 after a
-        # float32 product of unit quaternions, so q * (1.5 - 0.5 |q|^2) is unit to O(e^2) ~ 1e-14
+        quat = qmul(quat, torch.cat((w_b * k, c), dim=1))
         n2 = ((quat[:, 0:1] * quat[:, 0:1] + quat[:, 1:2] * quat[:, 1:2]) + quat[:, 2:3] * quat[:, 2:3]) + quat[:, 3:4] * quat[:, 3:4]
         quat = quat * (1.5 - 0.5 * n2)
-    angvel = qrot(quat, w_b)
-    return pos, quat, linvel, angvel
+    return pos, quat, linvel, w_b

@@ -74,7 +74,8 @@ __device__ __forceinline__ void write_rows(const float* __restrict__ in, float* 
 
 // TASK: task_mode (mix = per-env task from the global env id).  DR: per-env randomised model parameters live in the
 // D planes; when false the rotor polynomial / aero coefficients fold into instruction immediates.
-template <int TASK, bool DR>
+// SUB: physics sub-steps per simulate call (1 / 2 unrolled; 0 = runtime p.substeps).
+template <int TASK, bool DR, int SUB>
 __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p) {
     __shared__ float s_clean[kBlock * kFramePad];
     __shared__ float s_noisy[kBlock * kFramePad];
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
                 roll_cont += dl;
                 roll_old = roll;
             }
-            if (k > 0) { const Q4 qc = conj(q); vb = qrot(qc, vel); wb = qrot(qc, wld); }
+            if (k > 0) vb = qrot(conj(q), vel);               // wb is carried by the integrator between sub-steps
             // delayed action (:366-368): buffer position min(len-1, k)
             {
                 const int slot_abs = clk + min(q_len - 1, k);
@@ -410,36 +411,35 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
                 tb.z = ((t0 + t1) + t2) + t3;
                 if (R) { fb = v3(0.f, 0.f, 0.f); tb = v3(0.f, 0.f, 0.f); }        // fpv_asymmetry.py:629-630
             }
-            // free rigid body, `substeps` x h (DESIGN.md "integrator"; oracle/rigid_body.py)
+            // free rigid body, `substeps` x h (DESIGN.md "integrator"; oracle/rigid_body.py): force held in the world
+            // frame, torque in the body frame, angular velocity carried in body coordinates
             {
                 const V3 fw = qrot(q, fb);
-                V3 tw = tb;
-                if (p.substeps > 1) tw = qrot(q, tb);
                 const V3 acc = v3(fw.x * p.inv_mass + 0.0f, fw.y * p.inv_mass + 0.0f, fw.z * p.inv_mass + -9.81f);
-                V3 w = wb;
-                for (int s = 0; s < p.substeps; ++s) {
+                const int nsub = SUB ? SUB : p.substeps;
+#pragma unroll
+                for (int s = 0; s < nsub; ++s) {
                     vel.x = vel.x + h * acc.x; vel.y = vel.y + h * acc.y; vel.z = vel.z + h * acc.z;
-                    const V3 ts = (s == 0) ? tb : qrot(conj(q), tw);
-                    const V3 iw = v3(5e-4f * w.x, 7e-4f * w.y, 8e-4f * w.z);
-                    const V3 gy = cross(w, iw);
-                    w.x = w.x + h * ((ts.x - gy.x) * 2000.0f);
-                    w.y = w.y + h * ((ts.y - gy.y) * (float)(1.0 / 7e-4));
-                    w.z = w.z + h * ((ts.z - gy.z) * 1250.0f);
+                    const V3 iw = v3(5e-4f * wb.x, 7e-4f * wb.y, 8e-4f * wb.z);
+                    const V3 gy = cross(wb, iw);
+                    wb.x = wb.x + h * ((tb.x - gy.x) * 2000.0f);
+                    wb.y = wb.y + h * ((tb.y - gy.y) * (float)(1.0 / 7e-4));
+                    wb.z = wb.z + h * ((tb.z - gy.z) * 1250.0f);
                     pos.x = pos.x + h * vel.x; pos.y = pos.y + h * vel.y; pos.z = pos.z + h * vel.z;
-                    // exp(h/2 w) by its 4th-order series (exact to float32 for |w| h/2 < 0.1 rad), DESIGN.md "integrator"
-                    const float w2 = (w.x * w.x + w.y * w.y) + w.z * w.z;
+                    // exp(h/2 w) by its 4th-order series (exact to float32 for |w| h/2 < 0.1 rad)
+                    const float w2 = (wb.x * wb.x + wb.y * wb.y) + wb.z * wb.z;
                     const float th2 = w2 * p.half_h2;
                     const float kk = p.half_h * (1.0f + th2 * (p.c_sin3 + th2 * p.c_sin5));
                     const float cs = 1.0f + th2 * (-0.5f + th2 * p.c_cos4);
-                    Q4 dq; dq.x = w.x * kk; dq.y = w.y * kk; dq.z = w.z * kk; dq.w = cs;
+                    Q4 dq; dq.x = wb.x * kk; dq.y = wb.y * kk; dq.z = wb.z * kk; dq.w = cs;
                     q = qmul(q, dq);
                     const float n2 = ((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w;
                     const float rn = 1.5f - 0.5f * n2;                                   // one Newton step of 1/sqrt about 1
                     q.x = q.x * rn; q.y = q.y * rn; q.z = q.z * rn; q.w = q.w * rn;
                 }
-                wld = qrot(q, w);
             }
         }
+        wld = qrot(q, wb);                                            // world-frame root state at the end of the RL step
 
         // ------------------------------------------------------------------ post_physics_step (:374-388)
         progress += 1;
@@ -613,8 +613,15 @@ __global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p)
 template <int TASK>
 static void launch_task(const StepParams& p, cudaStream_t stream) {
     const int grid = p.n_pad / kBlock;
-    if (p.has_dr) fpv_step_kernel<TASK, true><<<grid, kBlock, 0, stream>>>(p);
-    else fpv_step_kernel<TASK, false><<<grid, kBlock, 0, stream>>>(p);
+    if (p.has_dr) {
+        if (p.substeps == 2) fpv_step_kernel<TASK, true, 2><<<grid, kBlock, 0, stream>>>(p);
+        else if (p.substeps == 1) fpv_step_kernel<TASK, true, 1><<<grid, kBlock, 0, stream>>>(p);
+        else fpv_step_kernel<TASK, true, 0><<<grid, kBlock, 0, stream>>>(p);
+    } else {
+        if (p.substeps == 2) fpv_step_kernel<TASK, false, 2><<<grid, kBlock, 0, stream>>>(p);
+        else if (p.substeps == 1) fpv_step_kernel<TASK, false, 1><<<grid, kBlock, 0, stream>>>(p);
+        else fpv_step_kernel<TASK, false, 0><<<grid, kBlock, 0, stream>>>(p);
+    }
 }
 
 static inline void launch_any(const StepParams& p, cudaStream_t stream) {

@@ -181,9 +181,9 @@ __global__ void import_state_kernel(StepParams p, const float* in) {
 template <int K>
 __device__ __forceinline__ bool divc_case(float x, float c) {
     const float a = divc_impl(x, c, 1.0f / c), b = x / c;
-    return __float_as_uint(a) == __float_as_uint(b);
+    return __float_as_uint(a) == __float_as_uint(b) || (a == 0.0f && b == 0.0f);   // -0 / C gives +0 (sign of zero only)
 }
-__global__ void selftest_divc_kernel(unsigned long long* bad, float dt) {
+__global__ void selftest_divc_kernel(unsigned long long* bad, float dt, uint32_t* rec) {
     const float cs[11] = {4500.0f, 0.75f, 9000.0f, 3.3f, 3.0f, 1000.0f, kPi, 6.0f, 100.0f, dt, 2.0f};
     unsigned long long local = 0;
     for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32); b += (unsigned long long)gridDim.x * blockDim.x) {
@@ -191,7 +191,12 @@ __global__ void selftest_divc_kernel(unsigned long long* bad, float dt) {
         const float ax = fabsf(x);
         if (!(ax == 0.0f || (ax >= 8.673617379884035e-19f && ax <= 1.152921504606847e18f))) continue;
 #pragma unroll
-        for (int k = 0; k < 11; ++k) local += divc_case<0>(x, cs[k]) ? 0 : 1;
+        for (int k = 0; k < 11; ++k)
+            if (!divc_case<0>(x, cs[k])) {
+                local += 1;
+                const unsigned long long slot = atomicAdd(bad + 1, 1ull);
+                if (slot < 32) { rec[2 * slot] = (uint32_t)b; rec[2 * slot + 1] = (uint32_t)k; }
+            }
     }
     if (local) atomicAdd(bad, local);
 }
@@ -210,14 +215,20 @@ int taco_selftest_divc(int device, float dt, uint64_t* n_mismatch) {
     if (!n_mismatch) return fail(TACO_E_INVALID, "taco_selftest_divc: null argument");
     DeviceGuard guard(device);
     unsigned long long* d = nullptr;
-    TACO_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
-    TACO_CUDA(cudaMemset(d, 0, sizeof(unsigned long long)));
-    selftest_divc_kernel<<<148 * 8, 256>>>(d, dt);
+    TACO_CUDA(cudaMalloc(&d, 2 * sizeof(unsigned long long) + 64 * sizeof(uint32_t)));
+    TACO_CUDA(cudaMemset(d, 0, 2 * sizeof(unsigned long long) + 64 * sizeof(uint32_t)));
+    selftest_divc_kernel<<<148 * 8, 256>>>(d, dt, (uint32_t*)(d + 2));
     TACO_CUDA(cudaGetLastError());
-    unsigned long long h = 0;
-    TACO_CUDA(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    unsigned long long h[2 + 32] = {0};
+    TACO_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(d);
-    *n_mismatch = h;
+    *n_mismatch = h[0];
+    if (h[0]) {
+        std::string msg = "divc mismatches (x bits, divisor index):";
+        const uint32_t* rec = (const uint32_t*)(h + 2);
+        for (unsigned long long i = 0; i < h[0] && i < 32; ++i) { char buf[64]; snprintf(buf, sizeof(buf), " (0x%08x,%u)", rec[2 * i], rec[2 * i + 1]); msg += buf; }
+        g_err = msg;
+    }
     return TACO_OK;
 }
 int taco_abi_version(void) { return TACO_ABI_VERSION; }

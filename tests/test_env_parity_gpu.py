@@ -1,13 +1,18 @@
 """Parity of the fused CUDA step (through the C ABI / FpvVecTask) against the oracle (RefFpvEnv) on
 identical Philox draws.  GPU only.
 
-Bars (BASELINE.json north_star):
+Bars (BASELINE.json north_star), for the default strict (-fmad=false) build -- the one bench.py times:
   * delay-buffer reads, reset masks, episode counters, time-outs: bit-exact, every step;
-  * single-step state / obs / reward: <= 1e-5 relative FP32 for the strict (-fmad=false) build, where
-    relative = |a-b| / max(|b|, field scale) with the scales in parity_util.SCALE;
-  * 50-step horizon: stated tolerances below.  The flip task is chaotic (roll rates of +-10 rad/s, derivative
-    gain 500, allocator saturation): float32 rounding differences between two correct implementations grow by
-    ~3 decades over 50 steps (measured 2e-2 worst env out of 4096), pos/rotate by ~1 decade (measured 1e-4).
+  * single-step state / obs / reward: <= 1e-5 relative FP32, relative = max_i |a_i-b_i| / max(||b||_2, scale)
+    per env and field (parity_util.rel_err / SCALE).  Measured: <= 5e-7 (pos, quat, velocities, PID state are
+    bit-identical after the first step; the rest is 1-ulp libm noise: atan2/asin, and torch's AVX-512 sqrt, which
+    is not correctly rounded for ~0.7 % of inputs while CUDA's sqrt.rn is);
+  * 50-step horizon: <= 5e-4 for every task (measured <= 3e-5).  The flip dynamics are chaotic, but the strict
+    build performs the same float32 operations in the same order as the oracle, so the trajectories only separate
+    through the 1-ulp sqrt differences above.
+The FMA-contracted build (strict_fp=False) rounds differently by construction: it is held to 2e-5 on the first
+step, and its long-horizon divergence (ill-conditioned battery sag near full throttle, battery_dynamics.py:68)
+is reported by tools/parity_report.py rather than asserted.
 """
 import numpy as np
 import pytest
@@ -16,8 +21,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 SINGLE_STEP_TOL_STRICT = 1.0e-5
-SINGLE_STEP_TOL_FAST = 2.0e-5        # FMA-contracted build: one rounding instead of two per multiply-add
-H50_TOL = {"flip": 1.0e-1, "pos": 2.0e-3, "rotate": 2.0e-3, "mix": 1.0e-1}
+SINGLE_STEP_TOL_FAST = 2.0e-5
+H50_TOL = 5.0e-4
 
 
 def _pair(task, n=4096, strict=True, **kw):
@@ -42,11 +47,11 @@ def test_single_step_and_50_step_horizon_strict(task):
     assert max(errs1.values()) <= SINGLE_STEP_TOL_STRICT, f"{task} single-step: {errs1}"
     # second step: first step with non-zero wrench (the first step after a reset applies zero force, quirk 1)
     errs2 = res[1][0]
-    assert max(errs2.values()) <= 3 * SINGLE_STEP_TOL_STRICT, f"{task} step 2: {errs2}"
+    assert max(errs2.values()) <= SINGLE_STEP_TOL_STRICT, f"{task} step 2: {errs2}"
     for t, (errs, mism, dmis, nfin) in enumerate(res):
         _assert_ints(mism, dmis, f"{task} step {t + 1}")
     errs50 = res[-1][0]
-    assert max(errs50.values()) <= H50_TOL[task], f"{task} 50-step: {errs50}"
+    assert max(errs50.values()) <= H50_TOL, f"{task} 50-step: {errs50}"
     # rollout statistics: integer counts exact, sums to float32 accumulation accuracy
     g = gpu.stats().cpu().numpy()
     s = ref.stats
@@ -58,7 +63,7 @@ def test_single_step_and_50_step_horizon_strict(task):
 
 def test_single_step_fast_build_flip():
     pu, gpu, ref = _pair("flip", strict=False)
-    res = pu.run_lockstep(gpu, ref, 2)
+    res = pu.run_lockstep(gpu, ref, 1)
     for t, (errs, mism, dmis, nfin) in enumerate(res):
         _assert_ints(mism, dmis, f"flip fast step {t + 1}")
     assert max(res[0][0].values()) <= SINGLE_STEP_TOL_FAST, res[0][0]

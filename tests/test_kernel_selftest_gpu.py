@@ -11,4 +11,4 @@ def test_divc_is_ieee_division_for_every_float():
     L = _capi.lib()
     bad = C.c_uint64(12345)
     _capi.check(L.taco_selftest_divc(0, float(np.float32(0.001)), C.byref(bad)), "taco_selftest_divc")
-    assert bad.value == 0, f"{bad.value} (x, C) pairs differ from IEEE x / C"
+    assert bad.value == 0, f"{bad.value} (x, C) pairs differ from IEEE x / C: {L.taco_last_error().decode()}"
