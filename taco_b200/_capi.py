@@ -8,7 +8,7 @@ The library must exist -- there is no CPU fallback; a missing or unloadable .so 
 import ctypes as C
 import os
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtaco_b200.so")
+_LIB_PATH = os.environ.get("TACO_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libtaco_b200.so")
 
 ABI_VERSION = 1
 TASK = {"pos": 0, "rotate": 1, "flip": 2, "mix": 3}

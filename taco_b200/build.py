@@ -14,7 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libtaco_b200.so")
+_MB = os.environ.get("TACO_MIN_BLOCKS")          # tuning builds: libtaco_b200_mb<N>.so next to the default library
+LIB_PATH = os.path.join(LIB_DIR, "libtaco_b200.so" if not _MB else f"libtaco_b200_mb{_MB}.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--threads", "4"]
 UNITS = [
@@ -42,7 +43,7 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     nvcc = _nvcc()
     os.makedirs(LIB_DIR, exist_ok=True)
-    obj_dir = os.path.join(HERE, "build")
+    obj_dir = os.path.join(HERE, "build" if not _MB else f"build_mb{_MB}")
     os.makedirs(obj_dir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "taco_b200.h"))
@@ -52,7 +53,7 @@ def build(force=False, verbose=False):
         o = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + ARCH + COMMON + ([f"-DTACO_MIN_BLOCKS={_MB}"] if _MB else []) + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, pr in procs:
         out, _ = pr.communicate()

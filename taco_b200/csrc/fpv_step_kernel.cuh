@@ -21,6 +21,9 @@
 #include "step_params.h"
 #include "../../include/taco_b200.h"
 
+#ifndef TACO_MIN_BLOCKS
+#define TACO_MIN_BLOCKS 6     // resident CTAs per SM the register allocation targets: 80 regs, 24 warps/SM (measured best of 4/5/6/8)
+#endif
 #ifndef TACO_VARIANT
 #error "define TACO_VARIANT (fast / strict) before including fpv_step_kernel.cuh"
 #endif
@@ -76,7 +79,7 @@ __device__ __forceinline__ void write_rows(const float* __restrict__ in, float* 
 // D planes; when false the rotor polynomial / aero coefficients fold into instruction immediates.
 // SUB: physics sub-steps per simulate call (1 / 2 unrolled; 0 = runtime p.substeps).
 template <int TASK, bool DR, int SUB>
-__global__ void __launch_bounds__(kBlock, 4) fpv_step_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const StepParams p) {
     __shared__ float s_clean[kBlock * kFramePad];
     __shared__ float s_noisy[kBlock * kFramePad];
     __shared__ double s_stats[kNumStats];
