@@ -137,19 +137,38 @@ int taco_env_import_state(TacoEnv* env, const float* in_host);
 /* delayed action read at each control sub-step of the last step: (num_envs, control_freq_inv, 4) f32, host */
 int taco_env_debug_delay(TacoEnv* env, float* out_host);
 
-/* -- actor MLP inference (algorithms/nets_asymmetry.py:23-39,326-346): see taco_actor.h section below */
+/* -- actor MLP inference in the rollout loop: MLP.forward + the actor branch of PPO_ActorCritic.act
+ * (IsaacGymEnvs/algorithms/nets_asymmetry.py:23-39, :326-346) and PPO.spectral_normalize_actors
+ * (IsaacGymEnvs/algorithms/ppo_asymmetry.py:398-404).  Two kernels compute the same function: an FP32 CUDA-core
+ * path (parity) and a tcgen05/TMEM bf16 path (throughput; 1..4 hidden layers, widths multiples of 64 up to 256,
+ * input width <= 256). */
 typedef struct TacoActor TacoActor;
-/* sizes = [in, h1, ..., hL, out] (n_sizes entries); weights/biases are host float32, row-major (out,in) per
- * layer like nn.Linear; spectral projection (ppo_asymmetry.py:398-404) with lipschitz_const > 0 is applied
- * once here ("pre-normalised once per update"). */
+/* sizes = [in, h1, ..., hL, out] (n_sizes entries, out <= 4 = num_acts) */
 int taco_actor_create(int device, const int32_t* sizes, int32_t n_sizes, TacoActor** out);
 int taco_actor_destroy(TacoActor* actor);
+/* weights/biases: host float32, row-major (out,in) per layer like nn.Linear.  With lipschitz_const > 0 every weight
+ * matrix whose largest singular value sigma exceeds it is scaled by lipschitz_const / sigma on the device (power
+ * iteration in double precision) -- the reference does this after each optimiser step, so calling it once per update
+ * gives rollouts pre-normalised weights.  Synchronises the stream (the host buffers are free on return). */
 int taco_actor_load(TacoActor* actor, const float* const* weights_host, const float* const* biases_host,
                     float lipschitz_const, void* stream);
-/* mean = tanh(MLP(obs)); obs_dev (n, in) f32, mean_dev (n, out) f32.  use_tensor_cores = 0 selects the FP32
- * CUDA-core path (parity), 1 the tcgen05 bf16 path. */
+/* largest singular value of every layer as measured by the last taco_actor_load (before scaling): n_layers doubles */
+int taco_actor_sigmas(TacoActor* actor, double* out_host);
+/* the (projected) float32 parameters of one layer, back on the host (either pointer may be NULL) */
+int taco_actor_weights(TacoActor* actor, int32_t layer, float* w_host, float* b_host);
+/* 1 when the tcgen05 path supports this actor's shape on this device */
+int taco_actor_tc_available(TacoActor* actor);
+/* mean = tanh(MLP(obs)); obs_dev (n, in) f32 contiguous, mean_dev (n, out) f32.  use_tensor_cores = 0 selects the FP32
+ * CUDA-core path, 1 the tcgen05 bf16 path (TACO_E_INVALID when unavailable).  Asynchronous on `stream`. */
 int taco_actor_forward(TacoActor* actor, const float* obs_dev, float* mean_dev, int32_t n, int32_t use_tensor_cores,
                        void* stream);
+/* PPO_ActorCritic.act, actor branch: mean as above; action = mean + exp(log_std)^2 * eps (scale_tril = diag(exp(log_std)^2),
+ * nets_asymmetry.py:338), eps ~ N(0,1) from Philox(seed; env_offset + row, step_index, stream 6); clipped =
+ * clamp(action, -1, 1) (ppo_asymmetry.py:310); logp = MultivariateNormal.log_prob(action).  log_std_host: `out` floats on
+ * the host.  clipped_dev / logp_dev may be NULL. */
+int taco_actor_act(TacoActor* actor, const float* obs_dev, int32_t n, const float* log_std_host, int64_t env_offset,
+                   uint64_t seed, uint32_t step_index, float* mean_dev, float* action_dev, float* clipped_dev,
+                   float* logp_dev, int32_t use_tensor_cores, void* stream);
 
 /* -- self-test: exhaustive comparison (all float bit patterns with |x| in [2^-60, 2^60]) of the kernel's 3-instruction
  * division-by-constant against IEEE division, for every divisor the step kernel uses; writes the mismatch count. */

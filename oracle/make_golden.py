@@ -151,6 +151,53 @@ def rewards(ns):
     np.savez(os.path.join(OUT, "rewards.npz"), **{k: np.asarray(t) for k, t in out.items()})
 
 
+def actor(ns):
+    """MLP.forward, PPO_ActorCritic.act (nets_asymmetry.py:23-39,:326-346) and PPO.spectral_normalize_actors
+    (ppo_asymmetry.py:398-404) run from the reference's own classes."""
+    import types
+    import torch.nn as nn
+    torch.manual_seed(2024)
+    hidden = [64, 128]
+    para = {"actor_critic_mlp_dict": {"actor_input_dim": 26, "actor_output_dim": 4, "critic_input_dim": 26 * 5, "critic_output_dim": 1,
+                                      "actor_hidden_sizes": hidden, "critic_hidden_sizes": [32], "activation": nn.ReLU},
+            "use_actor_encoder": False, "use_critic_encoder": False, "share_encoder": False}
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):        # the constructor prints the net structure
+        agent = ns.nets.PPO_ActorCritic(para)
+    lin = [m for m in agent.actor_mlp.layers if isinstance(m, nn.Linear)]
+    with torch.no_grad():                                   # "trained" weights: orthogonal init + drift, so the sigmas differ
+        for i, m in enumerate(lin):
+            m.weight += 0.05 * (i + 1) * torch.randn_like(m.weight) * m.weight.abs().mean() * 4
+            m.bias.uniform_(-0.2, 0.2)
+        agent.log_std.copy_(torch.tensor([-0.5, -0.25, 0.0, 0.1]))
+    n = 96
+    obs = torch.randn(n, 1, 26) * 0.8
+    states = torch.randn(n, 5, 26)
+    out = {}
+    for i, m in enumerate(lin):
+        out[f"w{i}"] = m.weight.detach().clone()
+        out[f"b{i}"] = m.bias.detach().clone()
+    out["obs"] = obs
+    with torch.no_grad():
+        out["mean"] = agent.actor_mlp(obs)
+        torch.manual_seed(77)
+        action, logp, value, mean, log_std = agent.act(obs, states)
+    out["act_action"], out["act_logp"], out["act_mean"], out["log_std"] = action, logp, mean, log_std[0]
+    e = agent.log_std.detach().exp()
+    out["act_eps"] = (action - mean) / (e * e)              # the noise torch drew, recovered for injection into the oracle
+    # spectral projection through the reference's own method (needs only self.agent)
+    lipschitz = 1.2
+    assert ns.ppo is not None, getattr(ns, "ppo_error", None)
+    out["sigma_before"] = torch.stack([torch.linalg.matrix_norm(m.weight.detach(), ord=2) for m in lin])
+    ns.ppo.PPO.spectral_normalize_actors(types.SimpleNamespace(agent=agent), lipschitz_const=lipschitz)
+    for i, m in enumerate(lin):
+        out[f"w{i}_proj"] = m.weight.detach().clone()
+    out["lipschitz"] = torch.tensor(lipschitz)
+    with torch.no_grad():
+        out["mean_proj"] = agent.actor_mlp(obs)
+    np.savez(os.path.join(OUT, "actor.npz"), **{k: np.asarray(t) for k, t in out.items()})
+
+
 def main():
     assert ref_loader.available(), "needs the reference tree (build container only)"
     os.makedirs(OUT, exist_ok=True)
@@ -159,6 +206,7 @@ def main():
     leaf_math(ns)
     dynamics(ns)
     rewards(ns)
+    actor(ns)
     print("golden vectors written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  ", f, os.path.getsize(os.path.join(OUT, f)), "bytes")

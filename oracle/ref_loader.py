@@ -78,6 +78,16 @@ def load():
     ns.task_reward = _load("ref_task_reward_cpu", patched)
     nets = os.path.join(REF, "IsaacGymEnvs", "algorithms", "nets_asymmetry.py")
     ns.nets = _load("ref_nets_asymmetry", nets)
+    # ppo_asymmetry / buffer_asymmetry import each other as `algorithms.*` (ppo_asymmetry.py:16-22, buffer_asymmetry.py:3-6)
+    alg = types.ModuleType("algorithms"); alg.__path__ = [os.path.join(REF, "IsaacGymEnvs", "algorithms")]
+    sys.modules.setdefault("algorithms", alg)
+    sys.modules["algorithms.nets_asymmetry"] = ns.nets
+    ns.buffer = _load("algorithms.buffer_asymmetry", os.path.join(REF, "IsaacGymEnvs", "algorithms", "buffer_asymmetry.py"))
+    try:
+        ns.ppo = _load("algorithms.ppo_asymmetry", os.path.join(REF, "IsaacGymEnvs", "algorithms", "ppo_asymmetry.py"))
+    except Exception as exc:            # tensorboard missing etc.: the PPO class is only needed for spectral_normalize_actors
+        ns.ppo = None
+        ns.ppo_error = exc
     _cache["ns"] = ns
     return ns
 

@@ -77,6 +77,10 @@ def lib():
         "taco_actor_destroy": (C.c_int, [vp]),
         "taco_actor_load": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), f32, vp]),
         "taco_actor_forward": (C.c_int, [vp, vp, vp, i32, i32, vp]),
+        "taco_actor_sigmas": (C.c_int, [vp, vp]),
+        "taco_actor_weights": (C.c_int, [vp, i32, vp, vp]),
+        "taco_actor_tc_available": (C.c_int, [vp]),
+        "taco_actor_act": (C.c_int, [vp, vp, i32, vp, C.c_int64, u64, u32, vp, vp, vp, vp, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError if the symbol is not exported

@@ -1,0 +1,123 @@
+"""Host-side mirror of the actor branch of ``PPO_ActorCritic`` for rollout inference.
+
+Mirrors (IsaacGymEnvs/algorithms/):
+  * ``MLP.forward``                        nets_asymmetry.py:23-39
+  * ``PPO_ActorCritic.act`` (actor branch) nets_asymmetry.py:326-346
+  * ``PPO.spectral_normalize_actors``      ppo_asymmetry.py:398-404  (``load(..., lipschitz_const=c)``)
+
+The math runs in libtaco_b200.so (FP32 CUDA-core kernel, or the tcgen05 bf16 kernel with
+``tensor_cores=True``); torch only provides device memory and the stream.  No CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+class ActorMLP:
+    def __init__(self, input_size, hidden_size, output_size=_capi.NUM_ACTS, device="cuda:0"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA is not available: the actor kernels have no CPU fallback")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"ActorMLP runs on CUDA only (got {device!r})")
+        self.device_id = dev.index if dev.index is not None else 0
+        self.device = f"cuda:{self.device_id}"
+        self.sizes = [int(input_size)] + [int(h) for h in hidden_size] + [int(output_size)]
+        self._lib = _capi.lib()
+        arr = (C.c_int32 * len(self.sizes))(*self.sizes)
+        h = C.c_void_p()
+        _capi.check(self._lib.taco_actor_create(self.device_id, arr, len(self.sizes), C.byref(h)), "taco_actor_create")
+        self._h = h
+        self.log_std = np.zeros(self.sizes[-1], dtype=np.float32)      # nets_asymmetry.py:315: log(1.0) * ones
+
+    @property
+    def n_layers(self):
+        return len(self.sizes) - 1
+
+    @property
+    def tensor_cores_available(self):
+        return bool(self._lib.taco_actor_tc_available(self._h))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device_id).cuda_stream)
+
+    def load(self, weights, biases, lipschitz_const=0.0, log_std=None):
+        """weights[l]: (out, in) like nn.Linear.weight; biases[l]: (out,).  torch tensors or numpy arrays.
+        lipschitz_const > 0 applies the spectral projection on the device, once (call after every update)."""
+        if len(weights) != self.n_layers or len(biases) != self.n_layers:
+            raise ValueError(f"expected {self.n_layers} layers")
+        ws, bs = [], []
+        for l in range(self.n_layers):
+            w = np.ascontiguousarray(weights[l].detach().cpu().numpy() if isinstance(weights[l], torch.Tensor) else weights[l], dtype=np.float32)
+            b = np.ascontiguousarray(biases[l].detach().cpu().numpy() if isinstance(biases[l], torch.Tensor) else biases[l], dtype=np.float32)
+            if w.shape != (self.sizes[l + 1], self.sizes[l]) or b.shape != (self.sizes[l + 1],):
+                raise ValueError(f"layer {l}: expected weight {(self.sizes[l + 1], self.sizes[l])}, bias {(self.sizes[l + 1],)}")
+            ws.append(w); bs.append(b)
+        wp = (C.c_void_p * self.n_layers)(*[w.ctypes.data for w in ws])
+        bp = (C.c_void_p * self.n_layers)(*[b.ctypes.data for b in bs])
+        _capi.check(self._lib.taco_actor_load(self._h, wp, bp, float(lipschitz_const), self._stream()), "taco_actor_load")
+        if log_std is not None:
+            self.log_std = np.ascontiguousarray(log_std.detach().cpu().numpy() if isinstance(log_std, torch.Tensor) else log_std, dtype=np.float32)
+
+    def load_module(self, actor_mlp, log_std=None, lipschitz_const=0.0):
+        """Load from a reference-style ``MLP`` (its ``.layers`` Sequential of Linear / activation modules)."""
+        lin = [m for m in actor_mlp.layers if isinstance(m, torch.nn.Linear)]
+        self.load([m.weight for m in lin], [m.bias for m in lin], lipschitz_const, log_std)
+
+    def sigmas(self):
+        out = np.zeros(self.n_layers, dtype=np.float64)
+        _capi.check(self._lib.taco_actor_sigmas(self._h, out.ctypes.data_as(C.c_void_p)), "taco_actor_sigmas")
+        return out
+
+    def weights(self, layer):
+        w = np.empty((self.sizes[layer + 1], self.sizes[layer]), dtype=np.float32)
+        b = np.empty(self.sizes[layer + 1], dtype=np.float32)
+        _capi.check(self._lib.taco_actor_weights(self._h, layer, w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)), "taco_actor_weights")
+        return w, b
+
+    def _check_obs(self, obs):
+        if obs.device.type != "cuda" or (obs.device.index or 0) != self.device_id:
+            obs = obs.to(self.device)
+        obs = obs.float().contiguous().view(obs.size(0), -1)          # nets_asymmetry.py:38
+        if obs.size(1) != self.sizes[0]:
+            raise ValueError(f"actor input must flatten to {self.sizes[0]} features, got {obs.size(1)}")
+        return obs
+
+    def forward(self, obs, tensor_cores=False, out=None):
+        """mean = tanh(MLP(obs)); obs (N, len_obs, 26) or (N, in) on the actor's device."""
+        obs = self._check_obs(obs)
+        n = obs.size(0)
+        if out is None:
+            out = torch.empty(n, self.sizes[-1], dtype=torch.float32, device=self.device)
+        _capi.check(self._lib.taco_actor_forward(self._h, C.c_void_p(obs.data_ptr()), C.c_void_p(out.data_ptr()), n,
+                                                 1 if tensor_cores else 0, self._stream()), "taco_actor_forward")
+        return out
+
+    def act(self, obs, step_index, seed=0, env_offset=0, tensor_cores=False):
+        """Returns (action, clipped_action, log_p, mean): the sample of nets_asymmetry.py:336-346 with Philox noise and
+        the clip of ppo_asymmetry.py:310."""
+        obs = self._check_obs(obs)
+        n, k = obs.size(0), self.sizes[-1]
+        mean = torch.empty(n, k, dtype=torch.float32, device=self.device)
+        action = torch.empty_like(mean)
+        clipped = torch.empty_like(mean)
+        logp = torch.empty(n, dtype=torch.float32, device=self.device)
+        _capi.check(self._lib.taco_actor_act(self._h, C.c_void_p(obs.data_ptr()), n, self.log_std.ctypes.data_as(C.c_void_p),
+                                             int(env_offset), int(seed) & 0xFFFFFFFFFFFFFFFF, int(step_index) & 0xFFFFFFFF,
+                                             C.c_void_p(mean.data_ptr()), C.c_void_p(action.data_ptr()), C.c_void_p(clipped.data_ptr()),
+                                             C.c_void_p(logp.data_ptr()), 1 if tensor_cores else 0, self._stream()), "taco_actor_act")
+        return action, clipped, logp, mean
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.taco_actor_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,358 @@
+// Actor MLP on the 5th-generation tensor cores (tcgen05 + TMEM), one persistent CTA per SM.
+//
+// Replaces, for rollout inference, MLP.forward + the actor branch of PPO_ActorCritic.act
+// (IsaacGymEnvs/algorithms/nets_asymmetry.py:23-39, :326-346):  mean = tanh(W_L relu(... relu(W_1 x + b_1) ...) + b_L).
+//
+// Shape of the work: a tile is 128 envs (rows = TMEM lanes).  Every hidden layer is one
+// D[128 x N] = A[128 x K] * W[N x K]^T accumulated in TMEM (fp32) by tcgen05.mma (bf16 operands, M=128, N<=256,
+// K=16 per instruction).  A (the activations) lives in shared memory in the canonical K-major SWIZZLE_128B layout and is
+// rewritten in place by the epilogue warps (TMEM -> registers -> +bias, ReLU -> bf16 -> smem); W streams from L2 through
+// a 4-stage ring of 32 KB K-chunks filled by the bulk async-copy engine (cp.async.bulk + mbarrier complete_tx) from
+// images that taco_actor_load pre-swizzled once per update.  The 4-wide output layer, tanh and the optional Gaussian
+// sampling are CUDA-core work in the last epilogue (a 4-column GEMM is not a dense contraction).
+//
+// Warp roles (192 threads): warp 0 = weight producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..5 = epilogue (thread <-> TMEM lane <-> env row).
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "philox.cuh"
+
+namespace taco {
+namespace actor {
+
+constexpr int kTileM = 128;                    // envs per tile = TMEM lanes
+constexpr int kKC = 64;                        // bf16 per K chunk: one 128-byte swizzle row
+constexpr int kMaxN = 256;                     // widest hidden layer (tcgen05 N limit)
+constexpr int kStages = 4;
+constexpr int kStageBytes = kMaxN * 128;       // 32 KB
+constexpr int kAChunkBytes = kTileM * 128;     // 16 KB: 128 rows x 64 bf16
+constexpr int kABytes = kAChunkBytes * (kMaxN / kKC);   // 64 KB
+constexpr int kMaxHidden = 4;
+constexpr int kOutPad = 4;                     // output layer width on the CUDA-core tail (num_acts = 4)
+constexpr int kTcThreads = 192;
+constexpr uint32_t STREAM_ACTOR = 6;           // Philox stream of the action noise
+
+struct TcLayer {
+    int n;               // output width of the layer (multiple of 64, <= 256)
+    int kchunks;         // ceil(K / 64)
+    uint32_t img_off;    // byte offset of the layer's first chunk image; chunk c is at img_off + c * n * 128
+};
+
+struct SampleParams {    // PPO_ActorCritic.act sampling (nets_asymmetry.py:336-346); enabled when action != nullptr
+    float* action;       // (n, out) mean + std * eps
+    float* clipped;      // (n, out) clamp(action, -1, 1)   (ppo_asymmetry.py:310)
+    float* logp;         // (n)
+    float std_[kOutPad]; // exp(log_std)^2: scale_tril = diag(exp(log_std)^2)  (nets_asymmetry.py:338)
+    float logp_const;    // -sum(log std) - out/2 * log(2 pi)
+    long long env_offset;
+    uint32_t seed_lo, seed_hi, step_index;
+};
+
+struct TcParams {
+    const float* obs;    // (n_rows, in_dim) f32
+    float* mean;         // (n_rows, out_dim) f32
+    int in_dim, out_dim, n_rows, num_tiles, n_hidden;
+    const uint8_t* wimg; // pre-swizzled bf16 chunk images of the hidden layers
+    const float* bias;   // [kMaxHidden][kMaxN] f32
+    const float* w_out;  // [kMaxN][kOutPad] f32 (transposed, zero padded)
+    const float* b_out;  // [kOutPad]
+    TcLayer layer[kMaxHidden];
+    SampleParams sp;
+};
+
+constexpr int kSmemBias = kMaxHidden * kMaxN * 4;          // 4 KB
+constexpr int kSmemWout = kMaxN * kOutPad * 4;             // 4 KB
+constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kABytes + kSmemBias + kSmemWout + 256;
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// bulk async copy global -> shared (the TMA engine, 1-D form): completes `bytes` on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: 8-row x 128-byte atoms, consecutive atoms 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout=2 [61,64))
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor, kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, both K-major, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued tcgen05.mma of this thread arrive (once) on the mbarrier when they have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t <-> lane base + t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);     // .x (low half) = lo
+    return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// byte offset of the 16-byte chunk c16 (0..7) of row r inside a [rows x 64 bf16] SWIZZLE_128B block
+__device__ __forceinline__ uint32_t sw128_off(int r, int c16) { return (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4)); }
+
+// tanh output + optional sampling, shared by the tensor-core and the FP32 kernels (one thread = one env row)
+__device__ __forceinline__ void actor_tail(const float* pre, int out_dim, long long row, float* mean, const SampleParams& sp) {
+    float mu[kOutPad];
+#pragma unroll
+    for (int o = 0; o < kOutPad; ++o) mu[o] = tanhf(pre[o]);
+    if (out_dim == 4) {
+        *reinterpret_cast<float4*>(mean + row * 4) = make_float4(mu[0], mu[1], mu[2], mu[3]);
+    } else {
+        for (int o = 0; o < out_dim; ++o) mean[row * out_dim + o] = mu[o];
+    }
+    if (sp.action) {
+        const uint4 r = philox4x32_10((uint32_t)(sp.env_offset + row), sp.step_index, 0, STREAM_ACTOR, sp.seed_lo, sp.seed_hi);
+        float z[4];
+        box_muller(r.x, r.y, z[0], z[1]);
+        box_muller(r.z, r.w, z[2], z[3]);
+        float lp = sp.logp_const;
+        for (int o = 0; o < out_dim; ++o) {
+            const float a = mu[o] + sp.std_[o] * z[o];
+            sp.action[row * out_dim + o] = a;
+            if (sp.clipped) sp.clipped[row * out_dim + o] = fminf(fmaxf(a, -1.0f), 1.0f);
+            lp += -0.5f * (z[o] * z[o]);
+        }
+        if (sp.logp) sp.logp[row] = lp;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B atoms need 1024-byte alignment
+    uint8_t* sm = smem_raw + (base - raw);
+    const uint32_t s_stage = base;                                   // kStages x 32 KB weight ring
+    const uint32_t s_a = base + kStages * kStageBytes;               // 64 KB activations (4 K-chunk blocks of 16 KB)
+    uint8_t* a_ptr = sm + kStages * kStageBytes;
+    float* s_bias = reinterpret_cast<float*>(a_ptr + kABytes);
+    float* s_wout = s_bias + kMaxHidden * kMaxN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_wout + kMaxN * kOutPad);
+    const uint32_t bar_full = smem_u32(bars);                        // [kStages] producer -> MMA
+    const uint32_t bar_empty = bar_full + 8 * kStages;               // [kStages] MMA -> producer
+    const uint32_t bar_a = bar_empty + 8 * kStages;                  // epilogue -> MMA: A of the next layer is in smem, D is drained
+    const uint32_t bar_d = bar_a + 8;                                // MMA -> epilogue: D of the layer is complete
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < kMaxHidden * kMaxN; i += kTcThreads) s_bias[i] = p.bias[i];
+    for (int i = threadIdx.x; i < kMaxN * kOutPad; i += kTcThreads) s_wout[i] = p.w_out[i];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_a, kTileM);
+        mbar_init(bar_d, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(s_tmem), kMaxN);              // 256 fp32 columns x 128 lanes
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *s_tmem;
+
+    if (warp == 0) {
+        // ===================== weight producer: stream the K-chunk images of every layer, every tile
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                for (int l = 0; l < p.n_hidden; ++l) {
+                    const uint32_t bytes = (uint32_t)p.layer[l].n * 128u;
+                    for (int c = 0; c < p.layer[l].kchunks; ++c) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        mbar_arrive_expect_tx(bar_full + 8 * stage, bytes);
+                        bulk_g2s(s_stage + stage * kStageBytes, p.wimg + p.layer[l].img_off + (size_t)c * bytes, bytes, bar_full + 8 * stage);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, a_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                for (int l = 0; l < p.n_hidden; ++l) {
+                    const uint32_t idesc = umma_idesc_bf16(kTileM, p.layer[l].n);
+                    mbar_wait(bar_a, a_phase); a_phase ^= 1;          // activations of layer l staged, previous D drained
+                    tc_fence_after();
+                    for (int c = 0; c < p.layer[l].kchunks; ++c) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint64_t adesc = umma_desc_sw128(s_a + c * kAChunkBytes);
+                        const uint64_t bdesc = umma_desc_sw128(s_stage + stage * kStageBytes);
+#pragma unroll
+                        for (int k = 0; k < kKC / 16; ++k)            // 16 bf16 = 32 bytes along K inside the swizzle atom
+                            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((c | k) != 0));
+                        umma_commit(bar_empty + 8 * stage);           // ring slot is free once these MMAs have read it
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(bar_d);
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps: thread <-> TMEM lane <-> env row
+        const int r = ((warp & 3) << 5) | lane;                       // a warp may only touch TMEM lanes 32*(warp%4)..+31
+        const uint32_t t_lane = tmem_d + ((uint32_t)((warp & 3) << 5) << 16);
+        uint32_t d_phase = 0;
+        const int kc0 = p.layer[0].kchunks;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const long long row = (long long)tile * kTileM + r;
+            const bool valid = row < p.n_rows;
+            // ---- stage the observation row as bf16, K padded with zeros to kc0 * 64
+            {
+                const float* x = p.obs + row * p.in_dim;
+                for (int c = 0; c < kc0 * 8; ++c) {
+                    float f[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = c * 8 + j;
+                        f[j] = (valid && k < p.in_dim) ? __ldg(x + k) : 0.0f;
+                    }
+                    const uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+                    *reinterpret_cast<uint4*>(a_ptr + (c >> 3) * kAChunkBytes + sw128_off(r, c & 7)) = pk;
+                }
+                fence_proxy_async_smem();                             // generic-proxy writes -> visible to the tensor core (async proxy)
+                tc_fence_before();
+                mbar_arrive(bar_a);
+            }
+            for (int l = 0; l < p.n_hidden; ++l) {
+                const int n = p.layer[l].n;
+                const float* bl = s_bias + l * kMaxN;
+                mbar_wait(bar_d, d_phase); d_phase ^= 1;
+                tc_fence_after();
+                if (l + 1 < p.n_hidden) {
+                    // hidden -> hidden: +bias, ReLU, bf16, back into A (all MMAs that read A have completed: bar_d)
+                    for (int j0 = 0; j0 < n; j0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(t_lane + (uint32_t)j0, v);
+                        tmem_ld_wait();
+                        uint8_t* blk = a_ptr + (j0 >> 6) * kAChunkBytes;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float h[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) h[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + bl[j0 + q * 8 + j], 0.0f);
+                            const uint4 pk = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+                            *reinterpret_cast<uint4*>(blk + sw128_off(r, ((j0 & 63) >> 3) + q)) = pk;
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    tc_fence_before();
+                    mbar_arrive(bar_a);
+                } else {
+                    // last hidden layer: +bias, ReLU, then the 4-wide output layer on the CUDA cores (fp32)
+                    float acc[kOutPad] = {0.f, 0.f, 0.f, 0.f};
+                    for (int j0 = 0; j0 < n; j0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(t_lane + (uint32_t)j0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float h = fmaxf(__uint_as_float(v[j]) + bl[j0 + j], 0.0f);
+                            const float4 w = *reinterpret_cast<const float4*>(s_wout + (j0 + j) * kOutPad);
+                            acc[0] = fmaf(h, w.x, acc[0]); acc[1] = fmaf(h, w.y, acc[1]);
+                            acc[2] = fmaf(h, w.z, acc[2]); acc[3] = fmaf(h, w.w, acc[3]);
+                        }
+                    }
+                    tc_fence_before();                                 // D is drained; the arrive on bar_a of the next tile publishes it
+                    if (valid) {
+#pragma unroll
+                        for (int o = 0; o < kOutPad; ++o) acc[o] += __ldg(p.b_out + o);
+                        actor_tail(acc, p.out_dim, row, p.mean, p.sp);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_d, kMaxN);
+    }
+}
+
+// fp32 (out, in) row-major weights -> bf16 K-chunk images in the SWIZZLE_128B K-major layout the kernel copies verbatim:
+// chunk c holds W[:, 64c .. 64c+63] as n rows of 128 bytes; the 16-byte piece q of row r sits at r*128 + ((q ^ (r&7)) << 4).
+__global__ void pack_weights_kernel(const float* __restrict__ w, int n, int k, uint8_t* __restrict__ img) {
+    const int kchunks = (k + kKC - 1) / kKC;
+    const int total = kchunks * n * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int q = i & 7, r = (i >> 3) % n, c = (i >> 3) / n;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int kk = c * kKC + q * 8 + j;
+            f[j] = kk < k ? w[(size_t)r * k + kk] : 0.0f;
+        }
+        const uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        *reinterpret_cast<uint4*>(img + (size_t)c * n * 128 + sw128_off(r, q)) = pk;
+    }
+}
+
+}  // namespace actor
+}  // namespace taco

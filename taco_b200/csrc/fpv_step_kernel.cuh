@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
     __shared__ double s_stats[kNumStats];
 
     const int tid = threadIdx.x;
-    const int i = blockIdx.x * kBlock + tid;
+    const int blk = blockIdx.x + p.block0;                      // a launch covers CTAs [block0, block0 + gridDim.x): chunked host pipeline
+    const int i = blk * kBlock + tid;
     const bool valid = i < p.n;
     const uint32_t flags = p.flags;
     const bool obs_noise = (flags & TACO_F_OBSERVATION_NOISE) != 0;
@@ -597,15 +598,15 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
     __syncthreads();   // frames + stats visible
     if (tid < 7) {
         const double v = s_stats[tid];
-        if (v != 0.0) atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * kStatStride + tid, v);
+        if (v != 0.0) atomicAdd(p.stats + (size_t)(blk % kStatSlots) * kStatStride + tid, v);
     } else if (tid == 7) {
-        const int nv = min(kBlock, p.n - blockIdx.x * kBlock);
-        atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * kStatStride + 7, (double)nv);
+        const int nv = min(kBlock, p.n - blk * kBlock);
+        atomicAdd(p.stats + (size_t)(blk % kStatSlots) * kStatStride + 7, (double)nv);
     }
 
     // ---------------------------------------------------------------------- history shift + newest frame (:392,:413)
     // out[e][f][:] = in[e][f+1][:] for f < L-1, newest frame last; ping-pong buffers, so no in-place hazard.
-    const size_t blk_env0 = (size_t)blockIdx.x * kBlock;
+    const size_t blk_env0 = (size_t)blk * kBlock;
     if (p.len_states == 5) write_rows<5>(p.states_in, p.states_out, s_clean, 5, blk_env0, tid);
     else write_rows<0>(p.states_in, p.states_out, s_clean, p.len_states, blk_env0, tid);
     const float* sf = obs_noise ? s_noisy : s_clean;
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
 
 template <int TASK>
 static void launch_task(const StepParams& p, cudaStream_t stream) {
-    const int grid = p.n_pad / kBlock;
+    const int grid = p.nblocks > 0 ? p.nblocks : p.n_pad / kBlock - p.block0;
     if (p.has_dr) {
         if (p.substeps == 2) fpv_step_kernel<TASK, true, 2><<<grid, kBlock, 0, stream>>>(p);
         else if (p.substeps == 1) fpv_step_kernel<TASK, true, 1><<<grid, kBlock, 0, stream>>>(p);

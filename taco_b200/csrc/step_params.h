@@ -19,6 +19,7 @@ constexpr uint32_t QM_HEAD_SHIFT = 0, QM_N_SHIFT = 4, QM_LEN_SHIFT = 9, QM_OVF_S
 
 struct StepParams {
     int n, n_pad;
+    int block0, nblocks;           // CTA range of this launch (nblocks = 0: all remaining CTAs)
     long long env_offset;
     long long mix_n1, mix_n2;      // global task-group boundaries (fpv_asymmetry.py:924-926)
     int task_mode, len_obs, len_states, max_len, cfi, substeps, delay_time;

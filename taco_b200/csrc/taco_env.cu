@@ -20,7 +20,7 @@
 namespace taco {
 
 static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define TACO_CUDA(expr)                                                                          \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \
@@ -51,6 +51,11 @@ struct TacoEnv {
     float* export_stage = nullptr;     // n * TACO_STATE_WORDS floats, device
     float4* dbg_delay = nullptr;
     uint32_t step_index = 0;
+    // host-buffer pipeline (taco_env_step_host): copy-in / kernel / copy-out of successive env chunks overlap
+    static constexpr int kMaxChunks = 16;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_begin = nullptr, ev_end = nullptr;
+    bool pipe_ready = false;
 };
 
 namespace taco {
@@ -334,6 +339,11 @@ int taco_env_create(const TacoCfg* cfg, int device, TacoEnv** out) {
 int taco_env_destroy(TacoEnv* env) {
     if (!env) return TACO_OK;
     DeviceGuard guard(env->device);
+    if (env->pipe_ready) {
+        cudaStreamDestroy(env->s_h2d); cudaStreamDestroy(env->s_d2h);
+        for (int c = 0; c < TacoEnv::kMaxChunks; ++c) { cudaEventDestroy(env->ev_h2d[c]); cudaEventDestroy(env->ev_k[c]); }
+        cudaEventDestroy(env->ev_begin); cudaEventDestroy(env->ev_end);
+    }
     if (env->export_stage) cudaFree(env->export_stage);
     if (env->arena) cudaFree(env->arena);
     delete env;
@@ -371,18 +381,70 @@ int taco_env_step(TacoEnv* env, const float* actions_dev, void* stream) {
     return TACO_OK;
 }
 
+static int pipe_init(TacoEnv* env) {
+    if (env->pipe_ready) return TACO_OK;
+    TACO_CUDA(cudaStreamCreateWithFlags(&env->s_h2d, cudaStreamNonBlocking));
+    TACO_CUDA(cudaStreamCreateWithFlags(&env->s_d2h, cudaStreamNonBlocking));
+    for (int c = 0; c < TacoEnv::kMaxChunks; ++c) {
+        TACO_CUDA(cudaEventCreateWithFlags(&env->ev_h2d[c], cudaEventDisableTiming));
+        TACO_CUDA(cudaEventCreateWithFlags(&env->ev_k[c], cudaEventDisableTiming));
+    }
+    TACO_CUDA(cudaEventCreateWithFlags(&env->ev_begin, cudaEventDisableTiming));
+    TACO_CUDA(cudaEventCreateWithFlags(&env->ev_end, cudaEventDisableTiming));
+    env->pipe_ready = true;
+    return TACO_OK;
+}
+
+// The step through HOST buffers.  Envs are independent, so the shard is cut into chunks of whole CTAs and the three
+// legs of successive chunks overlap: chunk c+1's actions cross PCIe while chunk c steps and chunk c-1's results return
+// (H2D and D2H use opposite directions of the link).  The kernel chunks run on the caller's stream, in order.
 int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host, int64_t* reset_host, uint8_t* time_outs_host,
                        void* stream) {
     if (!env || !actions_host) return fail(TACO_E_INVALID, "taco_env_step_host: null argument");
     DeviceGuard guard(env->device);
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t n = (size_t)env->n;
-    TACO_CUDA(cudaMemcpyAsync(env->actions_stage, actions_host, n * 4 * sizeof(float), cudaMemcpyHostToDevice, s));
-    int rc = taco_env_step(env, (const float*)env->actions_stage, stream);
+    int rc = pipe_init(env);
     if (rc != TACO_OK) return rc;
-    if (rew_host) TACO_CUDA(cudaMemcpyAsync(rew_host, env->p.rew, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (reset_host) TACO_CUDA(cudaMemcpyAsync(reset_host, env->p.reset_buf, n * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    if (time_outs_host) TACO_CUDA(cudaMemcpyAsync(time_outs_host, env->p.time_outs, n, cudaMemcpyDeviceToHost, s));
+    StepParams& p = env->p;
+    const int total_blocks = env->n_pad / kBlock;
+    // chunk = at least 64 Ki envs (4 waves of CTAs), at most kMaxChunks chunks
+    int nchunks = total_blocks / 512;
+    if (nchunks < 1) nchunks = 1;
+    if (nchunks > TacoEnv::kMaxChunks) nchunks = TacoEnv::kMaxChunks;
+    const int per = (total_blocks + nchunks - 1) / nchunks;
+    const int nxt = env->cur ^ 1;
+    p.actions = (const float4*)env->actions_stage;
+    p.obs_in = env->obs_ab[env->cur]; p.obs_out = env->obs_ab[nxt];
+    p.states_in = env->states_ab[env->cur]; p.states_out = env->states_ab[nxt];
+    p.step_index = env->step_index;
+    const bool strict = (env->cfg.flags & TACO_F_STRICT_FP) != 0;
+    TACO_CUDA(cudaEventRecord(env->ev_begin, s));                    // work already queued on the caller's stream comes first
+    TACO_CUDA(cudaStreamWaitEvent(env->s_h2d, env->ev_begin, 0));
+    for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * per, b1 = (b0 + per < total_blocks) ? b0 + per : total_blocks;
+        if (b0 >= b1) { nchunks = c; break; }
+        const size_t e0 = (size_t)b0 * kBlock;
+        const size_t e1 = ((size_t)b1 * kBlock < (size_t)env->n) ? (size_t)b1 * kBlock : (size_t)env->n;
+        const size_t cnt = e1 - e0;
+        TACO_CUDA(cudaMemcpyAsync(env->actions_stage + e0, actions_host + e0 * 4, cnt * 4 * sizeof(float), cudaMemcpyHostToDevice, env->s_h2d));
+        TACO_CUDA(cudaEventRecord(env->ev_h2d[c], env->s_h2d));
+        TACO_CUDA(cudaStreamWaitEvent(s, env->ev_h2d[c], 0));
+        p.block0 = b0; p.nblocks = b1 - b0;
+        if (strict) launch_fpv_step_strict(p, s); else launch_fpv_step_fast(p, s);
+        TACO_CUDA(cudaGetLastError());
+        if (rew_host || reset_host || time_outs_host) {
+            TACO_CUDA(cudaEventRecord(env->ev_k[c], s));
+            TACO_CUDA(cudaStreamWaitEvent(env->s_d2h, env->ev_k[c], 0));
+            if (rew_host) TACO_CUDA(cudaMemcpyAsync(rew_host + e0, p.rew + e0, cnt * sizeof(float), cudaMemcpyDeviceToHost, env->s_d2h));
+            if (reset_host) TACO_CUDA(cudaMemcpyAsync(reset_host + e0, p.reset_buf + e0, cnt * sizeof(int64_t), cudaMemcpyDeviceToHost, env->s_d2h));
+            if (time_outs_host) TACO_CUDA(cudaMemcpyAsync(time_outs_host + e0, p.time_outs + e0, cnt, cudaMemcpyDeviceToHost, env->s_d2h));
+        }
+    }
+    p.block0 = 0; p.nblocks = 0;
+    env->cur = nxt;
+    env->step_index += 1;
+    TACO_CUDA(cudaEventRecord(env->ev_end, env->s_d2h));
+    TACO_CUDA(cudaStreamWaitEvent(s, env->ev_end, 0));               // the caller's stream also orders after the copies
     TACO_CUDA(cudaStreamSynchronize(s));
     return TACO_OK;
 }

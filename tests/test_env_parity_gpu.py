@@ -160,13 +160,14 @@ def test_shard_invariance_single_gpu():
     full.close(); shard.close()
 
 
-def test_host_buffer_entry_point_matches_device_path():
+@pytest.mark.parametrize("n", [3000, 200_003])     # one chunk / three pipelined chunks; neither a multiple of 128 (tail block)
+def test_host_buffer_entry_point_matches_device_path(n):
     import taco_b200
     from taco_b200 import make_cfg
-    a_env = taco_b200.FpvVecTask(make_cfg("flip", 3000), "cuda:0", "cuda:0", -1, True, seed=3)     # not a multiple of 128: tail block
-    b_env = taco_b200.FpvVecTask(make_cfg("flip", 3000), "cuda:0", "cuda:0", -1, True, seed=3)
-    h_rew = torch.empty(3000).pin_memory(); h_reset = torch.empty(3000, dtype=torch.int64).pin_memory()
-    h_tout = torch.empty(3000, dtype=torch.uint8).pin_memory()
+    a_env = taco_b200.FpvVecTask(make_cfg("flip", n), "cuda:0", "cuda:0", -1, True, seed=3)
+    b_env = taco_b200.FpvVecTask(make_cfg("flip", n), "cuda:0", "cuda:0", -1, True, seed=3)
+    h_rew = torch.empty(n).pin_memory(); h_reset = torch.empty(n, dtype=torch.int64).pin_memory()
+    h_tout = torch.empty(n, dtype=torch.uint8).pin_memory()
     for t in range(5):
         act = a_env.random_actions(t)
         o, r, x, e = a_env.step(act)
@@ -174,6 +175,7 @@ def test_host_buffer_entry_point_matches_device_path():
         assert torch.equal(r.cpu(), h_rew) and torch.equal(x.cpu(), h_reset)
         assert torch.equal(e["time_outs"].cpu().to(torch.uint8), h_tout)
         assert torch.equal(o["states"], b_env.states_buf)
+    assert torch.equal(a_env.stats(), b_env.stats())
     a_env.close(); b_env.close()
 
 
