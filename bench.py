@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-small", action="store_true")
+    ap.add_argument("--no-actor", action="store_true", help="skip the BASELINE config 3 point (mix task + actor MLP in the rollout loop)")
+    ap.add_argument("--actor-envs", type=int, default=262144)
+    ap.add_argument("--actor-hidden", default="256,256,256", help="actor hidden sizes (not pinned by the reference: the YAML is missing; our stated default)")
     return ap.parse_args()
 
 
@@ -184,6 +187,68 @@ def time_steps(env, actions, steps, torch, dist, world):
     return ms, stats
 
 
+def _timed(torch, fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def actor_rollout_point(torch, taco_b200, dev, n, hidden, strict_fp, peaks, iters=50):
+    """BASELINE config 3: mix task, n envs, spectral-normalised actor MLP inference in the rollout loop
+    (obs -> actor.act -> clipped action -> env.step), random-init policy (orthogonal, gains sqrt2 / 0.01,
+    nets_asymmetry.py:41-55), weights projected once (lipschitz 4, ppo_asymmetry.py:398-404)."""
+    sizes = [26] + list(hidden) + [4]
+    gen = torch.Generator().manual_seed(SEED)
+    ws, bs = [], []
+    for l in range(len(sizes) - 1):
+        w = torch.empty(sizes[l + 1], sizes[l])
+        torch.nn.init.orthogonal_(w, gain=(2 ** 0.5 if l + 2 < len(sizes) else 0.01), generator=gen)
+        ws.append(w)
+        bs.append(torch.zeros(sizes[l + 1]))
+    actor = taco_b200.ActorMLP(26, list(hidden), 4, device=dev)
+    actor.load(ws, bs, lipschitz_const=4.0)
+    env = taco_b200.FpvVecTask(taco_b200.make_cfg("mix", n), dev, dev, -1, True, seed=SEED, strict_fp=strict_fp)
+    acts = [env.random_actions(t) for t in range(4)]
+    for t in range(5):
+        env.step(acts[t % 4])
+    obs = env.obs_buf.clone()
+    mean = torch.empty(n, 4, device=dev)
+    tc = actor.tensor_cores_available
+    ms_fp32 = _timed(torch, lambda: actor.forward(obs, tensor_cores=False, out=mean), max(iters // 5, 5))
+    ms_tc = _timed(torch, lambda: actor.forward(obs, tensor_cores=True, out=mean), iters) if tc else None
+    k = [0]
+
+    def env_only():
+        env.step(acts[k[0] % 4]); k[0] += 1
+
+    def loop():
+        _, clipped, _, _ = actor.act(env.obs_buf, k[0], seed=SEED, tensor_cores=tc)
+        env.step(clipped); k[0] += 1
+
+    ms_env = _timed(torch, env_only, iters)
+    ms_loop = _timed(torch, loop, iters)
+    flops = 2.0 * sum(sizes[i] * sizes[i + 1] for i in range(len(sizes) - 1))        # per env, SURVEY.md section 8(d)
+    out = {"workload": f"mix task, {n} envs, actor {'x'.join(map(str, sizes))} (hidden sizes are OUR stated default: the reference YAML is missing), "
+                       "random-init policy, spectral projection c=4 once per update, act -> clip -> step every step",
+           "value": n / (ms_loop * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_loop, "env_step_ms": ms_env,
+           "actor_fp32_ms": ms_fp32, "actor_tc_ms": ms_tc, "actor_flops_per_env": flops, "gpu_launches_per_step": 2}
+    if ms_tc:
+        ach = flops * n / (ms_tc * 1e-3) / 1e12
+        peak = float(peaks.get("bf16_tflops", 1590.0))
+        out["actor_roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                                 "peak_source": "measured burst (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "fallback (B200_PROFILING.md)",
+                                 "kernel": "actor_tc_kernel", "speedup_vs_fp32_kernel": ms_fp32 / ms_tc}
+    env.close(); actor.close()
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -259,10 +324,15 @@ def main():
         small = {"workload": f"{args.task}, 4096 envs (BASELINE config 2), L2-resident, launch-bound", "value": 4096 * 200 / (ms_s * 1e-3),
                  "unit": "env-steps/s", "us_per_step": ms_s / 200 * 1e3}
         env_s.close()
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    actor_pt = None
+    if not args.no_actor and world == 1:
+        env.close()
+        actor_pt = actor_rollout_point(torch, taco_b200, dev, args.actor_envs, [int(x) for x in args.actor_hidden.split(",")], not args.fast_fp, peaks)
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        if "hbm_gbs" in peaks:
+            peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         algo = ALGO_BYTES_DR if args.dr else ALGO_BYTES_NO_DR
@@ -296,6 +366,8 @@ def main():
             line["e2e"] = e2e
         if small is not None:
             line["config2_4096_envs"] = small
+        if actor_pt is not None:
+            line["config3_mix_actor"] = actor_pt
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.task, args.cpu_envs, args.cpu_steps, 3, args.dr).items() if k != "ms_per_step"}
         print(json.dumps(line), flush=True)

@@ -144,7 +144,11 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
         const float d = p.difficulty;
         const bool at500 = (progress == 500);                   // fpv_asymmetry.py:152,597 (before counters clear)
 
-        uint32_t q_head = (qm >> QM_HEAD_SHIFT) & 15u, q_n = (qm >> QM_N_SHIFT) & 31u;
+        // pending-action runs live in a ring indexed by the RL step of the LAUNCH (slot = step_index & 15, the same for
+        // every env of the launch -> coalesced planes however desynchronised the episodes are); an env's live runs are
+        // the last q_n slots, so the head is implied
+        const uint32_t tslot = t_rl & 15u;
+        uint32_t q_n = (qm >> QM_N_SHIFT) & 31u;
         int q_len = (int)((qm >> QM_LEN_SHIFT) & 2047u);
         uint32_t q_ovf = (qm >> QM_OVF_SHIFT) & 1u;
 
@@ -247,10 +251,11 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
             // pending-action queue (:574-578): `delay` slots of zero action
             q_len = p.delay_time;
             if (flags & TACO_F_RAMDOM_DELAY_TIME) q_len = max(p.delay_time - round_normal(b1.w, 3), 0);
-            q_head = 0; q_n = 0; q_ovf = 0;
+            q_n = 0; q_ovf = 0;
             if (q_len > 0) {
-                p.qact[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                p.qend[i] = (uint16_t)q_len;
+                const uint32_t zslot = (tslot + 15u) & 15u;
+                p.qact[(size_t)zslot * p.n_pad + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                p.qend[(size_t)zslot * p.n_pad + i] = (uint16_t)q_len;
                 q_n = 1;
             }
             // target (:523-548)
@@ -281,17 +286,16 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
             T = 10 - round_normal(db.x, 1);
         }
         const int clk = 10 * progress;                              // absolute slot clock of buffer position 0
-        if (q_len + T <= 100 && q_n < (uint32_t)kQueueCap) {
-            const uint32_t slot = (q_head + q_n) & 15u;
-            p.qact[(size_t)slot * p.n_pad + i] = act;
-            p.qend[(size_t)slot * p.n_pad + i] = (uint16_t)(clk + q_len + T);
-            q_n += 1;
-        } else {
+        if (q_len + T > 100 || q_n >= (uint32_t)kQueueCap) {
             q_ovf = 1;      // reference truncates the write at slot 100 (:329): outside delay_time_max, flagged + counted
+            if (q_n >= (uint32_t)kQueueCap) q_n = kQueueCap - 1;   // (flagged envs only) the oldest run is overwritten
         }
+        p.qact[(size_t)tslot * p.n_pad + i] = act;
+        p.qend[(size_t)tslot * p.n_pad + i] = (uint16_t)min(clk + q_len + T, 65535);
+        q_n += 1;
         q_len += T;
-        // head run
-        uint32_t q_cur = q_head, q_left = q_n;
+        // head run = the oldest of the last q_n slots
+        uint32_t q_cur = (tslot + 17u - q_n) & 15u, q_left = q_n;
         float4 dact = make_float4(0.f, 0.f, 0.f, 0.f);
         int run_end = 0;
         if (q_left > 0) {
@@ -449,10 +453,10 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
         progress += 1;
         {   // shift the delay buffer by 10 slots = advance the slot clock; drop exhausted runs
             const int clk2 = clk + 10;
-            q_n = q_left; q_head = q_cur;
+            q_n = q_left;
             while (q_n > 0 && run_end <= clk2) {
-                q_head = (q_head + 1) & 15u; q_n -= 1;
-                if (q_n > 0) run_end = p.qend[(size_t)q_head * p.n_pad + i];
+                q_cur = (q_cur + 1) & 15u; q_n -= 1;
+                if (q_n > 0) run_end = p.qend[(size_t)q_cur * p.n_pad + i];
             }
             q_len = max(q_len - 10, 0);
         }
@@ -575,7 +579,7 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
         p.S[6][i] = make_float4(pe[0], pe[1], pe[2], cmd);
         p.S[7][i] = make_float4(bu1, bec, bt, ep_ret);
         p.progress[i] = progress;
-        p.qmeta[i] = (q_head << QM_HEAD_SHIFT) | (q_n << QM_N_SHIFT) | ((uint32_t)min(q_len, 2047) << QM_LEN_SHIFT) | (q_ovf << QM_OVF_SHIFT);
+        p.qmeta[i] = (q_n << QM_N_SHIFT) | ((uint32_t)min(q_len, 2047) << QM_LEN_SHIFT) | (q_ovf << QM_OVF_SHIFT);
         p.reset_buf[i] = done ? 1ll : 0ll;
         p.time_outs[i] = tout ? 1 : 0;
         p.rew[i] = rew;

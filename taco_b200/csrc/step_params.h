@@ -14,8 +14,8 @@ constexpr int kStatSlots = 64;    // spread of the per-block stats atomics
 constexpr int kStatStride = 16;   // doubles per slot (128 B)
 constexpr int kNumStats = 8;
 
-// qmeta bit layout
-constexpr uint32_t QM_HEAD_SHIFT = 0, QM_N_SHIFT = 4, QM_LEN_SHIFT = 9, QM_OVF_SHIFT = 20;
+// qmeta bit layout: live runs (5 b), actions_remained_length (11 b), overflow flag
+constexpr uint32_t QM_N_SHIFT = 4, QM_LEN_SHIFT = 9, QM_OVF_SHIFT = 20;
 
 struct StepParams {
     int n, n_pad;

@@ -143,7 +143,7 @@ __global__ void export_state_kernel(StepParams p, float* out) {
     o[36] = (float)((qm >> QM_N_SHIFT) & 31u);                // live runs in the action queue
     o[37] = (float)((qm >> QM_OVF_SHIFT) & 1u);               // delay overflow flag
     o[38] = (float)p.reset_buf[i];
-    o[39] = (float)((qm >> QM_HEAD_SHIFT) & 15u);
+    o[39] = 0.f;                                              // (was: queue head; the head is implied by the step clock)
     if (p.has_dr) {
         const float4 d0 = p.D[0][i], d1 = p.D[1][i], d2 = p.D[2][i], d3 = p.D[3][i];
         o[40] = d0.x; o[41] = d0.y; o[42] = d0.z; o[43] = d0.w; o[44] = d1.x;             // omega polynomial
@@ -172,7 +172,7 @@ __global__ void import_state_kernel(StepParams p, const float* in) {
     p.progress[i] = (int)o[34];
     p.reset_buf[i] = (long long)o[38];
     // the pending-action queue itself is not imported: only its scalar meta (length / counts) is restored
-    p.qmeta[i] = (((uint32_t)o[39] & 15u) << QM_HEAD_SHIFT) | (((uint32_t)o[36] & 31u) << QM_N_SHIFT) |
+    p.qmeta[i] = (((uint32_t)o[36] & 31u) << QM_N_SHIFT) |
                  (((uint32_t)o[35] & 2047u) << QM_LEN_SHIFT) | (((uint32_t)o[37] & 1u) << QM_OVF_SHIFT);
     if (p.has_dr) {
         p.D[0][i] = make_float4(o[40], o[41], o[42], o[43]);

@@ -27,30 +27,34 @@ class DenseDelay:
 
 
 class RunQueue:
-    """Ring of (action, absolute end slot) runs; the slot clock is 10 * progress."""
+    """Ring of (action, absolute end slot) runs; the slot clock is 10 * progress.  The ring position of a run is the
+    RL step index of the LAUNCH that appended it (t & 15, identical for every env of a launch); an env's live runs are
+    the last n positions, so no head pointer is stored."""
 
-    def __init__(self, delay):
+    def __init__(self, delay, t0=0):
         self.act = np.zeros((CAP, 4), dtype=np.float32)
         self.end = np.zeros(CAP, dtype=np.int64)
-        self.head, self.n, self.len, self.progress, self.overflow = 0, 0, int(delay), 0, False
+        self.t = int(t0)                     # global step index at which the env was (lazily) reset
+        self.n, self.len, self.progress, self.overflow = 0, int(delay), 0, False
         if self.len > 0:
-            self.act[0] = 0.0
-            self.end[0] = self.len
+            z = (self.t - 1) % CAP
+            self.act[z] = 0.0
+            self.end[z] = self.len
             self.n = 1
 
     def step(self, action, T):
         clk = 10 * self.progress
-        if self.len + T <= 100 and self.n < CAP:
-            slot = (self.head + self.n) % CAP
-            self.act[slot] = action
-            self.end[slot] = clk + self.len + T
-            self.n += 1
-        else:
+        ts = self.t % CAP
+        if self.len + T > 100 or self.n >= CAP:
             self.overflow = True
+            if self.n >= CAP:
+                self.n = CAP - 1
+        self.act[ts] = action
+        self.end[ts] = clk + self.len + T
+        self.n += 1
         self.len += T
-        cur, left = self.head, self.n
-        dact = self.act[cur].copy() if left > 0 else np.zeros(4, dtype=np.float32)
-        run_end = self.end[cur] if left > 0 else 0
+        cur, left = (ts + 1 - self.n) % CAP, self.n
+        dact, run_end = self.act[cur].copy(), self.end[cur]
         reads = []
         for k in range(10):
             slot_abs = clk + min(self.len - 1, k)
@@ -61,11 +65,12 @@ class RunQueue:
             reads.append(dact.copy())
         self.progress += 1
         clk2 = clk + 10
-        self.n, self.head = left, cur
+        self.n = left
         while self.n > 0 and run_end <= clk2:
-            self.head = (self.head + 1) % CAP
+            cur = (cur + 1) % CAP
             self.n -= 1
             if self.n > 0:
-                run_end = self.end[self.head]
+                run_end = self.end[cur]
         self.len = max(self.len - 10, 0)
+        self.t += 1
         return reads

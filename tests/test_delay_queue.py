@@ -9,10 +9,10 @@ from queue_model import DenseDelay, RunQueue
 
 
 @settings(max_examples=300, deadline=None)
-@given(delay=st.integers(0, 100), deploys=st.lists(st.integers(9, 11), min_size=1, max_size=120), seed=st.integers(0, 2**31 - 1))
-def test_run_queue_matches_dense_buffer(delay, deploys, seed):
+@given(delay=st.integers(0, 100), deploys=st.lists(st.integers(9, 11), min_size=1, max_size=120), seed=st.integers(0, 2**31 - 1), t0=st.integers(0, 2**32 - 1))
+def test_run_queue_matches_dense_buffer(delay, deploys, seed, t0):
     rng = np.random.default_rng(seed)
-    dense, rq = DenseDelay(delay), RunQueue(delay)
+    dense, rq = DenseDelay(delay), RunQueue(delay, t0)
     for t, T in enumerate(deploys):
         a = rng.uniform(-1, 1, 4).astype(np.float32)
         r_dense = dense.step(a, T)

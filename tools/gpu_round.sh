@@ -1,16 +1,19 @@
 #!/bin/bash
-# One GPU session: parity tests, bench, ncu launch list + full capture of the step kernel.
-# usage (under gpurun): bash tools/gpu_round.sh <tag>
+# One GPU session: parity tests, bench, ncu launch list + full captures of the step kernel and the actor kernel.
+# usage (under gpurun): bash tools/gpu_round.sh <tag> [skip-tests]
 TAG=${1:-r01}
 mkdir -p gpurun_out
-python tools/parity_report.py 50 2>&1 | grep -E "==|step 1 |step 2 |step 50|mismatch" | cut -c1-700 > gpurun_out/parity_$TAG.log
-python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu_$TAG.log
-tail -5 gpurun_out/pytest_gpu_$TAG.log
-python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
-cat gpurun_out/bench_$TAG.json
-python bench.py --fast-fp --no-cpu-baseline > gpurun_out/bench_fast_$TAG.json 2>> gpurun_out/bench_$TAG.err
+if [ -z "$2" ]; then
+  timeout 600 python tools/parity_report.py 50 2>&1 | grep -E "==|step 1 |step 2 |step 50|mismatch" | cut -c1-700 > gpurun_out/parity_$TAG.log
+  timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu_$TAG.log
+  tail -5 gpurun_out/pytest_gpu_$TAG.log
+fi
+timeout 900 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
+cat gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err
+timeout 600 python bench.py --fast-fp --no-cpu-baseline --no-actor > gpurun_out/bench_fast_$TAG.json 2>> gpurun_out/bench_$TAG.err
 cat gpurun_out/bench_fast_$TAG.json
 BENCH_SMALL="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-small"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv $BENCH_SMALL > gpurun_out/ncu_launch_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:fpv_step_kernel -s 3 -c 2 -f -o gpurun_out/prof_$TAG $BENCH_SMALL > gpurun_out/ncu_full_$TAG.log 2>&1
-ls -la gpurun_out | tail -12
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $BENCH_SMALL > gpurun_out/ncu_launch_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:fpv_step_kernel -s 3 -c 2 -f -o gpurun_out/prof_step_$TAG $BENCH_SMALL --no-actor > gpurun_out/ncu_full_step_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:actor_tc_kernel -s 2 -c 2 -f -o gpurun_out/prof_actor_$TAG $BENCH_SMALL > gpurun_out/ncu_full_actor_$TAG.log 2>&1
+ls -la gpurun_out | tail -14
