@@ -3,16 +3,20 @@
 // Replaces, for rollout inference, MLP.forward + the actor branch of PPO_ActorCritic.act
 // (IsaacGymEnvs/algorithms/nets_asymmetry.py:23-39, :326-346):  mean = tanh(W_L relu(... relu(W_1 x + b_1) ...) + b_L).
 //
-// Shape of the work: a tile is 128 envs (rows = TMEM lanes).  Every hidden layer is one
-// D[128 x N] = A[128 x K] * W[N x K]^T accumulated in TMEM (fp32) by tcgen05.mma (bf16 operands, M=128, N<=256,
-// K=16 per instruction).  A (the activations) lives in shared memory in the canonical K-major SWIZZLE_128B layout and is
-// rewritten in place by the epilogue warps (TMEM -> registers -> +bias, ReLU -> bf16 -> smem); W streams from L2 through
-// a 4-stage ring of 32 KB K-chunks filled by the bulk async-copy engine (cp.async.bulk + mbarrier complete_tx) from
-// images that taco_actor_load pre-swizzled once per update.  The 4-wide output layer, tanh and the optional Gaussian
-// sampling are CUDA-core work in the last epilogue (a 4-column GEMM is not a dense contraction).
+// Shape of the work: a tile is 128 envs (rows = TMEM lanes); a CTA keeps TWO tiles in flight (a pair).  Every hidden
+// layer is D[128 x N] = A[128 x K] * W[N x K]^T accumulated in TMEM (fp32) by tcgen05.mma (bf16 operands, M=128,
+// N = 128-row parts, K=16 per instruction).  A (the activations of a tile) lives in shared memory in the canonical
+// K-major SWIZZLE_128B layout and is rewritten in place by the tile's epilogue warps (TMEM -> registers -> +bias, ReLU
+// -> bf16 -> smem).  W streams from L2 through a ring of 16 KB stages (one K-chunk of one 128-row part) filled by the
+// bulk async-copy engine (cp.async.bulk + mbarrier complete_tx) from images that taco_actor_load pre-swizzled once per
+// update; every stage is consumed by BOTH tiles of the pair before it is released, which halves the L2 traffic per env,
+// and while the tensor core works on one tile the epilogue warps of the other tile drain its accumulator.  The 4-wide
+// output layer, tanh and the optional Gaussian sampling are CUDA-core work in the last epilogue (a 4-column GEMM is not
+// a dense contraction).
 //
-// Warp roles (192 threads): warp 0 = weight producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..5 = epilogue (thread <-> TMEM lane <-> env row).
+// Warp roles (576 threads): warp 0 = weight producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..17 = epilogue: tile slot t = (warp-2)/8, column half = ((warp-2)/4)&1, TMEM lane quadrant = warp%4
+// (thread <-> TMEM lane <-> env row).
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -23,14 +27,17 @@ namespace actor {
 
 constexpr int kTileM = 128;                    // envs per tile = TMEM lanes
 constexpr int kKC = 64;                        // bf16 per K chunk: one 128-byte swizzle row
-constexpr int kMaxN = 256;                     // widest hidden layer (tcgen05 N limit)
-constexpr int kStages = 4;
-constexpr int kStageBytes = kMaxN * 128;       // 32 KB
+constexpr int kMaxN = 256;                     // widest hidden layer
+constexpr int kPartN = 128;                    // rows of W per stage / columns of D per MMA
+constexpr int kStages = 5;
+constexpr int kStageBytes = kPartN * 128;      // 16 KB
 constexpr int kAChunkBytes = kTileM * 128;     // 16 KB: 128 rows x 64 bf16
-constexpr int kABytes = kAChunkBytes * (kMaxN / kKC);   // 64 KB
+constexpr int kABytes = kAChunkBytes * (kMaxN / kKC);   // 64 KB per tile slot
 constexpr int kMaxHidden = 4;
 constexpr int kOutPad = 4;                     // output layer width on the CUDA-core tail (num_acts = 4)
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 16;
+constexpr int kTcThreads = (2 + kEpiWarps) * 32;   // 576
+constexpr int kTmemCols = 512;                 // two fp32 accumulators of 256 columns
 constexpr uint32_t STREAM_ACTOR = 6;           // Philox stream of the action noise
 
 struct TcLayer {
@@ -63,7 +70,8 @@ struct TcParams {
 
 constexpr int kSmemBias = kMaxHidden * kMaxN * 4;          // 4 KB
 constexpr int kSmemWout = kMaxN * kOutPad * 4;             // 4 KB
-constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kABytes + kSmemBias + kSmemWout + 256;
+constexpr int kSmemPart = 2 * kTileM * kOutPad * 4;        // 4 KB: output-layer partial sums of the upper column half
+constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + 2 * kABytes + kSmemBias + kSmemWout + kSmemPart + 256;
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -180,92 +188,117 @@ __device__ __forceinline__ void actor_tail(const float* pre, int out_dim, long l
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B atoms need 1024-byte alignment
     uint8_t* sm = smem_raw + (base - raw);
-    const uint32_t s_stage = base;                                   // kStages x 32 KB weight ring
-    const uint32_t s_a = base + kStages * kStageBytes;               // 64 KB activations (4 K-chunk blocks of 16 KB)
+    const uint32_t s_stage = base;                                   // kStages x 16 KB weight ring
+    const uint32_t s_a = base + kStages * kStageBytes;               // 2 tile slots x 64 KB activations (4 K-chunk blocks of 16 KB)
     uint8_t* a_ptr = sm + kStages * kStageBytes;
-    float* s_bias = reinterpret_cast<float*>(a_ptr + kABytes);
+    float* s_bias = reinterpret_cast<float*>(a_ptr + 2 * kABytes);
     float* s_wout = s_bias + kMaxHidden * kMaxN;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_wout + kMaxN * kOutPad);
+    float* s_part = s_wout + kMaxN * kOutPad;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * kTileM * kOutPad);
     const uint32_t bar_full = smem_u32(bars);                        // [kStages] producer -> MMA
     const uint32_t bar_empty = bar_full + 8 * kStages;               // [kStages] MMA -> producer
-    const uint32_t bar_a = bar_empty + 8 * kStages;                  // epilogue -> MMA: A of the next layer is in smem, D is drained
-    const uint32_t bar_d = bar_a + 8;                                // MMA -> epilogue: D of the layer is complete
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+    const uint32_t bar_a = bar_empty + 8 * kStages;                  // [2] epilogue(t) -> MMA: A of the next layer staged, D(t) drained
+    const uint32_t bar_d = bar_a + 16;                               // [2] MMA -> epilogue(t): D(t) of the layer is complete
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_pairs = (p.num_tiles + 1) >> 1;
 
     for (int i = threadIdx.x; i < kMaxHidden * kMaxN; i += kTcThreads) s_bias[i] = p.bias[i];
     for (int i = threadIdx.x; i < kMaxN * kOutPad; i += kTcThreads) s_wout[i] = p.w_out[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_a, kTileM);
-        mbar_init(bar_d, 1);
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_a + 8 * t, (kEpiWarps / 2) * 32); mbar_init(bar_d + 8 * t, 1); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(s_tmem), kMaxN);              // 256 fp32 columns x 128 lanes
+    if (warp == 1) tmem_alloc(smem_u32(s_tmem), kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *s_tmem;
 
     if (warp == 0) {
-        // ===================== weight producer: stream the K-chunk images of every layer, every tile
+        // ===================== weight producer: per pair, per layer, per 128-row part, per K chunk: one stage
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            uint32_t item = 0;
+            for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
                 for (int l = 0; l < p.n_hidden; ++l) {
-                    const uint32_t bytes = (uint32_t)p.layer[l].n * 128u;
-                    for (int c = 0; c < p.layer[l].kchunks; ++c) {
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                        mbar_arrive_expect_tx(bar_full + 8 * stage, bytes);
-                        bulk_g2s(s_stage + stage * kStageBytes, p.wimg + p.layer[l].img_off + (size_t)c * bytes, bytes, bar_full + 8 * stage);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    const int n = p.layer[l].n, kch = p.layer[l].kchunks;
+                    for (int h0 = 0; h0 < n; h0 += kPartN) {
+                        const uint32_t rows = (uint32_t)min(kPartN, n - h0);
+                        for (int c = 0; c < kch; ++c, ++item) {
+                            const uint32_t stage = item % kStages, phase = (item / kStages) & 1u;
+                            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                            mbar_arrive_expect_tx(bar_full + 8 * stage, rows * 128u);
+                            bulk_g2s(s_stage + stage * kStageBytes, p.wimg + p.layer[l].img_off + ((size_t)c * n + h0) * 128u, rows * 128u,
+                                     bar_full + 8 * stage);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer
+        // ===================== MMA issuer: tiles A (slot 0) and B (slot 1) of the pair share every weight stage
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0, a_phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            uint32_t item = 0, a_phase[2] = {0, 0};
+            for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+                const int nt = (2 * pair + 1 < p.num_tiles) ? 2 : 1;
                 for (int l = 0; l < p.n_hidden; ++l) {
-                    const uint32_t idesc = umma_idesc_bf16(kTileM, p.layer[l].n);
-                    mbar_wait(bar_a, a_phase); a_phase ^= 1;          // activations of layer l staged, previous D drained
-                    tc_fence_after();
-                    for (int c = 0; c < p.layer[l].kchunks; ++c) {
-                        mbar_wait(bar_full + 8 * stage, phase);
-                        tc_fence_after();
-                        const uint64_t adesc = umma_desc_sw128(s_a + c * kAChunkBytes);
-                        const uint64_t bdesc = umma_desc_sw128(s_stage + stage * kStageBytes);
+                    const int n = p.layer[l].n, kch = p.layer[l].kchunks;
+                    for (int h0 = 0; h0 < n; h0 += kPartN) {
+                        const int rows = min(kPartN, n - h0);
+                        const uint32_t idesc = umma_idesc_bf16(kTileM, rows);
+                        for (int t = 0; t < nt; ++t) {
+                            if (h0 == 0) {                            // activations of layer l staged, previous D(t) drained
+                                mbar_wait(bar_a + 8 * t, a_phase[t]); a_phase[t] ^= 1u;
+                                tc_fence_after();
+                            }
+                            const uint32_t d_addr = tmem_d + (uint32_t)(t * kMaxN + h0);
+                            for (int c = 0; c < kch; ++c) {
+                                const uint32_t it = item + (uint32_t)c, stage = it % kStages, phase = (it / kStages) & 1u;
+                                if (t == 0) { mbar_wait(bar_full + 8 * stage, phase); tc_fence_after(); }
+                                const uint64_t adesc = umma_desc_sw128(s_a + t * kABytes + c * kAChunkBytes);
+                                const uint64_t bdesc = umma_desc_sw128(s_stage + stage * kStageBytes);
 #pragma unroll
-                        for (int k = 0; k < kKC / 16; ++k)            // 16 bf16 = 32 bytes along K inside the swizzle atom
-                            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((c | k) != 0));
-                        umma_commit(bar_empty + 8 * stage);           // ring slot is free once these MMAs have read it
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                                for (int k = 0; k < kKC / 16; ++k)    // 16 bf16 = 32 bytes along K inside the swizzle atom
+                                    umma_bf16(d_addr, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((c | k) != 0));
+                                if (t == nt - 1) umma_commit(bar_empty + 8 * stage);   // slot free once the last user's MMAs have read it
+                            }
+                            if (h0 + kPartN >= n) umma_commit(bar_d + 8 * t);
+                        }
+                        item += (uint32_t)kch;
                     }
-                    umma_commit(bar_d);
                 }
             }
         }
     } else {
-        // ===================== epilogue warps: thread <-> TMEM lane <-> env row
-        const int r = ((warp & 3) << 5) | lane;                       // a warp may only touch TMEM lanes 32*(warp%4)..+31
-        const uint32_t t_lane = tmem_d + ((uint32_t)((warp & 3) << 5) << 16);
+        // ===================== epilogue warps: thread <-> TMEM lane <-> env row of tile slot t; the two column halves of a
+        // row are handled by the warps `ch` = 0 / 1 of the same lane quadrant
+        const int e = warp - 2;
+        const int t = e >> 3, ch = (e >> 2) & 1, quad = warp & 3;    // a warp may only touch TMEM lanes 32*(warp%4)..+31
+        const int r = (quad << 5) | lane;
+        const uint32_t t_lane = tmem_d + ((uint32_t)(quad << 5) << 16) + (uint32_t)(t * kMaxN);
+        uint8_t* a_t = a_ptr + t * kABytes;
+        float* part = s_part + (t * kTileM + r) * kOutPad;
+        const int pair_bar = 1 + t * 4 + quad;                       // named barrier of the (ch 0, ch 1) warp pair
         uint32_t d_phase = 0;
         const int kc0 = p.layer[0].kchunks;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+            const int tile = 2 * pair + t;
+            if (tile >= p.num_tiles) break;                           // odd tail: slot 1 has no tile (and this is the CTA's last pair)
             const long long row = (long long)tile * kTileM + r;
             const bool valid = row < p.n_rows;
-            // ---- stage the observation row as bf16, K padded with zeros to kc0 * 64
+            // ---- stage the observation row as bf16, K padded with zeros to kc0 * 64 (16-byte pieces split between ch 0 / 1)
             {
                 const float* x = p.obs + row * p.in_dim;
-                for (int c = 0; c < kc0 * 8; ++c) {
+                for (int c = ch; c < kc0 * 8; c += 2) {
                     float f[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -273,57 +306,71 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
                         f[j] = (valid && k < p.in_dim) ? __ldg(x + k) : 0.0f;
                     }
                     const uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-                    *reinterpret_cast<uint4*>(a_ptr + (c >> 3) * kAChunkBytes + sw128_off(r, c & 7)) = pk;
+                    *reinterpret_cast<uint4*>(a_t + (c >> 3) * kAChunkBytes + sw128_off(r, c & 7)) = pk;
                 }
                 fence_proxy_async_smem();                             // generic-proxy writes -> visible to the tensor core (async proxy)
                 tc_fence_before();
-                mbar_arrive(bar_a);
+                mbar_arrive(bar_a + 8 * t);
             }
             for (int l = 0; l < p.n_hidden; ++l) {
                 const int n = p.layer[l].n;
                 const float* bl = s_bias + l * kMaxN;
-                mbar_wait(bar_d, d_phase); d_phase ^= 1;
+                const int j_lo = ch * kPartN, j_hi = min(n, j_lo + kPartN);
+                mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
                 tc_fence_after();
                 if (l + 1 < p.n_hidden) {
-                    // hidden -> hidden: +bias, ReLU, bf16, back into A (all MMAs that read A have completed: bar_d)
-                    for (int j0 = 0; j0 < n; j0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(t_lane + (uint32_t)j0, v);
+                    // hidden -> hidden: +bias, ReLU, bf16, back into A (all MMAs that read A(t) have completed: bar_d)
+                    for (int j0 = j_lo; j0 < j_hi; j0 += 64) {
+                        uint32_t v[64];
+                        tmem_ld32(t_lane + (uint32_t)j0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                        tmem_ld32(t_lane + (uint32_t)(j0 + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
                         tmem_ld_wait();
-                        uint8_t* blk = a_ptr + (j0 >> 6) * kAChunkBytes;
+                        uint8_t* blk = a_t + (j0 >> 6) * kAChunkBytes;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float h[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) h[j] = fmaxf(__uint_as_float(v[q * 8 + j]) + bl[j0 + q * 8 + j], 0.0f);
-                            const uint4 pk = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-                            *reinterpret_cast<uint4*>(blk + sw128_off(r, ((j0 & 63) >> 3) + q)) = pk;
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(bl + j0 + q * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(bl + j0 + q * 8 + 4);
+                            const float h0 = fmaxf(__uint_as_float(v[q * 8 + 0]) + b0.x, 0.0f), h1 = fmaxf(__uint_as_float(v[q * 8 + 1]) + b0.y, 0.0f);
+                            const float h2 = fmaxf(__uint_as_float(v[q * 8 + 2]) + b0.z, 0.0f), h3 = fmaxf(__uint_as_float(v[q * 8 + 3]) + b0.w, 0.0f);
+                            const float h4 = fmaxf(__uint_as_float(v[q * 8 + 4]) + b1.x, 0.0f), h5 = fmaxf(__uint_as_float(v[q * 8 + 5]) + b1.y, 0.0f);
+                            const float h6 = fmaxf(__uint_as_float(v[q * 8 + 6]) + b1.z, 0.0f), h7 = fmaxf(__uint_as_float(v[q * 8 + 7]) + b1.w, 0.0f);
+                            const uint4 pk = make_uint4(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3), pack_bf16x2(h4, h5), pack_bf16x2(h6, h7));
+                            *reinterpret_cast<uint4*>(blk + sw128_off(r, q)) = pk;
                         }
                     }
                     fence_proxy_async_smem();
                     tc_fence_before();
-                    mbar_arrive(bar_a);
+                    mbar_arrive(bar_a + 8 * t);
                 } else {
-                    // last hidden layer: +bias, ReLU, then the 4-wide output layer on the CUDA cores (fp32)
+                    // last hidden layer: +bias, ReLU, then the 4-wide output layer on the CUDA cores (fp32), this warp's columns
                     float acc[kOutPad] = {0.f, 0.f, 0.f, 0.f};
-                    for (int j0 = 0; j0 < n; j0 += 32) {
+                    for (int j0 = j_lo; j0 < j_hi; j0 += 32) {
                         uint32_t v[32];
                         tmem_ld32(t_lane + (uint32_t)j0, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float h = fmaxf(__uint_as_float(v[j]) + bl[j0 + j], 0.0f);
-                            const float4 w = *reinterpret_cast<const float4*>(s_wout + (j0 + j) * kOutPad);
-                            acc[0] = fmaf(h, w.x, acc[0]); acc[1] = fmaf(h, w.y, acc[1]);
-                            acc[2] = fmaf(h, w.z, acc[2]); acc[3] = fmaf(h, w.w, acc[3]);
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(bl + j0 + j);
+                            const float hh[4] = {fmaxf(__uint_as_float(v[j]) + b.x, 0.0f), fmaxf(__uint_as_float(v[j + 1]) + b.y, 0.0f),
+                                                 fmaxf(__uint_as_float(v[j + 2]) + b.z, 0.0f), fmaxf(__uint_as_float(v[j + 3]) + b.w, 0.0f)};
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float4 w = *reinterpret_cast<const float4*>(s_wout + (j0 + j + u) * kOutPad);
+                                acc[0] = fmaf(hh[u], w.x, acc[0]); acc[1] = fmaf(hh[u], w.y, acc[1]);
+                                acc[2] = fmaf(hh[u], w.z, acc[2]); acc[3] = fmaf(hh[u], w.w, acc[3]);
+                            }
                         }
                     }
-                    tc_fence_before();                                 // D is drained; the arrive on bar_a of the next tile publishes it
-                    if (valid) {
-#pragma unroll
-                        for (int o = 0; o < kOutPad; ++o) acc[o] += __ldg(p.b_out + o);
+                    tc_fence_before();                                 // D(t) is drained; the arrive on bar_a of the next pair publishes it
+                    if (ch == 1) *reinterpret_cast<float4*>(part) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    named_bar_sync(pair_bar, 64);
+                    if (ch == 0 && valid) {
+                        const float4 o = *reinterpret_cast<const float4*>(part);
+                        acc[0] = (acc[0] + o.x) + __ldg(p.b_out + 0); acc[1] = (acc[1] + o.y) + __ldg(p.b_out + 1);
+                        acc[2] = (acc[2] + o.z) + __ldg(p.b_out + 2); acc[3] = (acc[3] + o.w) + __ldg(p.b_out + 3);
                         actor_tail(acc, p.out_dim, row, p.mean, p.sp);
                     }
+                    named_bar_sync(pair_bar, 64);                      // `part` may be rewritten by the next pair
                 }
             }
         }
@@ -332,7 +379,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_d, kMaxN);
+        tmem_dealloc(tmem_d, kTmemCols);
     }
 }
 

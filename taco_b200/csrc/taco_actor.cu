@@ -209,7 +209,8 @@ static int actor_run(TacoActor* a, const float* obs_dev, float* mean_dev, int32_
         p.wimg = a->wimg; p.bias = a->bias_pad; p.w_out = a->w_out_t; p.b_out = a->b_out;
         for (int l = 0; l < p.n_hidden; ++l) p.layer[l] = a->tc_layer[l];
         p.sp = sp;
-        const int grid = p.num_tiles < a->num_sms ? p.num_tiles : a->num_sms;
+        const int num_pairs = (p.num_tiles + 1) / 2;                   // a CTA keeps two tiles in flight
+        const int grid = num_pairs < a->num_sms ? num_pairs : a->num_sms;
         actor_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(p);
     } else {
         FpParams p;
