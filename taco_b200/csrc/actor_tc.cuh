@@ -4,19 +4,22 @@
 // (IsaacGymEnvs/algorithms/nets_asymmetry.py:23-39, :326-346):  mean = tanh(W_L relu(... relu(W_1 x + b_1) ...) + b_L).
 //
 // Shape of the work: a tile is 128 envs (rows = TMEM lanes); a CTA keeps TWO tiles in flight (a pair).  Every hidden
-// layer is D[128 x N] = A[128 x K] * W[N x K]^T accumulated in TMEM (fp32) by tcgen05.mma (bf16 operands, M=128,
-// N = 128-row parts, K=16 per instruction).  A (the activations of a tile) lives in shared memory in the canonical
-// K-major SWIZZLE_128B layout and is rewritten in place by the tile's epilogue warps (TMEM -> registers -> +bias, ReLU
-// -> bf16 -> smem).  W streams from L2 through a ring of 16 KB stages (one K-chunk of one 128-row part) filled by the
-// bulk async-copy engine (cp.async.bulk + mbarrier complete_tx) from images that taco_actor_load pre-swizzled once per
-// update; every stage is consumed by BOTH tiles of the pair before it is released, which halves the L2 traffic per env,
-// and while the tensor core works on one tile the epilogue warps of the other tile drain its accumulator.  The 4-wide
-// output layer, tanh and the optional Gaussian sampling are CUDA-core work in the last epilogue (a 4-column GEMM is not
-// a dense contraction).
+// layer is D[128 x N] = A[128 x K] * W[N x K]^T by tcgen05.mma (bf16 operands, fp32 accumulation, M=128, N = one
+// 128-row part of W, K=16 per instruction).  The activations never touch shared memory: A lives in TENSOR MEMORY as
+// packed bf16 pairs (the "TS" form of the instruction, A from TMEM), D in the neighbouring 128 TMEM columns, and the
+// tile's epilogue warps turn D into the next layer's A register-side (tcgen05.ld -> +bias, ReLU -> bf16x2 ->
+// tcgen05.st).  Shared memory holds only the weight ring: W streams from L2 through 16 KB stages (one K-chunk of one
+// 128-row part, K-major SWIZZLE_128B) filled by the bulk async-copy engine (cp.async.bulk + mbarrier complete_tx) from
+// images that taco_actor_load pre-swizzled once per update; every stage is consumed by BOTH tiles of the pair before it
+// is released (half the L2 traffic per env), and the two tiles alternate part by part, so while the tensor core works
+// on one tile the epilogue warps of the other drain its accumulator.  The 4-wide output layer, tanh and the optional
+// Gaussian sampling are CUDA-core work in the last epilogue (a 4-column GEMM is not a dense contraction).
 //
+// TMEM map (512 columns): tile slot t owns columns [256 t, 256 t + 256): A = first 128 (K <= 256 as bf16 pairs),
+// D = last 128 (one part of N).
 // Warp roles (576 threads): warp 0 = weight producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..17 = epilogue: tile slot t = (warp-2)/8, column half = ((warp-2)/4)&1, TMEM lane quadrant = warp%4
-// (thread <-> TMEM lane <-> env row).
+// warps 2..17 = epilogue: tile slot t = (warp-2)/8, column half of the part = ((warp-2)/4)&1, TMEM lane quadrant =
+// warp%4 (thread <-> TMEM lane <-> env row).
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -28,16 +31,16 @@ namespace actor {
 constexpr int kTileM = 128;                    // envs per tile = TMEM lanes
 constexpr int kKC = 64;                        // bf16 per K chunk: one 128-byte swizzle row
 constexpr int kMaxN = 256;                     // widest hidden layer
-constexpr int kPartN = 128;                    // rows of W per stage / columns of D per MMA
-constexpr int kStages = 5;
+constexpr int kPartN = 128;                    // rows of W per stage = columns of D per part
+constexpr int kStages = 12;
 constexpr int kStageBytes = kPartN * 128;      // 16 KB
-constexpr int kAChunkBytes = kTileM * 128;     // 16 KB: 128 rows x 64 bf16
-constexpr int kABytes = kAChunkBytes * (kMaxN / kKC);   // 64 KB per tile slot
 constexpr int kMaxHidden = 4;
 constexpr int kOutPad = 4;                     // output layer width on the CUDA-core tail (num_acts = 4)
 constexpr int kEpiWarps = 16;
 constexpr int kTcThreads = (2 + kEpiWarps) * 32;   // 576
-constexpr int kTmemCols = 512;                 // two fp32 accumulators of 256 columns
+constexpr int kTmemCols = 512;
+constexpr int kTmemSlot = 256;                 // columns per tile slot: A (128, packed bf16 pairs) + D (128, fp32)
+constexpr int kTmemD = 128;                    // offset of D inside a slot
 constexpr uint32_t STREAM_ACTOR = 6;           // Philox stream of the action noise
 
 struct TcLayer {
@@ -71,7 +74,7 @@ struct TcParams {
 constexpr int kSmemBias = kMaxHidden * kMaxN * 4;          // 4 KB
 constexpr int kSmemWout = kMaxN * kOutPad * 4;             // 4 KB
 constexpr int kSmemPart = 2 * kTileM * kOutPad * 4;        // 4 KB: output-layer partial sums of the upper column half
-constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + 2 * kABytes + kSmemBias + kSmemWout + kSmemPart + 256;
+constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kSmemBias + kSmemWout + kSmemPart + 256;
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -152,6 +155,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> 32 lanes x 16 consecutive columns (thread t <-> lane base + t)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem, packed bf16 pairs] * B[smem descriptor]^T   (the "TS" form: A operand from tensor memory)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);     // .x (low half) = lo
@@ -190,22 +211,45 @@ __device__ __forceinline__ void actor_tail(const float* pre, int out_dim, long l
 // ---------------------------------------------------------------------------------------------- the kernel
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+// relu(D + bias) of 32 accumulator columns -> 16 packed bf16 pairs (column 2j in the low half)
+__device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], const float* bias, uint32_t* pk) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + q * 4);
+        pk[q * 2 + 0] = pack_bf16x2(fmaxf(__uint_as_float(v[q * 4 + 0]) + b.x, 0.0f), fmaxf(__uint_as_float(v[q * 4 + 1]) + b.y, 0.0f));
+        pk[q * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(v[q * 4 + 2]) + b.z, 0.0f), fmaxf(__uint_as_float(v[q * 4 + 3]) + b.w, 0.0f));
+    }
+}
+// acc += relu(D + bias) . W_out rows, 32 accumulator columns
+__device__ __forceinline__ void relu_dot32(const uint32_t (&v)[32], const float* bias, const float* wout, float (&acc)[kOutPad]) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + j);
+        const float hh[4] = {fmaxf(__uint_as_float(v[j]) + b.x, 0.0f), fmaxf(__uint_as_float(v[j + 1]) + b.y, 0.0f),
+                             fmaxf(__uint_as_float(v[j + 2]) + b.z, 0.0f), fmaxf(__uint_as_float(v[j + 3]) + b.w, 0.0f)};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float4 w = *reinterpret_cast<const float4*>(wout + (j + u) * kOutPad);
+            acc[0] = fmaf(hh[u], w.x, acc[0]); acc[1] = fmaf(hh[u], w.y, acc[1]);
+            acc[2] = fmaf(hh[u], w.z, acc[2]); acc[3] = fmaf(hh[u], w.w, acc[3]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B atoms need 1024-byte alignment
     uint8_t* sm = smem_raw + (base - raw);
     const uint32_t s_stage = base;                                   // kStages x 16 KB weight ring
-    const uint32_t s_a = base + kStages * kStageBytes;               // 2 tile slots x 64 KB activations (4 K-chunk blocks of 16 KB)
-    uint8_t* a_ptr = sm + kStages * kStageBytes;
-    float* s_bias = reinterpret_cast<float*>(a_ptr + 2 * kABytes);
+    float* s_bias = reinterpret_cast<float*>(sm + kStages * kStageBytes);
     float* s_wout = s_bias + kMaxHidden * kMaxN;
     float* s_part = s_wout + kMaxN * kOutPad;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * kTileM * kOutPad);
     const uint32_t bar_full = smem_u32(bars);                        // [kStages] producer -> MMA
     const uint32_t bar_empty = bar_full + 8 * kStages;               // [kStages] MMA -> producer
-    const uint32_t bar_a = bar_empty + 8 * kStages;                  // [2] epilogue(t) -> MMA: A of the next layer staged, D(t) drained
-    const uint32_t bar_d = bar_a + 16;                               // [2] MMA -> epilogue(t): D(t) of the layer is complete
+    const uint32_t bar_a = bar_empty + 8 * kStages;                  // [2] epilogue(t) -> MMA: D(t) drained (and, for a new layer, A(t) written)
+    const uint32_t bar_d = bar_a + 16;                               // [2] MMA -> epilogue(t): the part of D(t) is complete
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -222,7 +266,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = *s_tmem;
+    const uint32_t tmem0 = *s_tmem;
 
     if (warp == 0) {
         // ===================== weight producer: per pair, per layer, per 128-row part, per K chunk: one stage
@@ -245,7 +289,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer: tiles A (slot 0) and B (slot 1) of the pair share every weight stage
+        // ===================== MMA issuer: tiles A (slot 0) and B (slot 1) of the pair alternate part by part and share every stage
         if (lane == 0) {
             uint32_t item = 0, a_phase[2] = {0, 0};
             for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
@@ -255,23 +299,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
                     for (int h0 = 0; h0 < n; h0 += kPartN) {
                         const int rows = min(kPartN, n - h0);
                         const uint32_t idesc = umma_idesc_bf16(kTileM, rows);
-                        for (int t = 0; t < nt; ++t) {
-                            if (h0 == 0) {                            // activations of layer l staged, previous D(t) drained
-                                mbar_wait(bar_a + 8 * t, a_phase[t]); a_phase[t] ^= 1u;
-                                tc_fence_after();
-                            }
-                            const uint32_t d_addr = tmem_d + (uint32_t)(t * kMaxN + h0);
-                            for (int c = 0; c < kch; ++c) {
-                                const uint32_t it = item + (uint32_t)c, stage = it % kStages, phase = (it / kStages) & 1u;
-                                if (t == 0) { mbar_wait(bar_full + 8 * stage, phase); tc_fence_after(); }
-                                const uint64_t adesc = umma_desc_sw128(s_a + t * kABytes + c * kAChunkBytes);
-                                const uint64_t bdesc = umma_desc_sw128(s_stage + stage * kStageBytes);
 #pragma unroll
-                                for (int k = 0; k < kKC / 16; ++k)    // 16 bf16 = 32 bytes along K inside the swizzle atom
-                                    umma_bf16(d_addr, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)((c | k) != 0));
-                                if (t == nt - 1) umma_commit(bar_empty + 8 * stage);   // slot free once the last user's MMAs have read it
+                        for (int t = 0; t < 2; ++t) {
+                            if (t < nt) {
+                                mbar_wait(bar_a + 8 * t, a_phase[t]); a_phase[t] ^= 1u;   // D(t) free; A(t) of this layer in TMEM
+                                tc_fence_after();
+                                const uint32_t a_addr = tmem0 + (uint32_t)(t * kTmemSlot);
+                                const uint32_t d_addr = a_addr + (uint32_t)kTmemD;
+                                for (int c = 0; c < kch; ++c) {
+                                    const uint32_t it = item + (uint32_t)c, stage = it % kStages, phase = (it / kStages) & 1u;
+                                    if (t == 0) { mbar_wait(bar_full + 8 * stage, phase); tc_fence_after(); }
+                                    const uint64_t bdesc = umma_desc_sw128(s_stage + stage * kStageBytes);
+#pragma unroll
+                                    for (int k = 0; k < kKC / 16; ++k)    // 16 bf16 along K = 8 packed TMEM columns of A = 32 bytes of the B atom
+                                        umma_bf16_ts(d_addr, a_addr + (uint32_t)(c * (kKC / 2) + k * 8), bdesc + (uint64_t)(k * 2), idesc,
+                                                     (uint32_t)((c | k) != 0));
+                                    if (t == nt - 1) umma_commit(bar_empty + 8 * stage);   // slot free once the last user's MMAs have read it
+                                }
+                                umma_commit(bar_d + 8 * t);
                             }
-                            if (h0 + kPartN >= n) umma_commit(bar_d + 8 * t);
                         }
                         item += (uint32_t)kch;
                     }
@@ -279,13 +325,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
             }
         }
     } else {
-        // ===================== epilogue warps: thread <-> TMEM lane <-> env row of tile slot t; the two column halves of a
-        // row are handled by the warps `ch` = 0 / 1 of the same lane quadrant
+        // ===================== epilogue warps: thread <-> TMEM lane <-> env row of tile slot t; the two 64-column halves of a
+        // part are handled by the warps `ch` = 0 / 1 of the same lane quadrant
         const int e = warp - 2;
         const int t = e >> 3, ch = (e >> 2) & 1, quad = warp & 3;    // a warp may only touch TMEM lanes 32*(warp%4)..+31
         const int r = (quad << 5) | lane;
-        const uint32_t t_lane = tmem_d + ((uint32_t)(quad << 5) << 16) + (uint32_t)(t * kMaxN);
-        uint8_t* a_t = a_ptr + t * kABytes;
+        const uint32_t t_a = tmem0 + ((uint32_t)(quad << 5) << 16) + (uint32_t)(t * kTmemSlot);
+        const uint32_t t_d = t_a + (uint32_t)kTmemD + (uint32_t)(ch * 64);
         float* part = s_part + (t * kTileM + r) * kOutPad;
         const int pair_bar = 1 + t * 4 + quad;                       // named barrier of the (ch 0, ch 1) warp pair
         uint32_t d_phase = 0;
@@ -295,73 +341,81 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
             if (tile >= p.num_tiles) break;                           // odd tail: slot 1 has no tile (and this is the CTA's last pair)
             const long long row = (long long)tile * kTileM + r;
             const bool valid = row < p.n_rows;
-            // ---- stage the observation row as bf16, K padded with zeros to kc0 * 64 (16-byte pieces split between ch 0 / 1)
+            // ---- the observation row as packed bf16 into A(t), K padded with zeros to kc0 * 64; groups of 32 features
+            // (16 TMEM columns) alternate between ch 0 / 1.  D(t) of the previous pair is drained at this point.
             {
                 const float* x = p.obs + row * p.in_dim;
-                for (int c = ch; c < kc0 * 8; c += 2) {
-                    float f[8];
+                for (int g = ch; g < kc0 * 2; g += 2) {
+                    uint32_t pk[16];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int k = c * 8 + j;
-                        f[j] = (valid && k < p.in_dim) ? __ldg(x + k) : 0.0f;
+                    for (int j = 0; j < 16; ++j) {
+                        const int k = g * 32 + 2 * j;
+                        const float f0 = (valid && k < p.in_dim) ? __ldg(x + k) : 0.0f;
+                        const float f1 = (valid && k + 1 < p.in_dim) ? __ldg(x + k + 1) : 0.0f;
+                        pk[j] = pack_bf16x2(f0, f1);
                     }
-                    const uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-                    *reinterpret_cast<uint4*>(a_t + (c >> 3) * kAChunkBytes + sw128_off(r, c & 7)) = pk;
+                    tmem_st16(t_a + (uint32_t)(g * 16), pk);
                 }
-                fence_proxy_async_smem();                             // generic-proxy writes -> visible to the tensor core (async proxy)
+                tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(bar_a + 8 * t);
             }
             for (int l = 0; l < p.n_hidden; ++l) {
                 const int n = p.layer[l].n;
                 const float* bl = s_bias + l * kMaxN;
-                const int j_lo = ch * kPartN, j_hi = min(n, j_lo + kPartN);
-                mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
-                tc_fence_after();
+                const bool two_parts = n > kPartN;
                 if (l + 1 < p.n_hidden) {
-                    // hidden -> hidden: +bias, ReLU, bf16, back into A (all MMAs that read A(t) have completed: bar_d)
-                    for (int j0 = j_lo; j0 < j_hi; j0 += 64) {
-                        uint32_t v[64];
-                        tmem_ld32(t_lane + (uint32_t)j0, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                        tmem_ld32(t_lane + (uint32_t)(j0 + 32), *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-                        tmem_ld_wait();
-                        uint8_t* blk = a_t + (j0 >> 6) * kAChunkBytes;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 b0 = *reinterpret_cast<const float4*>(bl + j0 + q * 8);
-                            const float4 b1 = *reinterpret_cast<const float4*>(bl + j0 + q * 8 + 4);
-                            const float h0 = fmaxf(__uint_as_float(v[q * 8 + 0]) + b0.x, 0.0f), h1 = fmaxf(__uint_as_float(v[q * 8 + 1]) + b0.y, 0.0f);
-                            const float h2 = fmaxf(__uint_as_float(v[q * 8 + 2]) + b0.z, 0.0f), h3 = fmaxf(__uint_as_float(v[q * 8 + 3]) + b0.w, 0.0f);
-                            const float h4 = fmaxf(__uint_as_float(v[q * 8 + 4]) + b1.x, 0.0f), h5 = fmaxf(__uint_as_float(v[q * 8 + 5]) + b1.y, 0.0f);
-                            const float h6 = fmaxf(__uint_as_float(v[q * 8 + 6]) + b1.z, 0.0f), h7 = fmaxf(__uint_as_float(v[q * 8 + 7]) + b1.w, 0.0f);
-                            const uint4 pk = make_uint4(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3), pack_bf16x2(h4, h5), pack_bf16x2(h6, h7));
-                            *reinterpret_cast<uint4*>(blk + sw128_off(r, q)) = pk;
-                        }
+                    // hidden -> hidden: relu(D + bias) as bf16 pairs, held in registers until every MMA of the layer has read
+                    // A(t), then written over A(t) as the next layer's operand
+                    uint32_t pk0[32];
+                    const bool mine0 = ch * 64 < min(n, kPartN);                 // this warp has columns in part 0
+                    const bool mine1 = two_parts && (kPartN + ch * 64 < n);      // ... in part 1
+                    mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
+                    tc_fence_after();
+                    if (mine0) {
+                        uint32_t v[32];
+                        tmem_ld32(t_d, v); tmem_ld_wait();
+                        relu_pack32(v, bl + ch * 64, pk0);
+                        tmem_ld32(t_d + 32u, v); tmem_ld_wait();
+                        if (two_parts) { tc_fence_before(); mbar_arrive(bar_a + 8 * t); }   // D drained: part 1 may start
+                        relu_pack32(v, bl + ch * 64 + 32, pk0 + 16);
+                    } else if (two_parts) { tc_fence_before(); mbar_arrive(bar_a + 8 * t); }
+                    if (two_parts) {
+                        mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
+                        tc_fence_after();
                     }
-                    fence_proxy_async_smem();
+                    // every MMA of layer l on this tile is complete: overwrite A(t) (feature k -> packed column k/2)
+                    if (mine0) { tmem_st16(t_a + (uint32_t)(ch * 32), pk0); tmem_st16(t_a + (uint32_t)(ch * 32 + 16), pk0 + 16); }
+                    if (mine1) {
+                        uint32_t v[32], pk1[16];
+                        tmem_ld32(t_d, v); tmem_ld_wait();
+                        relu_pack32(v, bl + kPartN + ch * 64, pk1);
+                        tmem_st16(t_a + (uint32_t)(64 + ch * 32), pk1);
+                        tmem_ld32(t_d + 32u, v); tmem_ld_wait();
+                        relu_pack32(v, bl + kPartN + ch * 64 + 32, pk1);
+                        tmem_st16(t_a + (uint32_t)(64 + ch * 32 + 16), pk1);
+                    }
+                    tmem_st_wait();
                     tc_fence_before();
                     mbar_arrive(bar_a + 8 * t);
                 } else {
-                    // last hidden layer: +bias, ReLU, then the 4-wide output layer on the CUDA cores (fp32), this warp's columns
+                    // last hidden layer: relu(D + bias), then the 4-wide output layer on the CUDA cores (fp32), this warp's columns
                     float acc[kOutPad] = {0.f, 0.f, 0.f, 0.f};
-                    for (int j0 = j_lo; j0 < j_hi; j0 += 32) {
-                        uint32_t v[32];
-                        tmem_ld32(t_lane + (uint32_t)j0, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b = *reinterpret_cast<const float4*>(bl + j0 + j);
-                            const float hh[4] = {fmaxf(__uint_as_float(v[j]) + b.x, 0.0f), fmaxf(__uint_as_float(v[j + 1]) + b.y, 0.0f),
-                                                 fmaxf(__uint_as_float(v[j + 2]) + b.z, 0.0f), fmaxf(__uint_as_float(v[j + 3]) + b.w, 0.0f)};
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float4 w = *reinterpret_cast<const float4*>(s_wout + (j0 + j + u) * kOutPad);
-                                acc[0] = fmaf(hh[u], w.x, acc[0]); acc[1] = fmaf(hh[u], w.y, acc[1]);
-                                acc[2] = fmaf(hh[u], w.z, acc[2]); acc[3] = fmaf(hh[u], w.w, acc[3]);
-                            }
-                        }
+                    for (int h0 = 0; h0 < n; h0 += kPartN) {
+                        const bool mine = h0 + ch * 64 < n;
+                        const bool more = h0 + kPartN < n;
+                        mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
+                        tc_fence_after();
+                        if (mine) {
+                            uint32_t v[32];
+                            tmem_ld32(t_d, v); tmem_ld_wait();
+                            relu_dot32(v, bl + h0 + ch * 64, s_wout + (h0 + ch * 64) * kOutPad, acc);
+                            tmem_ld32(t_d + 32u, v); tmem_ld_wait();
+                            if (more) { tc_fence_before(); mbar_arrive(bar_a + 8 * t); }
+                            relu_dot32(v, bl + h0 + ch * 64 + 32, s_wout + (h0 + ch * 64 + 32) * kOutPad, acc);
+                        } else if (more) { tc_fence_before(); mbar_arrive(bar_a + 8 * t); }
                     }
-                    tc_fence_before();                                 // D(t) is drained; the arrive on bar_a of the next pair publishes it
+                    tc_fence_before();                                 // D(t) is drained; the arrive after staging the next pair publishes it
                     if (ch == 1) *reinterpret_cast<float4*>(part) = make_float4(acc[0], acc[1], acc[2], acc[3]);
                     named_bar_sync(pair_bar, 64);
                     if (ch == 0 && valid) {
@@ -379,7 +433,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_d, kTmemCols);
+        tmem_dealloc(tmem0, kTmemCols);
     }
 }
 
