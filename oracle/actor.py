@@ -32,15 +32,16 @@ def mlp_forward(obs, weights, biases):
 
 
 def mlp_forward_bf16(obs, weights, biases):
-    """What the tcgen05 kernel computes: bf16 operands, fp32 accumulation and bias, activations rounded to bf16
-    between hidden layers; the last hidden activation and the output layer stay in fp32."""
+    """What the tcgen05 kernel computes: bf16 operands (activations and weights of every layer, the output layer
+    included), fp32 accumulation, fp32 bias, ReLU in fp32, then rounding to bf16 for the next layer's operand."""
     x = obs.contiguous().view(obs.size(0), -1).float()
     n = len(weights)
-    for l in range(n - 1):
+    for l in range(n):
         xa = x.to(torch.bfloat16).double()
         wa = weights[l].to(torch.bfloat16).double()
-        x = torch.relu((xa @ wa.t()).float() + biases[l])
-    return torch.tanh((x.double() @ weights[-1].double().t()).float() + biases[-1])
+        x = (xa @ wa.t()).float() + biases[l]
+        x = torch.relu(x) if l + 1 < n else torch.tanh(x)
+    return x
 
 
 def spectral_normalize(weights, lipschitz_const):

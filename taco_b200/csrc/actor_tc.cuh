@@ -12,12 +12,13 @@
 // 128-row part, K-major SWIZZLE_128B) filled by the bulk async-copy engine (cp.async.bulk + mbarrier complete_tx) from
 // images that taco_actor_load pre-swizzled once per update; every stage is consumed by BOTH tiles of the pair before it
 // is released (half the L2 traffic per env), and the two tiles alternate part by part, so while the tensor core works
-// on one tile the epilogue warps of the other drain its accumulator.  The 4-wide output layer, tanh and the optional
-// Gaussian sampling are CUDA-core work in the last epilogue (a 4-column GEMM is not a dense contraction).
+// on one tile the epilogue warps of the other drain its accumulator.  The 4-wide output layer rides the same chain as
+// one more (N = 16, zero-padded) MMA part; tanh and the optional Gaussian sampling are CUDA-core work in its epilogue.
 //
 // TMEM map (512 columns): tile slot t owns columns [256 t, 256 t + 256): A = first 128 (K <= 256 as bf16 pairs),
 // D = last 128 (one part of N).
-// Warp roles (576 threads): warp 0 = weight producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// Warp roles (576 threads): warp 0 = weight producer, warp 1 = TMEM allocator + MMA issuer (both warp-uniform loops
+// with one elected lane issuing, so that every operand stays in uniform registers),
 // warps 2..17 = epilogue: tile slot t = (warp-2)/8, column half of the part = ((warp-2)/4)&1, TMEM lane quadrant =
 // warp%4 (thread <-> TMEM lane <-> env row).
 #pragma once
@@ -35,7 +36,8 @@ constexpr int kPartN = 128;                    // rows of W per stage = columns 
 constexpr int kStages = 12;
 constexpr int kStageBytes = kPartN * 128;      // 16 KB
 constexpr int kMaxHidden = 4;
-constexpr int kOutPad = 4;                     // output layer width on the CUDA-core tail (num_acts = 4)
+constexpr int kOutPad = 4;                     // num_acts = 4
+constexpr int kOutN = 16;                      // output layer as an MMA part: N padded to the instruction minimum
 constexpr int kEpiWarps = 16;
 constexpr int kTcThreads = (2 + kEpiWarps) * 32;   // 576
 constexpr int kTmemCols = 512;
@@ -63,18 +65,22 @@ struct TcParams {
     const float* obs;    // (n_rows, in_dim) f32
     float* mean;         // (n_rows, out_dim) f32
     int in_dim, out_dim, n_rows, num_tiles, n_hidden;
-    const uint8_t* wimg; // pre-swizzled bf16 chunk images of the hidden layers
+    const uint8_t* wimg; // pre-swizzled bf16 chunk images of the hidden layers and of the (16-row padded) output layer
     const float* bias;   // [kMaxHidden][kMaxN] f32
-    const float* w_out;  // [kMaxN][kOutPad] f32 (transposed, zero padded)
     const float* b_out;  // [kOutPad]
-    TcLayer layer[kMaxHidden];
+    TcLayer layer[kMaxHidden + 1];   // hidden layers, then the output layer (n = kOutN)
     SampleParams sp;
+    unsigned long long* dbg;   // optional timeline of CTA 0 (TACO_ACTOR_TIMELINE=<file>): 3 regions of kDbgCap (clock << 8 | code) words
 };
+constexpr int kDbgCap = 4096;
+#define TACO_DBG(region, cnt, code)                                                                         \
+    do {                                                                                                    \
+        if (p.dbg && blockIdx.x == 0 && (cnt) < kDbgCap)                                                    \
+            p.dbg[(region) * kDbgCap + (cnt)++] = ((unsigned long long)clock64() << 8) | (unsigned)(code);  \
+    } while (0)
 
 constexpr int kSmemBias = kMaxHidden * kMaxN * 4;          // 4 KB
-constexpr int kSmemWout = kMaxN * kOutPad * 4;             // 4 KB
-constexpr int kSmemPart = 2 * kTileM * kOutPad * 4;        // 4 KB: output-layer partial sums of the upper column half
-constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kSmemBias + kSmemWout + kSmemPart + 256;
+constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kSmemBias + 256;
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,6 +105,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ uint32_t elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xFFFFFFFF;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -209,8 +221,6 @@ __device__ __forceinline__ void actor_tail(const float* pre, int out_dim, long l
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-
 // relu(D + bias) of 32 accumulator columns -> 16 packed bf16 pairs (column 2j in the low half)
 __device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], const float* bias, uint32_t* pk) {
 #pragma unroll
@@ -218,21 +228,6 @@ __device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], const float
         const float4 b = *reinterpret_cast<const float4*>(bias + q * 4);
         pk[q * 2 + 0] = pack_bf16x2(fmaxf(__uint_as_float(v[q * 4 + 0]) + b.x, 0.0f), fmaxf(__uint_as_float(v[q * 4 + 1]) + b.y, 0.0f));
         pk[q * 2 + 1] = pack_bf16x2(fmaxf(__uint_as_float(v[q * 4 + 2]) + b.z, 0.0f), fmaxf(__uint_as_float(v[q * 4 + 3]) + b.w, 0.0f));
-    }
-}
-// acc += relu(D + bias) . W_out rows, 32 accumulator columns
-__device__ __forceinline__ void relu_dot32(const uint32_t (&v)[32], const float* bias, const float* wout, float (&acc)[kOutPad]) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(bias + j);
-        const float hh[4] = {fmaxf(__uint_as_float(v[j]) + b.x, 0.0f), fmaxf(__uint_as_float(v[j + 1]) + b.y, 0.0f),
-                             fmaxf(__uint_as_float(v[j + 2]) + b.z, 0.0f), fmaxf(__uint_as_float(v[j + 3]) + b.w, 0.0f)};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float4 w = *reinterpret_cast<const float4*>(wout + (j + u) * kOutPad);
-            acc[0] = fmaf(hh[u], w.x, acc[0]); acc[1] = fmaf(hh[u], w.y, acc[1]);
-            acc[2] = fmaf(hh[u], w.z, acc[2]); acc[3] = fmaf(hh[u], w.w, acc[3]);
-        }
     }
 }
 
@@ -243,9 +238,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
     uint8_t* sm = smem_raw + (base - raw);
     const uint32_t s_stage = base;                                   // kStages x 16 KB weight ring
     float* s_bias = reinterpret_cast<float*>(sm + kStages * kStageBytes);
-    float* s_wout = s_bias + kMaxHidden * kMaxN;
-    float* s_part = s_wout + kMaxN * kOutPad;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 2 * kTileM * kOutPad);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kMaxHidden * kMaxN);
     const uint32_t bar_full = smem_u32(bars);                        // [kStages] producer -> MMA
     const uint32_t bar_empty = bar_full + 8 * kStages;               // [kStages] MMA -> producer
     const uint32_t bar_a = bar_empty + 8 * kStages;                  // [2] epilogue(t) -> MMA: D(t) drained (and, for a new layer, A(t) written)
@@ -254,9 +247,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_pairs = (p.num_tiles + 1) >> 1;
+    const int n_layers = p.n_hidden + 1;                             // hidden layers + the output layer as a 16-wide part
 
     for (int i = threadIdx.x; i < kMaxHidden * kMaxN; i += kTcThreads) s_bias[i] = p.bias[i];
-    for (int i = threadIdx.x; i < kMaxN * kOutPad; i += kTcThreads) s_wout[i] = p.w_out[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int t = 0; t < 2; ++t) { mbar_init(bar_a + 8 * t, (kEpiWarps / 2) * 32); mbar_init(bar_d + 8 * t, 1); }
@@ -270,57 +263,69 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
 
     if (warp == 0) {
         // ===================== weight producer: per pair, per layer, per 128-row part, per K chunk: one stage
-        if (lane == 0) {
-            uint32_t item = 0;
-            for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-                for (int l = 0; l < p.n_hidden; ++l) {
-                    const int n = p.layer[l].n, kch = p.layer[l].kchunks;
-                    for (int h0 = 0; h0 < n; h0 += kPartN) {
-                        const uint32_t rows = (uint32_t)min(kPartN, n - h0);
-                        for (int c = 0; c < kch; ++c, ++item) {
-                            const uint32_t stage = item % kStages, phase = (item / kStages) & 1u;
-                            mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-                            mbar_arrive_expect_tx(bar_full + 8 * stage, rows * 128u);
-                            bulk_g2s(s_stage + stage * kStageBytes, p.wimg + p.layer[l].img_off + ((size_t)c * n + h0) * 128u, rows * 128u,
-                                     bar_full + 8 * stage);
+        uint32_t stage = 0, phase = 0;
+        for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+            for (int l = 0; l < n_layers; ++l) {
+                const int n = p.layer[l].n, kch = p.layer[l].kchunks;
+                const uint8_t* img = p.wimg + p.layer[l].img_off;
+                for (int h0 = 0; h0 < n; h0 += kPartN) {
+                    const uint32_t bytes = (uint32_t)min(kPartN, n - h0) * 128u;
+                    for (int c = 0; c < kch; ++c) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                        if (elect_one_sync()) {
+                            mbar_arrive_expect_tx(bar_full + 8 * stage, bytes);
+                            bulk_g2s(s_stage + stage * kStageBytes, img + ((size_t)c * n + h0) * 128u, bytes, bar_full + 8 * stage);
                         }
+                        __syncwarp();
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer: tiles A (slot 0) and B (slot 1) of the pair alternate part by part and share every stage
-        if (lane == 0) {
-            uint32_t item = 0, a_phase[2] = {0, 0};
-            for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-                const int nt = (2 * pair + 1 < p.num_tiles) ? 2 : 1;
-                for (int l = 0; l < p.n_hidden; ++l) {
-                    const int n = p.layer[l].n, kch = p.layer[l].kchunks;
-                    for (int h0 = 0; h0 < n; h0 += kPartN) {
-                        const int rows = min(kPartN, n - h0);
-                        const uint32_t idesc = umma_idesc_bf16(kTileM, rows);
+        uint32_t stage = 0, phase = 0, a_phase = 0;
+        int dbg_n = lane == 0 ? 0 : kDbgCap;
+        const uint64_t bdesc0 = umma_desc_sw128(s_stage);
+        for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+            const int nt = (2 * pair + 1 < p.num_tiles) ? 2 : 1;
+            for (int l = 0; l < n_layers; ++l) {
+                const int n = p.layer[l].n, kch = p.layer[l].kchunks;
+                for (int h0 = 0; h0 < n; h0 += kPartN) {
+                    const uint32_t idesc = umma_idesc_bf16(kTileM, min(kPartN, n - h0));
+                    uint32_t st_end = stage, ph_end = phase;
 #pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            if (t < nt) {
-                                mbar_wait(bar_a + 8 * t, a_phase[t]); a_phase[t] ^= 1u;   // D(t) free; A(t) of this layer in TMEM
-                                tc_fence_after();
-                                const uint32_t a_addr = tmem0 + (uint32_t)(t * kTmemSlot);
-                                const uint32_t d_addr = a_addr + (uint32_t)kTmemD;
-                                for (int c = 0; c < kch; ++c) {
-                                    const uint32_t it = item + (uint32_t)c, stage = it % kStages, phase = (it / kStages) & 1u;
-                                    if (t == 0) { mbar_wait(bar_full + 8 * stage, phase); tc_fence_after(); }
-                                    const uint64_t bdesc = umma_desc_sw128(s_stage + stage * kStageBytes);
-#pragma unroll
-                                    for (int k = 0; k < kKC / 16; ++k)    // 16 bf16 along K = 8 packed TMEM columns of A = 32 bytes of the B atom
-                                        umma_bf16_ts(d_addr, a_addr + (uint32_t)(c * (kKC / 2) + k * 8), bdesc + (uint64_t)(k * 2), idesc,
-                                                     (uint32_t)((c | k) != 0));
-                                    if (t == nt - 1) umma_commit(bar_empty + 8 * stage);   // slot free once the last user's MMAs have read it
+                    for (int t = 0; t < 2; ++t) {
+                        if (t < nt) {
+                            TACO_DBG(0, dbg_n, 0x10 | t);
+                            mbar_wait(bar_a + 8 * t, (a_phase >> t) & 1u); a_phase ^= (1u << t);   // D(t) free; A(t) of this layer in TMEM
+                            tc_fence_after();
+                            TACO_DBG(0, dbg_n, 0x20 | t);
+                            const uint32_t a_addr = tmem0 + (uint32_t)(t * kTmemSlot);
+                            const uint32_t d_addr = a_addr + (uint32_t)kTmemD;
+                            uint32_t st = stage, ph = phase;
+                            for (int c = 0; c < kch; ++c) {
+                                if (t == 0) { mbar_wait(bar_full + 8 * st, ph); tc_fence_after(); }
+                                if (elect_one_sync()) {
+                                    const uint64_t bdesc = bdesc0 + (uint64_t)(st * (kStageBytes >> 4));
+                                    const uint32_t a_c = a_addr + (uint32_t)(c * (kKC / 2));
+                                    // 16 bf16 along K = 8 packed TMEM columns of A = 32 bytes inside the B swizzle atom
+                                    umma_bf16_ts(d_addr, a_c, bdesc, idesc, (uint32_t)(c != 0));
+                                    umma_bf16_ts(d_addr, a_c + 8u, bdesc + 2u, idesc, 1u);
+                                    umma_bf16_ts(d_addr, a_c + 16u, bdesc + 4u, idesc, 1u);
+                                    umma_bf16_ts(d_addr, a_c + 24u, bdesc + 6u, idesc, 1u);
+                                    if (t == nt - 1) umma_commit(bar_empty + 8 * st);   // slot free once the last user's MMAs have read it
                                 }
-                                umma_commit(bar_d + 8 * t);
+                                __syncwarp();
+                                if (++st == kStages) { st = 0; ph ^= 1u; }
                             }
+                            if (elect_one_sync()) umma_commit(bar_d + 8 * t);
+                            __syncwarp();
+                            TACO_DBG(0, dbg_n, 0x30 | t);
+                            st_end = st; ph_end = ph;
                         }
-                        item += (uint32_t)kch;
                     }
+                    stage = st_end; phase = ph_end;
                 }
             }
         }
@@ -332,10 +337,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
         const int r = (quad << 5) | lane;
         const uint32_t t_a = tmem0 + ((uint32_t)(quad << 5) << 16) + (uint32_t)(t * kTmemSlot);
         const uint32_t t_d = t_a + (uint32_t)kTmemD + (uint32_t)(ch * 64);
-        float* part = s_part + (t * kTileM + r) * kOutPad;
-        const int pair_bar = 1 + t * 4 + quad;                       // named barrier of the (ch 0, ch 1) warp pair
         uint32_t d_phase = 0;
         const int kc0 = p.layer[0].kchunks;
+        const size_t row_bytes = (size_t)p.in_dim * sizeof(float);
+        int dbg_n = (ch == 0 && quad == 0 && lane == 0) ? 0 : kDbgCap;
         for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
             const int tile = 2 * pair + t;
             if (tile >= p.num_tiles) break;                           // odd tail: slot 1 has no tile (and this is the CTA's last pair)
@@ -359,74 +364,72 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(bar_a + 8 * t);
+                TACO_DBG(1 + t, dbg_n, 0x01);
+                // pull the row this thread stages for the CTA's NEXT pair towards L2 while this pair computes
+                const long long row_next = row + 2ll * gridDim.x * kTileM;
+                if (ch == 0 && row_next < p.n_rows) {
+                    const char* xn = reinterpret_cast<const char*>(p.obs + row_next * p.in_dim);
+                    for (size_t o = 0; o < row_bytes; o += 128) prefetch_l2(xn + o);
+                }
             }
             for (int l = 0; l < p.n_hidden; ++l) {
+                // hidden layer: relu(D + bias) as bf16 pairs, held in registers until every MMA of the layer has read A(t), then
+                // written over A(t) as the next layer's operand
                 const int n = p.layer[l].n;
                 const float* bl = s_bias + l * kMaxN;
                 const bool two_parts = n > kPartN;
-                if (l + 1 < p.n_hidden) {
-                    // hidden -> hidden: relu(D + bias) as bf16 pairs, held in registers until every MMA of the layer has read
-                    // A(t), then written over A(t) as the next layer's operand
-                    uint32_t pk0[32];
-                    const bool mine0 = ch * 64 < min(n, kPartN);                 // this warp has columns in part 0
-                    const bool mine1 = two_parts && (kPartN + ch * 64 < n);      // ... in part 1
+                uint32_t pk0[32];
+                const bool mine0 = ch * 64 < min(n, kPartN);                 // this warp has columns in part 0
+                const bool mine1 = two_parts && (kPartN + ch * 64 < n);      // ... in part 1
+                mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
+                tc_fence_after();
+                TACO_DBG(1 + t, dbg_n, 0x02);
+                if (mine0) {
+                    uint32_t v[32];
+                    tmem_ld32(t_d, v); tmem_ld_wait();
+                    relu_pack32(v, bl + ch * 64, pk0);
+                    tmem_ld32(t_d + 32u, v); tmem_ld_wait();
+                    if (two_parts) { tc_fence_before(); mbar_arrive(bar_a + 8 * t); TACO_DBG(1 + t, dbg_n, 0x03); }   // D drained: part 1 may start
+                    relu_pack32(v, bl + ch * 64 + 32, pk0 + 16);
+                } else if (two_parts) { tc_fence_before(); mbar_arrive(bar_a + 8 * t); }
+                if (two_parts) {
                     mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
                     tc_fence_after();
-                    if (mine0) {
-                        uint32_t v[32];
-                        tmem_ld32(t_d, v); tmem_ld_wait();
-                        relu_pack32(v, bl + ch * 64, pk0);
-                        tmem_ld32(t_d + 32u, v); tmem_ld_wait();
-                        if (two_parts) { tc_fence_before(); mbar_arrive(bar_a + 8 * t); }   // D drained: part 1 may start
-                        relu_pack32(v, bl + ch * 64 + 32, pk0 + 16);
-                    } else if (two_parts) { tc_fence_before(); mbar_arrive(bar_a + 8 * t); }
-                    if (two_parts) {
-                        mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
-                        tc_fence_after();
-                    }
-                    // every MMA of layer l on this tile is complete: overwrite A(t) (feature k -> packed column k/2)
-                    if (mine0) { tmem_st16(t_a + (uint32_t)(ch * 32), pk0); tmem_st16(t_a + (uint32_t)(ch * 32 + 16), pk0 + 16); }
-                    if (mine1) {
-                        uint32_t v[32], pk1[16];
-                        tmem_ld32(t_d, v); tmem_ld_wait();
-                        relu_pack32(v, bl + kPartN + ch * 64, pk1);
-                        tmem_st16(t_a + (uint32_t)(64 + ch * 32), pk1);
-                        tmem_ld32(t_d + 32u, v); tmem_ld_wait();
-                        relu_pack32(v, bl + kPartN + ch * 64 + 32, pk1);
-                        tmem_st16(t_a + (uint32_t)(64 + ch * 32 + 16), pk1);
-                    }
-                    tmem_st_wait();
-                    tc_fence_before();
-                    mbar_arrive(bar_a + 8 * t);
-                } else {
-                    // last hidden layer: relu(D + bias), then the 4-wide output layer on the CUDA cores (fp32), this warp's columns
-                    float acc[kOutPad] = {0.f, 0.f, 0.f, 0.f};
-                    for (int h0 = 0; h0 < n; h0 += kPartN) {
-                        const bool mine = h0 + ch * 64 < n;
-                        const bool more = h0 + kPartN < n;
-                        mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
-                        tc_fence_after();
-                        if (mine) {
-                            uint32_t v[32];
-                            tmem_ld32(t_d, v); tmem_ld_wait();
-                            relu_dot32(v, bl + h0 + ch * 64, s_wout + (h0 + ch * 64) * kOutPad, acc);
-                            tmem_ld32(t_d + 32u, v); tmem_ld_wait();
-                            if (more) { tc_fence_before(); mbar_arrive(bar_a + 8 * t); }
-                            relu_dot32(v, bl + h0 + ch * 64 + 32, s_wout + (h0 + ch * 64 + 32) * kOutPad, acc);
-                        } else if (more) { tc_fence_before(); mbar_arrive(bar_a + 8 * t); }
-                    }
-                    tc_fence_before();                                 // D(t) is drained; the arrive after staging the next pair publishes it
-                    if (ch == 1) *reinterpret_cast<float4*>(part) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                    named_bar_sync(pair_bar, 64);
-                    if (ch == 0 && valid) {
-                        const float4 o = *reinterpret_cast<const float4*>(part);
-                        acc[0] = (acc[0] + o.x) + __ldg(p.b_out + 0); acc[1] = (acc[1] + o.y) + __ldg(p.b_out + 1);
-                        acc[2] = (acc[2] + o.z) + __ldg(p.b_out + 2); acc[3] = (acc[3] + o.w) + __ldg(p.b_out + 3);
-                        actor_tail(acc, p.out_dim, row, p.mean, p.sp);
-                    }
-                    named_bar_sync(pair_bar, 64);                      // `part` may be rewritten by the next pair
+                    TACO_DBG(1 + t, dbg_n, 0x04);
+                }
+                // every MMA of layer l on this tile is complete: overwrite A(t) (feature k -> packed column k/2)
+                if (mine0) { tmem_st16(t_a + (uint32_t)(ch * 32), pk0); tmem_st16(t_a + (uint32_t)(ch * 32 + 16), pk0 + 16); }
+                if (mine1) {
+                    uint32_t v[32], pk1[16];
+                    tmem_ld32(t_d, v); tmem_ld_wait();
+                    relu_pack32(v, bl + kPartN + ch * 64, pk1);
+                    tmem_st16(t_a + (uint32_t)(64 + ch * 32), pk1);
+                    tmem_ld32(t_d + 32u, v); tmem_ld_wait();
+                    relu_pack32(v, bl + kPartN + ch * 64 + 32, pk1);
+                    tmem_st16(t_a + (uint32_t)(64 + ch * 32 + 16), pk1);
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(bar_a + 8 * t);
+                TACO_DBG(1 + t, dbg_n, 0x05);
+            }
+            // ---- output layer (columns 0..3 of its 16-wide part) + tanh / sampling; the arrive after staging the next pair
+            // tells the MMA issuer that D(t) is drained
+            mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
+            tc_fence_after();
+            TACO_DBG(1 + t, dbg_n, 0x06);
+            if (ch == 0) {
+                uint32_t v[32];
+                tmem_ld32(t_d, v); tmem_ld_wait();
+                tc_fence_before();
+                if (valid) {
+                    float pre[kOutPad];
+#pragma unroll
+                    for (int o = 0; o < kOutPad; ++o) pre[o] = __uint_as_float(v[o]) + __ldg(p.b_out + o);
+                    actor_tail(pre, p.out_dim, row, p.mean, p.sp);
                 }
             }
+            TACO_DBG(1 + t, dbg_n, 0x07);
         }
     }
     tc_fence_before();
@@ -438,8 +441,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
 }
 
 // fp32 (out, in) row-major weights -> bf16 K-chunk images in the SWIZZLE_128B K-major layout the kernel copies verbatim:
-// chunk c holds W[:, 64c .. 64c+63] as n rows of 128 bytes; the 16-byte piece q of row r sits at r*128 + ((q ^ (r&7)) << 4).
-__global__ void pack_weights_kernel(const float* __restrict__ w, int n, int k, uint8_t* __restrict__ img) {
+// chunk c holds W[:, 64c .. 64c+63] as n rows of 128 bytes (rows >= n_real are zero); the 16-byte piece q of row r sits
+// at r*128 + ((q ^ (r&7)) << 4).
+__global__ void pack_weights_kernel(const float* __restrict__ w, int n_real, int n, int k, uint8_t* __restrict__ img) {
     const int kchunks = (k + kKC - 1) / kKC;
     const int total = kchunks * n * 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -448,7 +452,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int n, int k, u
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int kk = c * kKC + q * 8 + j;
-            f[j] = kk < k ? w[(size_t)r * k + kk] : 0.0f;
+            f[j] = (kk < k && r < n_real) ? w[(size_t)r * k + kk] : 0.0f;
         }
         const uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         *reinterpret_cast<uint4*>(img + (size_t)c * n * 128 + sw128_off(r, q)) = pk;

@@ -10,6 +10,7 @@
 // (power iteration in double precision, once per update) and pre-swizzles the bf16 weight images.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -156,16 +157,6 @@ __global__ void __launch_bounds__(kSnThreads) spectral_norm_kernel(float* w, int
     }
 }
 
-__global__ void transpose_out_kernel(const float* __restrict__ w, const float* __restrict__ b, int out, int k, float* __restrict__ wt,
-                                     float* __restrict__ bt) {
-    // (out, k) -> [kMaxN][kOutPad], zero padded
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kMaxN * kOutPad; i += gridDim.x * blockDim.x) {
-        const int kk = i / kOutPad, o = i % kOutPad;
-        wt[i] = (o < out && kk < k) ? w[(size_t)o * k + kk] : 0.0f;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < kOutPad) bt[threadIdx.x] = threadIdx.x < out ? b[threadIdx.x] : 0.0f;
-}
-
 }  // namespace actor
 }  // namespace taco
 
@@ -185,9 +176,8 @@ struct TacoActor {
     std::string tc_why;
     uint8_t* wimg = nullptr;
     float* bias_pad = nullptr;           // [kMaxHidden][kMaxN]
-    float* w_out_t = nullptr;            // [kMaxN][kOutPad]
     float* b_out = nullptr;              // [kOutPad]
-    TcLayer tc_layer[kMaxHidden];
+    TcLayer tc_layer[kMaxHidden + 1];    // hidden layers + the output layer (16-row padded image)
     int num_sms = 148;
     int fp_smem = 0;
 };
@@ -206,12 +196,25 @@ static int actor_run(TacoActor* a, const float* obs_dev, float* mean_dev, int32_
         p.obs = obs_dev; p.mean = mean_dev;
         p.in_dim = a->sizes[0]; p.out_dim = a->sizes.back(); p.n_rows = n; p.num_tiles = (n + kTileM - 1) / kTileM;
         p.n_hidden = a->n_layers - 1;
-        p.wimg = a->wimg; p.bias = a->bias_pad; p.w_out = a->w_out_t; p.b_out = a->b_out;
-        for (int l = 0; l < p.n_hidden; ++l) p.layer[l] = a->tc_layer[l];
+        p.wimg = a->wimg; p.bias = a->bias_pad; p.b_out = a->b_out;
+        for (int l = 0; l <= p.n_hidden; ++l) p.layer[l] = a->tc_layer[l];
         p.sp = sp;
         const int num_pairs = (p.num_tiles + 1) / 2;                   // a CTA keeps two tiles in flight
         const int grid = num_pairs < a->num_sms ? num_pairs : a->num_sms;
+        // developer aid: TACO_ACTOR_TIMELINE=<file> records clock64 stamps of CTA 0's MMA issuer / epilogue (synchronous)
+        const char* tl = getenv("TACO_ACTOR_TIMELINE");
+        if (tl && *tl) {
+            ACT_CUDA(cudaMalloc(&p.dbg, 3 * kDbgCap * sizeof(unsigned long long)));
+            ACT_CUDA(cudaMemsetAsync(p.dbg, 0, 3 * kDbgCap * sizeof(unsigned long long), s));
+        }
         actor_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(p);
+        if (p.dbg) {
+            std::vector<unsigned long long> h(3 * kDbgCap);
+            ACT_CUDA(cudaStreamSynchronize(s));
+            ACT_CUDA(cudaMemcpy(h.data(), p.dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            cudaFree(p.dbg);
+            if (FILE* f = fopen(tl, "wb")) { fwrite(h.data(), sizeof(unsigned long long), h.size(), f); fclose(f); }
+        }
     } else {
         FpParams p;
         memset(&p, 0, sizeof(p));
@@ -274,15 +277,14 @@ int taco_actor_create(int device, const int32_t* sizes, int32_t n_sizes, TacoAct
     if (ce == cudaSuccess) ce = cudaMemset(a->sigma, 0, kMaxLayers * sizeof(double));
     if (ce == cudaSuccess && a->tc_ok) {
         size_t img = 0;
-        for (int l = 0; l < n_hidden; ++l) {
-            const int k = sizes[l], nn = sizes[l + 1];
+        for (int l = 0; l <= n_hidden; ++l) {
+            const int k = sizes[l], nn = l < n_hidden ? sizes[l + 1] : kOutN;
             const int kch = (k + kKC - 1) / kKC;
             a->tc_layer[l].n = nn; a->tc_layer[l].kchunks = kch; a->tc_layer[l].img_off = (uint32_t)img;
             img += (size_t)kch * nn * 128;
         }
         ce = cudaMalloc(&a->wimg, img);
         if (ce == cudaSuccess) ce = cudaMalloc(&a->bias_pad, kMaxHidden * kMaxN * sizeof(float));
-        if (ce == cudaSuccess) ce = cudaMalloc(&a->w_out_t, kMaxN * kOutPad * sizeof(float));
         if (ce == cudaSuccess) ce = cudaMalloc(&a->b_out, kOutPad * sizeof(float));
         if (ce == cudaSuccess) ce = cudaFuncSetAttribute(actor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
     }
@@ -301,7 +303,7 @@ int taco_actor_destroy(TacoActor* a) {
     if (!a) return TACO_OK;
     DevGuard guard(a->device);
     cudaFree(a->w_f32); cudaFree(a->b_f32); cudaFree(a->sigma);
-    cudaFree(a->wimg); cudaFree(a->bias_pad); cudaFree(a->w_out_t); cudaFree(a->b_out);
+    cudaFree(a->wimg); cudaFree(a->bias_pad); cudaFree(a->b_out);
     delete a;
     return TACO_OK;
 }
@@ -327,13 +329,14 @@ int taco_actor_load(TacoActor* a, const float* const* weights_host, const float*
     if (a->tc_ok) {
         const int n_hidden = a->n_layers - 1;
         ACT_CUDA(cudaMemsetAsync(a->bias_pad, 0, kMaxHidden * kMaxN * sizeof(float), s));
-        for (int l = 0; l < n_hidden; ++l) {
+        for (int l = 0; l <= n_hidden; ++l) {
             const int in = a->sizes[l], out = a->sizes[l + 1];
-            pack_weights_kernel<<<64, 256, 0, s>>>(a->w_f32 + a->w_off[l], out, in, a->wimg + a->tc_layer[l].img_off);
-            ACT_CUDA(cudaMemcpyAsync(a->bias_pad + l * kMaxN, a->b_f32 + a->b_off[l], (size_t)out * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            pack_weights_kernel<<<64, 256, 0, s>>>(a->w_f32 + a->w_off[l], out, a->tc_layer[l].n, in, a->wimg + a->tc_layer[l].img_off);
+            if (l < n_hidden)
+                ACT_CUDA(cudaMemcpyAsync(a->bias_pad + l * kMaxN, a->b_f32 + a->b_off[l], (size_t)out * sizeof(float), cudaMemcpyDeviceToDevice, s));
         }
-        const int lo = a->n_layers - 1;
-        transpose_out_kernel<<<4, 256, 0, s>>>(a->w_f32 + a->w_off[lo], a->b_f32 + a->b_off[lo], a->sizes[lo + 1], a->sizes[lo], a->w_out_t, a->b_out);
+        ACT_CUDA(cudaMemsetAsync(a->b_out, 0, kOutPad * sizeof(float), s));
+        ACT_CUDA(cudaMemcpyAsync(a->b_out, a->b_f32 + a->b_off[n_hidden], (size_t)a->sizes[n_hidden + 1] * sizeof(float), cudaMemcpyDeviceToDevice, s));
         ACT_CUDA(cudaGetLastError());
     }
     ACT_CUDA(cudaStreamSynchronize(s));     // the host weight buffers may be released by the caller on return
