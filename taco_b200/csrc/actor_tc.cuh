@@ -8,10 +8,10 @@
 // 128-row part of W, K=16 per instruction).  The activations never touch shared memory: A lives in TENSOR MEMORY as
 // packed bf16 pairs (the "TS" form of the instruction, A from TMEM), D in the neighbouring 128 TMEM columns, and the
 // tile's epilogue warps turn D into the next layer's A register-side (tcgen05.ld -> +bias, ReLU -> bf16x2 ->
-// tcgen05.st).  Shared memory holds only the weight ring: W streams from L2 through 16 KB stages (one K-chunk of one
-// 128-row part, K-major SWIZZLE_128B) filled by the bulk async-copy engine (cp.async.bulk + mbarrier complete_tx) from
-// images that taco_actor_load pre-swizzled once per update; every stage is consumed by BOTH tiles of the pair before it
-// is released (half the L2 traffic per env), and the two tiles alternate part by part, so while the tensor core works
+// tcgen05.st).  Shared memory holds only the weight ring: W streams from L2 through 64 KB slots (one 128-row part of a
+// layer = up to four 16 KB K-chunks, K-major SWIZZLE_128B) filled by the bulk async-copy engine (cp.async.bulk + mbarrier
+// complete_tx) from images that taco_actor_load pre-swizzled once per update; every slot is consumed by BOTH tiles of the
+// pair before it is released (half the L2 traffic per env), and the two tiles alternate part by part, so while the tensor core works
 // on one tile the epilogue warps of the other drain its accumulator.  The 4-wide output layer rides the same chain as
 // one more (N = 16, zero-padded) MMA part; tanh and the optional Gaussian sampling are CUDA-core work in its epilogue.
 //
@@ -33,8 +33,9 @@ constexpr int kTileM = 128;                    // envs per tile = TMEM lanes
 constexpr int kKC = 64;                        // bf16 per K chunk: one 128-byte swizzle row
 constexpr int kMaxN = 256;                     // widest hidden layer
 constexpr int kPartN = 128;                    // rows of W per stage = columns of D per part
-constexpr int kStages = 12;
-constexpr int kStageBytes = kPartN * 128;      // 16 KB
+constexpr int kSlots = 3;                      // weight ring: slots of one part (all K chunks)
+constexpr int kChunkBytes = kPartN * 128;      // 16 KB: 128 rows x 64 bf16
+constexpr int kSlotBytes = kChunkBytes * (kMaxN / kKC);   // 64 KB
 constexpr int kMaxHidden = 4;
 constexpr int kOutPad = 4;                     // num_acts = 4
 constexpr int kOutN = 16;                      // output layer as an MMA part: N padded to the instruction minimum
@@ -80,7 +81,7 @@ constexpr int kDbgCap = 4096;
     } while (0)
 
 constexpr int kSmemBias = kMaxHidden * kMaxN * 4;          // 4 KB
-constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kSmemBias + 256;
+constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kSlots * kSlotBytes + kSmemBias + 256;
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -166,6 +167,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // registers -> 32 lanes x 16 consecutive columns (thread t <-> lane base + t)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
@@ -231,19 +235,30 @@ __device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], const float
     }
 }
 
+// the observation features [32 g, 32 g + 32) of one row as 16 packed bf16 pairs (zero beyond in_dim / for invalid rows)
+__device__ __forceinline__ void load_obs_group(const float* x, int g, int in_dim, bool valid, uint32_t* pk) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int k = g * 32 + 2 * j;
+        const float f0 = (valid && k < in_dim) ? __ldg(x + k) : 0.0f;
+        const float f1 = (valid && k + 1 < in_dim) ? __ldg(x + k + 1) : 0.0f;
+        pk[j] = pack_bf16x2(f0, f1);
+    }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B atoms need 1024-byte alignment
     uint8_t* sm = smem_raw + (base - raw);
-    const uint32_t s_stage = base;                                   // kStages x 16 KB weight ring
-    float* s_bias = reinterpret_cast<float*>(sm + kStages * kStageBytes);
+    const uint32_t s_ring = base;                                    // kSlots x 64 KB weight ring
+    float* s_bias = reinterpret_cast<float*>(sm + kSlots * kSlotBytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + kMaxHidden * kMaxN);
-    const uint32_t bar_full = smem_u32(bars);                        // [kStages] producer -> MMA
-    const uint32_t bar_empty = bar_full + 8 * kStages;               // [kStages] MMA -> producer
-    const uint32_t bar_a = bar_empty + 8 * kStages;                  // [2] epilogue(t) -> MMA: D(t) drained (and, for a new layer, A(t) written)
+    const uint32_t bar_full = smem_u32(bars);                        // [kSlots] producer -> MMA
+    const uint32_t bar_empty = bar_full + 8 * kSlots;                // [kSlots] MMA -> producer
+    const uint32_t bar_a = bar_empty + 8 * kSlots;                   // [2] epilogue(t) -> MMA: D(t) drained (and, for a new layer, A(t) written)
     const uint32_t bar_d = bar_a + 16;                               // [2] MMA -> epilogue(t): the part of D(t) is complete
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_pairs = (p.num_tiles + 1) >> 1;
@@ -251,7 +266,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
 
     for (int i = threadIdx.x; i < kMaxHidden * kMaxN; i += kTcThreads) s_bias[i] = p.bias[i];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < kSlots; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int t = 0; t < 2; ++t) { mbar_init(bar_a + 8 * t, (kEpiWarps / 2) * 32); mbar_init(bar_d + 8 * t, 1); }
         fence_barrier_init();
     }
@@ -262,70 +277,64 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
     const uint32_t tmem0 = *s_tmem;
 
     if (warp == 0) {
-        // ===================== weight producer: per pair, per layer, per 128-row part, per K chunk: one stage
-        uint32_t stage = 0, phase = 0;
+        // ===================== weight producer: per pair, per layer, per 128-row part: one slot (all its K chunks)
+        uint32_t slot = 0, phase = 0;
         for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
             for (int l = 0; l < n_layers; ++l) {
                 const int n = p.layer[l].n, kch = p.layer[l].kchunks;
                 const uint8_t* img = p.wimg + p.layer[l].img_off;
                 for (int h0 = 0; h0 < n; h0 += kPartN) {
                     const uint32_t bytes = (uint32_t)min(kPartN, n - h0) * 128u;
-                    for (int c = 0; c < kch; ++c) {
-                        mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
-                        if (elect_one_sync()) {
-                            mbar_arrive_expect_tx(bar_full + 8 * stage, bytes);
-                            bulk_g2s(s_stage + stage * kStageBytes, img + ((size_t)c * n + h0) * 128u, bytes, bar_full + 8 * stage);
-                        }
-                        __syncwarp();
-                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    mbar_wait(bar_empty + 8 * slot, phase ^ 1u);
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(bar_full + 8 * slot, bytes * (uint32_t)kch);
+                        for (int c = 0; c < kch; ++c)
+                            bulk_g2s(s_ring + slot * kSlotBytes + c * kChunkBytes, img + ((size_t)c * n + h0) * 128u, bytes, bar_full + 8 * slot);
                     }
+                    __syncwarp();
+                    if (++slot == kSlots) { slot = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer: tiles A (slot 0) and B (slot 1) of the pair alternate part by part and share every stage
-        uint32_t stage = 0, phase = 0, a_phase = 0;
+        // ===================== MMA issuer: tiles A (slot 0) and B (slot 1) of the pair alternate part by part and share every weight slot
+        uint32_t slot = 0, phase = 0, a_phase = 0;
         int dbg_n = lane == 0 ? 0 : kDbgCap;
-        const uint64_t bdesc0 = umma_desc_sw128(s_stage);
+        const uint64_t bdesc0 = umma_desc_sw128(s_ring);
         for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
             const int nt = (2 * pair + 1 < p.num_tiles) ? 2 : 1;
             for (int l = 0; l < n_layers; ++l) {
                 const int n = p.layer[l].n, kch = p.layer[l].kchunks;
                 for (int h0 = 0; h0 < n; h0 += kPartN) {
                     const uint32_t idesc = umma_idesc_bf16(kTileM, min(kPartN, n - h0));
-                    uint32_t st_end = stage, ph_end = phase;
+                    const uint64_t bdesc = bdesc0 + (uint64_t)(slot * (kSlotBytes >> 4));
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
                         if (t < nt) {
-                            TACO_DBG(0, dbg_n, 0x10 | t);
                             mbar_wait(bar_a + 8 * t, (a_phase >> t) & 1u); a_phase ^= (1u << t);   // D(t) free; A(t) of this layer in TMEM
+                            if (t == 0) mbar_wait(bar_full + 8 * slot, phase);
                             tc_fence_after();
                             TACO_DBG(0, dbg_n, 0x20 | t);
-                            const uint32_t a_addr = tmem0 + (uint32_t)(t * kTmemSlot);
-                            const uint32_t d_addr = a_addr + (uint32_t)kTmemD;
-                            uint32_t st = stage, ph = phase;
-                            for (int c = 0; c < kch; ++c) {
-                                if (t == 0) { mbar_wait(bar_full + 8 * st, ph); tc_fence_after(); }
-                                if (elect_one_sync()) {
-                                    const uint64_t bdesc = bdesc0 + (uint64_t)(st * (kStageBytes >> 4));
+                            if (elect_one_sync()) {
+                                const uint32_t a_addr = tmem0 + (uint32_t)(t * kTmemSlot);
+                                const uint32_t d_addr = a_addr + (uint32_t)kTmemD;
+                                for (int c = 0; c < kch; ++c) {
+                                    const uint64_t b_c = bdesc + (uint64_t)(c * (kChunkBytes >> 4));
                                     const uint32_t a_c = a_addr + (uint32_t)(c * (kKC / 2));
                                     // 16 bf16 along K = 8 packed TMEM columns of A = 32 bytes inside the B swizzle atom
-                                    umma_bf16_ts(d_addr, a_c, bdesc, idesc, (uint32_t)(c != 0));
-                                    umma_bf16_ts(d_addr, a_c + 8u, bdesc + 2u, idesc, 1u);
-                                    umma_bf16_ts(d_addr, a_c + 16u, bdesc + 4u, idesc, 1u);
-                                    umma_bf16_ts(d_addr, a_c + 24u, bdesc + 6u, idesc, 1u);
-                                    if (t == nt - 1) umma_commit(bar_empty + 8 * st);   // slot free once the last user's MMAs have read it
+                                    umma_bf16_ts(d_addr, a_c, b_c, idesc, (uint32_t)(c != 0));
+                                    umma_bf16_ts(d_addr, a_c + 8u, b_c + 2u, idesc, 1u);
+                                    umma_bf16_ts(d_addr, a_c + 16u, b_c + 4u, idesc, 1u);
+                                    umma_bf16_ts(d_addr, a_c + 24u, b_c + 6u, idesc, 1u);
                                 }
-                                __syncwarp();
-                                if (++st == kStages) { st = 0; ph ^= 1u; }
+                                if (t == nt - 1) umma_commit(bar_empty + 8 * slot);   // slot free once the last user's MMAs have read it
+                                umma_commit(bar_d + 8 * t);
                             }
-                            if (elect_one_sync()) umma_commit(bar_d + 8 * t);
                             __syncwarp();
                             TACO_DBG(0, dbg_n, 0x30 | t);
-                            st_end = st; ph_end = ph;
                         }
                     }
-                    stage = st_end; phase = ph_end;
+                    if (++slot == kSlots) { slot = 0; phase ^= 1u; }
                 }
             }
         }
@@ -339,39 +348,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
         const uint32_t t_d = t_a + (uint32_t)kTmemD + (uint32_t)(ch * 64);
         uint32_t d_phase = 0;
         const int kc0 = p.layer[0].kchunks;
-        const size_t row_bytes = (size_t)p.in_dim * sizeof(float);
         int dbg_n = (ch == 0 && quad == 0 && lane == 0) ? 0 : kDbgCap;
-        for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-            const int tile = 2 * pair + t;
-            if (tile >= p.num_tiles) break;                           // odd tail: slot 1 has no tile (and this is the CTA's last pair)
+        int tile = 2 * (int)blockIdx.x + t;
+        const int tile_step = 2 * (int)gridDim.x;
+        if (tile < p.num_tiles) {
+            // ---- the first tile's observation row as packed bf16 into A(t), K padded with zeros to kc0 * 64; groups of 32
+            // features (16 TMEM columns) alternate between ch 0 / 1
+            const long long row0 = (long long)tile * kTileM + r;
+            for (int g = ch; g < kc0 * 2; g += 2) {
+                uint32_t pk[16];
+                load_obs_group(p.obs + row0 * p.in_dim, g, p.in_dim, row0 < p.n_rows, pk);
+                tmem_st16(t_a + (uint32_t)(g * 16), pk);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_a + 8 * t);
+            TACO_DBG(1 + t, dbg_n, 0x01);
+        }
+        for (; tile < p.num_tiles; tile += tile_step) {
             const long long row = (long long)tile * kTileM + r;
             const bool valid = row < p.n_rows;
-            // ---- the observation row as packed bf16 into A(t), K padded with zeros to kc0 * 64; groups of 32 features
-            // (16 TMEM columns) alternate between ch 0 / 1.  D(t) of the previous pair is drained at this point.
-            {
-                const float* x = p.obs + row * p.in_dim;
-                for (int g = ch; g < kc0 * 2; g += 2) {
-                    uint32_t pk[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int k = g * 32 + 2 * j;
-                        const float f0 = (valid && k < p.in_dim) ? __ldg(x + k) : 0.0f;
-                        const float f1 = (valid && k + 1 < p.in_dim) ? __ldg(x + k + 1) : 0.0f;
-                        pk[j] = pack_bf16x2(f0, f1);
-                    }
-                    tmem_st16(t_a + (uint32_t)(g * 16), pk);
-                }
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(bar_a + 8 * t);
-                TACO_DBG(1 + t, dbg_n, 0x01);
-                // pull the row this thread stages for the CTA's NEXT pair towards L2 while this pair computes
-                const long long row_next = row + 2ll * gridDim.x * kTileM;
-                if (ch == 0 && row_next < p.n_rows) {
-                    const char* xn = reinterpret_cast<const char*>(p.obs + row_next * p.in_dim);
-                    for (size_t o = 0; o < row_bytes; o += 128) prefetch_l2(xn + o);
-                }
-            }
+            const bool has_next = tile + tile_step < p.num_tiles;
+            const long long row_next = row + (long long)tile_step * kTileM;
+            const float* x_next = p.obs + row_next * p.in_dim;
+            if (has_next && row_next < p.n_rows) prefetch_l2(x_next + ch * 32);   // this thread's first group of the next tile
             for (int l = 0; l < p.n_hidden; ++l) {
                 // hidden layer: relu(D + bias) as bf16 pairs, held in registers until every MMA of the layer has read A(t), then
                 // written over A(t) as the next layer's operand
@@ -413,21 +413,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
                 mbar_arrive(bar_a + 8 * t);
                 TACO_DBG(1 + t, dbg_n, 0x05);
             }
-            // ---- output layer (columns 0..3 of its 16-wide part) + tanh / sampling; the arrive after staging the next pair
-            // tells the MMA issuer that D(t) is drained
+            // ---- output layer (columns 0..3 of its 16-wide part).  The next tile's first observation group is fetched while the
+            // output MMAs run; once D is in registers the next A(t) is written and the issuer released, and only then the tanh /
+            // sampling tail of this tile runs (overlapping the next tile's first MMAs).
+            uint32_t pkn[16];
+            if (has_next) load_obs_group(x_next, ch, p.in_dim, row_next < p.n_rows, pkn);
             mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
             tc_fence_after();
             TACO_DBG(1 + t, dbg_n, 0x06);
-            if (ch == 0) {
-                uint32_t v[32];
-                tmem_ld32(t_d, v); tmem_ld_wait();
-                tc_fence_before();
-                if (valid) {
-                    float pre[kOutPad];
-#pragma unroll
-                    for (int o = 0; o < kOutPad; ++o) pre[o] = __uint_as_float(v[o]) + __ldg(p.b_out + o);
-                    actor_tail(pre, p.out_dim, row, p.mean, p.sp);
+            uint32_t v[4];
+            if (ch == 0) { tmem_ld4(t_d, v); tmem_ld_wait(); }
+            if (has_next) {
+                tmem_st16(t_a + (uint32_t)(ch * 16), pkn);
+                for (int g = ch + 2; g < kc0 * 2; g += 2) {
+                    load_obs_group(x_next, g, p.in_dim, row_next < p.n_rows, pkn);
+                    tmem_st16(t_a + (uint32_t)(g * 16), pkn);
                 }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(bar_a + 8 * t);
+                TACO_DBG(1 + t, dbg_n, 0x01);
+            }
+            if (ch == 0 && valid) {
+                float pre[kOutPad];
+#pragma unroll
+                for (int o = 0; o < kOutPad; ++o) pre[o] = __uint_as_float(v[o]) + __ldg(p.b_out + o);
+                actor_tail(pre, p.out_dim, row, p.mean, p.sp);
             }
             TACO_DBG(1 + t, dbg_n, 0x07);
         }
