@@ -170,6 +170,20 @@ int taco_actor_act(TacoActor* actor, const float* obs_dev, int32_t n, const floa
                    uint64_t seed, uint32_t step_index, float* mean_dev, float* action_dev, float* clipped_dev,
                    float* logp_dev, int32_t use_tensor_cores, void* stream);
 
+/* -- rollout-buffer post-processing: PPOReplayBuffer.compute_returns_and_advantage
+ * (IsaacGymEnvs/algorithms/buffer_asymmetry.py:93-132) and the time-out bootstrap PPO applies to the reward it stores
+ * (IsaacGymEnvs/algorithms/ppo_asymmetry.py:313-324).  All buffers are contiguous float32 (horizon, num_envs[, 1]) on
+ * `device`, like the reference's rew_buf / done_buf / value_buf / adv_buf / ret_buf; last_value is (num_envs[, 1]).
+ * taco_gae_advantages: backward GAE(lambda) scan -> adv (un-normalised), ret = adv + value, and moments_dev[0..2] =
+ * [sum adv, sum adv^2, sample count] in float64 (overwritten).  time_outs_dev (horizon, num_envs) bool/u8 may be NULL;
+ * when given, rew + gamma * value is used for the steps with time_outs * done != 0.  A multi-GPU job all-reduces (SUM)
+ * the three moments, then every rank calls taco_gae_normalize(adv, horizon * num_envs, moments): adv = (adv - mean) /
+ * (std + 1e-8) with the unbiased std of ALL samples (buffer_asymmetry.py:132).  Asynchronous on `stream`, no host sync. */
+int taco_gae_advantages(int device, int32_t horizon, int32_t num_envs, const float* rew_dev, const float* done_dev,
+                        const uint8_t* time_outs_dev, const float* value_dev, const float* last_value_dev, float gamma, float lam,
+                        float* adv_dev, float* ret_dev, double* moments_dev, void* stream);
+int taco_gae_normalize(int device, float* adv_dev, int64_t count, const double* moments_dev, void* stream);
+
 /* -- self-test: exhaustive comparison (all float bit patterns with |x| in [2^-60, 2^60]) of the kernel's 3-instruction
  * division-by-constant against IEEE division, for every divisor the step kernel uses; writes the mismatch count. */
 int taco_selftest_divc(int device, float dt, uint64_t* n_mismatch);

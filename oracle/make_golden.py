@@ -198,6 +198,33 @@ def actor(ns):
     np.savez(os.path.join(OUT, "actor.npz"), **{k: np.asarray(t) for k, t in out.items()})
 
 
+def gae(ns):
+    """PPOReplayBuffer.store / compute_returns_and_advantage (buffer_asymmetry.py:49-68,93-132) run from the reference's
+    own class, with the time-out bootstrap of ppo_asymmetry.py:313-324 applied to the stored reward."""
+    torch.manual_seed(31)
+    H, N, gamma, lam = 12, 77, 0.99, 0.95
+    buf = ns.buffer.PPOReplayBuffer(N, 26, 1, 26, 5, 4, H, 4, gamma, lam, "cpu")
+    rew = torch.rand(H, N) * 0.02
+    value = torch.randn(H, N, 1) * 0.3 + 0.5
+    done = (torch.rand(H, N) < 0.08).float()
+    time_outs = (torch.rand(H, N) < 0.5)
+    last_value = torch.randn(N, 1) * 0.3 + 0.5
+    rew_aug = rew.clone()
+    for s in range(H):
+        # ppo_asymmetry.py:313-324: truncated envs get gamma * V(pre-step obs, states) = gamma * value[s]
+        ids = (time_outs[s] * done[s]).nonzero(as_tuple=False).squeeze(-1).tolist()
+        r = rew[s].clone()
+        if ids:
+            r[ids] += gamma * value[s, ids].squeeze()
+        rew_aug[s] = r
+        z = torch.zeros
+        buf.store(z(N, 1, 26), z(N, 5, 26), z(N, 4), r, z(N), done[s], value[s], z(N, 4), z(N, 4))
+    buf.compute_returns_and_advantage(last_value)
+    out = dict(rew=rew, rew_aug=rew_aug, value=value, done=done, time_outs=time_outs.to(torch.uint8), last_value=last_value,
+               gamma=torch.tensor(gamma), lam=torch.tensor(lam), adv_norm=buf.adv_buf, ret=buf.ret_buf)
+    np.savez(os.path.join(OUT, "gae.npz"), **{k: np.asarray(t) for k, t in out.items()})
+
+
 def main():
     assert ref_loader.available(), "needs the reference tree (build container only)"
     os.makedirs(OUT, exist_ok=True)
@@ -207,6 +234,7 @@ def main():
     dynamics(ns)
     rewards(ns)
     actor(ns)
+    gae(ns)
     print("golden vectors written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  ", f, os.path.getsize(os.path.join(OUT, f)), "bytes")

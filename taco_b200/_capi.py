@@ -81,6 +81,8 @@ def lib():
         "taco_actor_weights": (C.c_int, [vp, i32, vp, vp]),
         "taco_actor_tc_available": (C.c_int, [vp]),
         "taco_actor_act": (C.c_int, [vp, vp, i32, vp, C.c_int64, u64, u32, vp, vp, vp, vp, i32, vp]),
+        "taco_gae_advantages": (C.c_int, [C.c_int, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp]),
+        "taco_gae_normalize": (C.c_int, [C.c_int, vp, C.c_int64, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)          # AttributeError if the symbol is not exported

@@ -1,0 +1,101 @@
+"""Host-side mirror of the reference rollout buffer, with the return / advantage pass on the device.
+
+Mirrors ``PPOReplayBuffer`` (IsaacGymEnvs/algorithms/buffer_asymmetry.py:9-139): same constructor arguments, same buffer
+attributes and shapes (``obs_buf (H,N,Lo,26)``, ``states_buf``, ``act_buf``, ``rew_buf (H,N,1)``, ``done_buf``, ``ret_buf``,
+``value_buf``, ``adv_buf``, ``mu_buf``, ``sigma_buf``, ``logp_buf``), ``store``, ``reset``, ``compute_returns_and_advantage``
+and ``batch_idx_generator``.  Differences, all on purpose:
+
+  * ``compute_returns_and_advantage`` is two CUDA launches behind the C ABI (``taco_gae_advantages`` / ``taco_gae_normalize``,
+    csrc/taco_gae.cu) instead of a Python loop over the horizon plus two full-buffer reductions; under
+    ``torch.distributed`` the three float64 moments [sum, sum^2, n] are all-reduced so that every rank normalises with the
+    statistics of ALL envs of the job (buffer_asymmetry.py:132 semantics for the sharded rollout);
+  * ``store`` accepts ``time_outs``: the bootstrap of truncated episodes (ppo_asymmetry.py:313-324) then happens inside
+    the device pass with no ``nonzero().tolist()`` host round trip;
+  * ``reset`` only rewinds the write index (the reference re-allocates every buffer each epoch, buffer_asymmetry.py:70-91;
+    every slot is overwritten by the next rollout before it is read).
+There is no CPU fallback: the buffer lives on a CUDA device.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _capi
+
+
+class RolloutBuffer:
+    def __init__(self, num_envs, obs_dim, obs_len, states_dim, states_len, act_dim, horizon_len, mini_batch_num, gamma, lam, device):
+        dev = torch.device(device)
+        if dev.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("RolloutBuffer runs on CUDA only; there is no CPU path")
+        self.num_envs, self.obs_dim, self.obs_len = int(num_envs), int(obs_dim), int(obs_len)
+        self.states_dim, self.states_len, self.act_dim = int(states_dim), int(states_len), int(act_dim)
+        self.horizon_len, self.mini_batch_num = int(horizon_len), int(mini_batch_num)
+        self.gamma, self.lam = float(gamma), float(lam)
+        self.device = dev
+        self.device_id = dev.index if dev.index is not None else torch.cuda.current_device()
+        self._lib = _capi.lib()
+        H, N = self.horizon_len, self.num_envs
+        z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=dev)
+        self.obs_buf = z(H, N, self.obs_len, self.obs_dim)
+        self.states_buf = z(H, N, self.states_len, self.states_dim)
+        self.act_buf = z(H, N, self.act_dim)
+        self.rew_buf = z(H, N, 1)
+        self.done_buf = z(H, N, 1)
+        self.timeout_buf = z(H, N, 1, dtype=torch.uint8)
+        self.ret_buf = z(H, N, 1)
+        self.value_buf = z(H, N, 1)
+        self.adv_buf = z(H, N, 1)
+        self.mu_buf = z(H, N, self.act_dim)
+        self.sigma_buf = z(H, N, self.act_dim)
+        self.logp_buf = z(H, N, 1)
+        self.moments = torch.zeros(3, dtype=torch.float64, device=dev)     # [sum adv, sum adv^2, samples], all ranks after the reduce
+        self._have_timeouts = False
+        self.step = 0
+
+    def store(self, obs, states, act, rew, log_prob, done, value, mu, sigma, time_outs=None):
+        """buffer_asymmetry.py:49-68.  ``rew`` is the RAW env reward when ``time_outs`` is given (the bootstrap is applied
+        in compute_returns_and_advantage), else the already-augmented reward like the reference."""
+        if self.step >= self.horizon_len:
+            raise AssertionError("Rollout buffer overflow")
+        s = self.step
+        self.obs_buf[s].copy_(obs)
+        self.states_buf[s].copy_(states)
+        self.act_buf[s].copy_(act)
+        self.rew_buf[s].copy_(rew.view(-1, 1))
+        self.done_buf[s].copy_(done.view(-1, 1))
+        self.value_buf[s].copy_(value)
+        self.mu_buf[s].copy_(mu)
+        self.sigma_buf[s].copy_(sigma)
+        self.logp_buf[s].copy_(log_prob.view(-1, 1))
+        if time_outs is not None:
+            self.timeout_buf[s].copy_(time_outs.view(-1, 1))
+            self._have_timeouts = True
+        elif s == 0:
+            self._have_timeouts = False
+        self.step += 1
+
+    def reset(self):
+        self.step = 0
+
+    def compute_returns_and_advantage(self, last_values, group=None):
+        """buffer_asymmetry.py:93-132 on the device; fills ret_buf and the normalised adv_buf.  Asynchronous."""
+        last = last_values.detach().to(self.device, torch.float32).contiguous().view(-1)
+        if last.numel() != self.num_envs:
+            raise ValueError(f"last_values must hold {self.num_envs} values")
+        stream = C.c_void_p(torch.cuda.current_stream(self.device_id).cuda_stream)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        tout = p(self.timeout_buf) if self._have_timeouts else C.c_void_p(0)
+        _capi.check(self._lib.taco_gae_advantages(self.device_id, self.horizon_len, self.num_envs, p(self.rew_buf), p(self.done_buf), tout,
+                                                  p(self.value_buf), p(last), self.gamma, self.lam, p(self.adv_buf), p(self.ret_buf),
+                                                  p(self.moments), stream), "taco_gae_advantages")
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.moments, op=dist.ReduceOp.SUM, group=group)          # 3 doubles: the path's second tiny collective
+        _capi.check(self._lib.taco_gae_normalize(self.device_id, p(self.adv_buf), self.horizon_len * self.num_envs, p(self.moments), stream),
+                    "taco_gae_normalize")
+        self._keep = last
+
+    def batch_idx_generator(self):
+        """buffer_asymmetry.py:134-139."""
+        n = self.num_envs * self.horizon_len
+        return torch.randperm(n).reshape(self.mini_batch_num, -1).tolist()
