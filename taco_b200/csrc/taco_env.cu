@@ -53,7 +53,8 @@ struct TacoEnv {
     uint32_t step_index = 0;
     // host-buffer pipeline (taco_env_step_host): copy-in / kernel / copy-out of successive env chunks overlap
     static constexpr int kMaxChunks = 16;
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    static constexpr int kKernelStreams = 3;     // chunk kernels rotate over these so that a chunk's tail wave overlaps the next chunk
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_k[kKernelStreams] = {};
     cudaEvent_t ev_h2d[kMaxChunks] = {}, ev_k[kMaxChunks] = {}, ev_begin = nullptr, ev_end = nullptr;
     bool pipe_ready = false;
 };
@@ -341,6 +342,7 @@ int taco_env_destroy(TacoEnv* env) {
     DeviceGuard guard(env->device);
     if (env->pipe_ready) {
         cudaStreamDestroy(env->s_h2d); cudaStreamDestroy(env->s_d2h);
+        for (int k = 0; k < TacoEnv::kKernelStreams; ++k) cudaStreamDestroy(env->s_k[k]);
         for (int c = 0; c < TacoEnv::kMaxChunks; ++c) { cudaEventDestroy(env->ev_h2d[c]); cudaEventDestroy(env->ev_k[c]); }
         cudaEventDestroy(env->ev_begin); cudaEventDestroy(env->ev_end);
     }
@@ -385,6 +387,7 @@ static int pipe_init(TacoEnv* env) {
     if (env->pipe_ready) return TACO_OK;
     TACO_CUDA(cudaStreamCreateWithFlags(&env->s_h2d, cudaStreamNonBlocking));
     TACO_CUDA(cudaStreamCreateWithFlags(&env->s_d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < TacoEnv::kKernelStreams; ++k) TACO_CUDA(cudaStreamCreateWithFlags(&env->s_k[k], cudaStreamNonBlocking));
     for (int c = 0; c < TacoEnv::kMaxChunks; ++c) {
         TACO_CUDA(cudaEventCreateWithFlags(&env->ev_h2d[c], cudaEventDisableTiming));
         TACO_CUDA(cudaEventCreateWithFlags(&env->ev_k[c], cudaEventDisableTiming));
@@ -397,7 +400,9 @@ static int pipe_init(TacoEnv* env) {
 
 // The step through HOST buffers.  Envs are independent, so the shard is cut into chunks of whole CTAs and the three
 // legs of successive chunks overlap: chunk c+1's actions cross PCIe while chunk c steps and chunk c-1's results return
-// (H2D and D2H use opposite directions of the link).  The kernel chunks run on the caller's stream, in order.
+// (H2D and D2H use opposite directions of the link).  Chunk kernels rotate over a few internal streams, so the partial
+// last wave of one chunk overlaps the first wave of the next; everything is ordered after the work already queued on
+// the caller's stream, which in turn waits for the last copy before the call synchronises it.
 int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host, int64_t* reset_host, uint8_t* time_outs_host,
                        void* stream) {
     if (!env || !actions_host) return fail(TACO_E_INVALID, "taco_env_step_host: null argument");
@@ -407,44 +412,61 @@ int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host,
     if (rc != TACO_OK) return rc;
     StepParams& p = env->p;
     const int total_blocks = env->n_pad / kBlock;
-    // chunk = at least 64 Ki envs (4 waves of CTAs), at most kMaxChunks chunks
-    int nchunks = total_blocks / 512;
-    if (nchunks < 1) nchunks = 1;
-    if (nchunks > TacoEnv::kMaxChunks) nchunks = TacoEnv::kMaxChunks;
-    const int per = (total_blocks + nchunks - 1) / nchunks;
+    // 4 equal chunks of at least 512 CTAs (64 Ki envs): measured best of 4 / 8 / 12 / 16 equal chunks and of a graded
+    // 1-2-4-5-3-1 schedule at 2 Mi envs (per-copy and per-launch overheads outweigh shorter fill / drain phases; the call
+    // is bound by the 16 B/env action upload at ~50 GB/s).  TACO_HOST_CHUNKS=<n> overrides (tuning aid).
+    static const int forced_chunks = [] { const char* e = getenv("TACO_HOST_CHUNKS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 0; }();
+    int bounds[TacoEnv::kMaxChunks + 1];
+    int nchunks = 0;
+    bounds[0] = 0;
+    {
+        int want = forced_chunks ? forced_chunks : 4;
+        if (want > TacoEnv::kMaxChunks) want = TacoEnv::kMaxChunks;
+        int per = (total_blocks + want - 1) / want;
+        if (per < 512) per = 512;
+        for (int b = per; nchunks < TacoEnv::kMaxChunks; b += per) { bounds[++nchunks] = b < total_blocks ? b : total_blocks; if (b >= total_blocks) break; }
+    }
+    bounds[nchunks] = total_blocks;
     const int nxt = env->cur ^ 1;
     p.actions = (const float4*)env->actions_stage;
     p.obs_in = env->obs_ab[env->cur]; p.obs_out = env->obs_ab[nxt];
     p.states_in = env->states_ab[env->cur]; p.states_out = env->states_ab[nxt];
     p.step_index = env->step_index;
     const bool strict = (env->cfg.flags & TACO_F_STRICT_FP) != 0;
+    const bool want_out = rew_host || reset_host || time_outs_host;
     TACO_CUDA(cudaEventRecord(env->ev_begin, s));                    // work already queued on the caller's stream comes first
     TACO_CUDA(cudaStreamWaitEvent(env->s_h2d, env->ev_begin, 0));
+    for (int k = 0; k < TacoEnv::kKernelStreams; ++k) TACO_CUDA(cudaStreamWaitEvent(env->s_k[k], env->ev_begin, 0));
     for (int c = 0; c < nchunks; ++c) {
-        const int b0 = c * per, b1 = (b0 + per < total_blocks) ? b0 + per : total_blocks;
-        if (b0 >= b1) { nchunks = c; break; }
+        const int b0 = bounds[c], b1 = bounds[c + 1];
+        if (b0 >= b1) continue;
         const size_t e0 = (size_t)b0 * kBlock;
         const size_t e1 = ((size_t)b1 * kBlock < (size_t)env->n) ? (size_t)b1 * kBlock : (size_t)env->n;
         const size_t cnt = e1 - e0;
+        cudaStream_t sk = env->s_k[c % TacoEnv::kKernelStreams];
         TACO_CUDA(cudaMemcpyAsync(env->actions_stage + e0, actions_host + e0 * 4, cnt * 4 * sizeof(float), cudaMemcpyHostToDevice, env->s_h2d));
         TACO_CUDA(cudaEventRecord(env->ev_h2d[c], env->s_h2d));
-        TACO_CUDA(cudaStreamWaitEvent(s, env->ev_h2d[c], 0));
+        TACO_CUDA(cudaStreamWaitEvent(sk, env->ev_h2d[c], 0));
         p.block0 = b0; p.nblocks = b1 - b0;
-        if (strict) launch_fpv_step_strict(p, s); else launch_fpv_step_fast(p, s);
+        if (strict) launch_fpv_step_strict(p, sk); else launch_fpv_step_fast(p, sk);
         TACO_CUDA(cudaGetLastError());
-        if (rew_host || reset_host || time_outs_host) {
-            TACO_CUDA(cudaEventRecord(env->ev_k[c], s));
+        TACO_CUDA(cudaEventRecord(env->ev_k[c], sk));
+        if (want_out) {
             TACO_CUDA(cudaStreamWaitEvent(env->s_d2h, env->ev_k[c], 0));
-            if (rew_host) TACO_CUDA(cudaMemcpyAsync(rew_host + e0, p.rew + e0, cnt * sizeof(float), cudaMemcpyDeviceToHost, env->s_d2h));
             if (reset_host) TACO_CUDA(cudaMemcpyAsync(reset_host + e0, p.reset_buf + e0, cnt * sizeof(int64_t), cudaMemcpyDeviceToHost, env->s_d2h));
+            if (rew_host) TACO_CUDA(cudaMemcpyAsync(rew_host + e0, p.rew + e0, cnt * sizeof(float), cudaMemcpyDeviceToHost, env->s_d2h));
             if (time_outs_host) TACO_CUDA(cudaMemcpyAsync(time_outs_host + e0, p.time_outs + e0, cnt, cudaMemcpyDeviceToHost, env->s_d2h));
+        } else {
+            TACO_CUDA(cudaStreamWaitEvent(s, env->ev_k[c], 0));
         }
     }
     p.block0 = 0; p.nblocks = 0;
     env->cur = nxt;
     env->step_index += 1;
-    TACO_CUDA(cudaEventRecord(env->ev_end, env->s_d2h));
-    TACO_CUDA(cudaStreamWaitEvent(s, env->ev_end, 0));               // the caller's stream also orders after the copies
+    if (want_out) {
+        TACO_CUDA(cudaEventRecord(env->ev_end, env->s_d2h));         // s_d2h has waited for every chunk kernel
+        TACO_CUDA(cudaStreamWaitEvent(s, env->ev_end, 0));
+    }
     TACO_CUDA(cudaStreamSynchronize(s));
     return TACO_OK;
 }
