@@ -118,6 +118,19 @@ int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host,
 /* -- VecTask.reset (vec_task_asymmetry.py:352-361) does not simulate; this additionally marks every env for
  * reset on the next step and zeroes the observation history, i.e. restores the freshly-constructed state. */
 int taco_env_reset_all(TacoEnv* env, void* stream);
+/* -- zero-copy rollout storage: what PPOReplayBuffer.store copies every step (IsaacGymEnvs/algorithms/buffer_asymmetry.py:49-68:
+ * obs_buf (H,N,Lo,26), states_buf (H,N,Ls,26), rew_buf, done_buf) the step kernel writes in place.  obs_ring / states_ring
+ * are caller-owned contiguous float32 device buffers of `slots` = horizon + 1 slots of (num_envs, len, 26); with a ring
+ * attached, step k of a rollout reads the history in slot k and writes slot k + 1 (slot k is exactly what the agent saw
+ * before step k, i.e. obs_buf[k] / states_buf[k]) and, when the row pointers are given, rew_rows[k] / done_rows[k] (float32
+ * (horizon, num_envs)) and time_out_rows[k] (u8).  Attaching copies the newest history into slot 0; stepping with the
+ * ring full fails with TACO_E_INVALID; taco_env_rewind_rollout moves the newest slot to slot 0 for the next rollout;
+ * taco_env_detach_rollout returns to the env's own double buffer.  taco_env_buffers reports the newest slot. */
+int taco_env_attach_rollout(TacoEnv* env, float* obs_ring, float* states_ring, int32_t slots, float* rew_rows, float* done_rows,
+                            uint8_t* time_out_rows, void* stream);
+int taco_env_rewind_rollout(TacoEnv* env, void* stream);
+int taco_env_detach_rollout(TacoEnv* env, void* stream);
+int taco_env_rollout_cursor(TacoEnv* env);   /* newest slot index, or -1 when no ring is attached */
 /* -- env.difficulty is written by the trainer every epoch (algorithms/ppo_asymmetry.py:173-175) */
 int taco_env_set_difficulty(TacoEnv* env, float difficulty);
 int taco_env_set_seed(TacoEnv* env, uint64_t seed);

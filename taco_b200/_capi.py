@@ -65,6 +65,10 @@ def lib():
         "taco_env_step": (C.c_int, [vp, vp, vp]),
         "taco_env_step_host": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "taco_env_reset_all": (C.c_int, [vp, vp]),
+        "taco_env_attach_rollout": (C.c_int, [vp, vp, vp, i32, vp, vp, vp, vp]),
+        "taco_env_rewind_rollout": (C.c_int, [vp, vp]),
+        "taco_env_detach_rollout": (C.c_int, [vp, vp]),
+        "taco_env_rollout_cursor": (C.c_int, [vp]),
         "taco_env_set_difficulty": (C.c_int, [vp, f32]),
         "taco_env_set_seed": (C.c_int, [vp, u64]),
         "taco_env_stats": (C.c_int, [vp, vp, vp, vp]),

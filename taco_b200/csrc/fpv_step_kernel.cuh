@@ -40,16 +40,18 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
 // One CTA writes its 128 rows of an (N, L, 26) history buffer: frames 1..L-1 of the previous buffer shifted down by one
 // (coalesced 64-bit copies: a row is 13*L float2, the shift is 13 float2) and the newest frame from shared memory.
-// LC = compile-time L (fast paths for the README shapes L=5 / L=1), 0 = runtime L.
+// LC = compile-time L (fast paths for the README shapes L=5 / L=1), 0 = runtime L.  nv = valid rows of this CTA (only the
+// last CTA of a shard whose env count is not a multiple of 128 has nv < 128): rows >= nv are never touched, so the
+// buffers may be exactly (num_envs, L, 26) -- e.g. a slot of a caller-owned rollout ring.
 template <int LC>
 __device__ __forceinline__ void write_rows(const float* __restrict__ in, float* __restrict__ out, const float* frames,
-                                           int L_rt, size_t blk_env0, int tid) {
+                                           int L_rt, size_t blk_env0, int tid, int nv) {
     const int L = LC ? LC : L_rt;
     const int row2 = 13 * L, keep2 = 13 * (L - 1);
     const float2* in2 = reinterpret_cast<const float2*>(in) + blk_env0 * row2;
     float2* out2 = reinterpret_cast<float2*>(out) + blk_env0 * row2;
     if (keep2 > 0) {
-        const int total = kBlock * keep2;                       // multiple of kBlock
+        const int total = nv * keep2;
         constexpr int U = 13;                                   // loads in flight per thread
         for (int k0 = tid; k0 < total; k0 += kBlock * U) {
             float2 v[U];
@@ -71,7 +73,7 @@ __device__ __forceinline__ void write_rows(const float* __restrict__ in, float* 
         const int k = tid + u * kBlock;
         const int e = k / 13, j = k - e * 13;
         const float* fr = frames + e * kFramePad + 2 * j;
-        out2[e * row2 + keep2 + j] = make_float2(fr[0], fr[1]);
+        if (e < nv) out2[e * row2 + keep2 + j] = make_float2(fr[0], fr[1]);
     }
 }
 
@@ -583,6 +585,11 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
         p.reset_buf[i] = done ? 1ll : 0ll;
         p.time_outs[i] = tout ? 1 : 0;
         p.rew[i] = rew;
+        if (p.roll_rew) {       // rows of an attached rollout buffer: rew_buf / done_buf as float32, time-outs as bytes
+            p.roll_rew[i] = rew;
+            p.roll_done[i] = done ? 1.0f : 0.0f;
+            p.roll_tout[i] = tout ? 1 : 0;
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < 26; ++j) { fc[j] = 0.f; fn[j] = 0.f; }
@@ -611,11 +618,12 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
     // ---------------------------------------------------------------------- history shift + newest frame (:392,:413)
     // out[e][f][:] = in[e][f+1][:] for f < L-1, newest frame last; ping-pong buffers, so no in-place hazard.
     const size_t blk_env0 = (size_t)blk * kBlock;
-    if (p.len_states == 5) write_rows<5>(p.states_in, p.states_out, s_clean, 5, blk_env0, tid);
-    else write_rows<0>(p.states_in, p.states_out, s_clean, p.len_states, blk_env0, tid);
+    const int nv = min(kBlock, p.n - blk * kBlock);
+    if (p.len_states == 5) write_rows<5>(p.states_in, p.states_out, s_clean, 5, blk_env0, tid, nv);
+    else write_rows<0>(p.states_in, p.states_out, s_clean, p.len_states, blk_env0, tid, nv);
     const float* sf = obs_noise ? s_noisy : s_clean;
-    if (p.len_obs == 1) write_rows<1>(p.obs_in, p.obs_out, sf, 1, blk_env0, tid);
-    else write_rows<0>(p.obs_in, p.obs_out, sf, p.len_obs, blk_env0, tid);
+    if (p.len_obs == 1) write_rows<1>(p.obs_in, p.obs_out, sf, 1, blk_env0, tid, nv);
+    else write_rows<0>(p.obs_in, p.obs_out, sf, p.len_obs, blk_env0, tid, nv);
 }
 
 template <int TASK>

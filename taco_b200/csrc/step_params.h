@@ -44,6 +44,9 @@ struct StepParams {
     float* obs_out;
     const float* states_in;
     float* states_out;
+    float* roll_rew;               // row of the attached rollout buffer for this step (or null): rew, done as f32, time-outs
+    float* roll_done;
+    uint8_t* roll_tout;
     double* stats;                 // [kStatSlots][kStatStride]
     float4* dbg_delay;             // [cfi][n_pad] or null
 };

@@ -46,6 +46,13 @@ struct TacoEnv {
     float* obs_ab[2] = {nullptr, nullptr};
     float* states_ab[2] = {nullptr, nullptr};
     int cur = 0;                 // index of the buffers holding the latest obs/states
+    // caller-owned rollout ring (taco_env_attach_rollout): slot k of obs / states, row k of rew / done / time-outs
+    float* ring_obs = nullptr;
+    float* ring_states = nullptr;
+    float* ring_rew = nullptr;
+    float* ring_done = nullptr;
+    uint8_t* ring_tout = nullptr;
+    int ring_slots = 0, ring_cur = 0;
     float4* actions_stage = nullptr;   // device staging for taco_env_step_host
     double* stats_out = nullptr;       // 8 doubles, device
     float* export_stage = nullptr;     // n * TACO_STATE_WORDS floats, device
@@ -354,8 +361,13 @@ int taco_env_destroy(TacoEnv* env) {
 
 int taco_env_buffers(TacoEnv* env, TacoBuffers* out) {
     if (!env || !out) return fail(TACO_E_INVALID, "taco_env_buffers: null argument");
-    out->obs = env->obs_ab[env->cur];
-    out->states = env->states_ab[env->cur];
+    if (env->ring_slots) {
+        out->obs = env->ring_obs + (size_t)env->n * env->cfg.len_obs * kObs * env->ring_cur;
+        out->states = env->ring_states + (size_t)env->n * env->cfg.len_states * kObs * env->ring_cur;
+    } else {
+        out->obs = env->obs_ab[env->cur];
+        out->states = env->states_ab[env->cur];
+    }
     out->rew = env->p.rew;
     out->reset = (int64_t*)env->p.reset_buf;
     out->time_outs = env->p.time_outs;
@@ -365,21 +377,44 @@ int taco_env_buffers(TacoEnv* env, TacoBuffers* out) {
     return TACO_OK;
 }
 
+// history buffers of the next step: the env's own ping-pong pair, or consecutive slots of the attached rollout ring
+static int bind_history(TacoEnv* env) {
+    StepParams& p = env->p;
+    if (env->ring_slots) {
+        if (env->ring_cur + 1 >= env->ring_slots)
+            return fail(TACO_E_INVALID, "rollout ring is full: call taco_env_rewind_rollout before stepping again");
+        const size_t so = (size_t)env->n * env->cfg.len_obs * kObs, ss = (size_t)env->n * env->cfg.len_states * kObs;
+        p.obs_in = env->ring_obs + so * env->ring_cur; p.obs_out = env->ring_obs + so * (env->ring_cur + 1);
+        p.states_in = env->ring_states + ss * env->ring_cur; p.states_out = env->ring_states + ss * (env->ring_cur + 1);
+        p.roll_rew = env->ring_rew ? env->ring_rew + (size_t)env->n * env->ring_cur : nullptr;
+        p.roll_done = env->ring_rew ? env->ring_done + (size_t)env->n * env->ring_cur : nullptr;
+        p.roll_tout = env->ring_rew ? env->ring_tout + (size_t)env->n * env->ring_cur : nullptr;
+    } else {
+        const int nxt = env->cur ^ 1;
+        p.obs_in = env->obs_ab[env->cur]; p.obs_out = env->obs_ab[nxt];
+        p.states_in = env->states_ab[env->cur]; p.states_out = env->states_ab[nxt];
+        p.roll_rew = nullptr; p.roll_done = nullptr; p.roll_tout = nullptr;
+    }
+    return TACO_OK;
+}
+static void advance_history(TacoEnv* env) {
+    if (env->ring_slots) env->ring_cur += 1; else env->cur ^= 1;
+    env->step_index += 1;
+}
+
 int taco_env_step(TacoEnv* env, const float* actions_dev, void* stream) {
     if (!env || !actions_dev) return fail(TACO_E_INVALID, "taco_env_step: null argument");
     if (((uintptr_t)actions_dev & 15u) != 0) return fail(TACO_E_INVALID, "actions must be 16-byte aligned (contiguous (N,4) float32)");
     DeviceGuard guard(env->device);
     StepParams& p = env->p;
-    const int nxt = env->cur ^ 1;
+    const int rc = bind_history(env);
+    if (rc != TACO_OK) return rc;
     p.actions = (const float4*)actions_dev;
-    p.obs_in = env->obs_ab[env->cur]; p.obs_out = env->obs_ab[nxt];
-    p.states_in = env->states_ab[env->cur]; p.states_out = env->states_ab[nxt];
     p.step_index = env->step_index;
     if (env->cfg.flags & TACO_F_STRICT_FP) launch_fpv_step_strict(p, (cudaStream_t)stream);
     else launch_fpv_step_fast(p, (cudaStream_t)stream);
     TACO_CUDA(cudaGetLastError());
-    env->cur = nxt;
-    env->step_index += 1;
+    advance_history(env);
     return TACO_OK;
 }
 
@@ -427,10 +462,9 @@ int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host,
         for (int b = per; nchunks < TacoEnv::kMaxChunks; b += per) { bounds[++nchunks] = b < total_blocks ? b : total_blocks; if (b >= total_blocks) break; }
     }
     bounds[nchunks] = total_blocks;
-    const int nxt = env->cur ^ 1;
+    rc = bind_history(env);
+    if (rc != TACO_OK) return rc;
     p.actions = (const float4*)env->actions_stage;
-    p.obs_in = env->obs_ab[env->cur]; p.obs_out = env->obs_ab[nxt];
-    p.states_in = env->states_ab[env->cur]; p.states_out = env->states_ab[nxt];
     p.step_index = env->step_index;
     const bool strict = (env->cfg.flags & TACO_F_STRICT_FP) != 0;
     const bool want_out = rew_host || reset_host || time_outs_host;
@@ -461,8 +495,7 @@ int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host,
         }
     }
     p.block0 = 0; p.nblocks = 0;
-    env->cur = nxt;
-    env->step_index += 1;
+    advance_history(env);
     if (want_out) {
         TACO_CUDA(cudaEventRecord(env->ev_end, env->s_d2h));         // s_d2h has waited for every chunk kernel
         TACO_CUDA(cudaStreamWaitEvent(s, env->ev_end, 0));
@@ -470,6 +503,54 @@ int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host,
     TACO_CUDA(cudaStreamSynchronize(s));
     return TACO_OK;
 }
+
+int taco_env_attach_rollout(TacoEnv* env, float* obs_ring, float* states_ring, int32_t slots, float* rew_rows, float* done_rows,
+                            uint8_t* time_out_rows, void* stream) {
+    if (!env || !obs_ring || !states_ring) return fail(TACO_E_INVALID, "taco_env_attach_rollout: null argument");
+    if (slots < 2) return fail(TACO_E_INVALID, "taco_env_attach_rollout: need at least 2 slots (horizon + 1)");
+    if ((rew_rows || done_rows || time_out_rows) && !(rew_rows && done_rows && time_out_rows))
+        return fail(TACO_E_INVALID, "taco_env_attach_rollout: rew / done / time-out rows must be given together (or all NULL)");
+    if (((uintptr_t)obs_ring | (uintptr_t)states_ring) & 7u) return fail(TACO_E_INVALID, "taco_env_attach_rollout: rings must be 8-byte aligned");
+    if (env->ring_slots) return fail(TACO_E_INVALID, "taco_env_attach_rollout: a ring is already attached");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    // the newest observation / state history moves into slot 0
+    TACO_CUDA(cudaMemcpyAsync(obs_ring, env->obs_ab[env->cur], (size_t)env->n * env->cfg.len_obs * kObs * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    TACO_CUDA(cudaMemcpyAsync(states_ring, env->states_ab[env->cur], (size_t)env->n * env->cfg.len_states * kObs * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    env->ring_obs = obs_ring; env->ring_states = states_ring;
+    env->ring_rew = rew_rows; env->ring_done = done_rows; env->ring_tout = time_out_rows;
+    env->ring_slots = slots; env->ring_cur = 0;
+    return TACO_OK;
+}
+
+int taco_env_rewind_rollout(TacoEnv* env, void* stream) {
+    if (!env) return fail(TACO_E_INVALID, "taco_env_rewind_rollout: null argument");
+    if (!env->ring_slots) return fail(TACO_E_INVALID, "taco_env_rewind_rollout: no ring attached");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (env->ring_cur > 0) {
+        const size_t so = (size_t)env->n * env->cfg.len_obs * kObs, ss = (size_t)env->n * env->cfg.len_states * kObs;
+        TACO_CUDA(cudaMemcpyAsync(env->ring_obs, env->ring_obs + so * env->ring_cur, so * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        TACO_CUDA(cudaMemcpyAsync(env->ring_states, env->ring_states + ss * env->ring_cur, ss * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    env->ring_cur = 0;
+    return TACO_OK;
+}
+
+int taco_env_detach_rollout(TacoEnv* env, void* stream) {
+    if (!env) return fail(TACO_E_INVALID, "taco_env_detach_rollout: null argument");
+    if (!env->ring_slots) return TACO_OK;
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t so = (size_t)env->n * env->cfg.len_obs * kObs, ss = (size_t)env->n * env->cfg.len_states * kObs;
+    TACO_CUDA(cudaMemcpyAsync(env->obs_ab[env->cur], env->ring_obs + so * env->ring_cur, so * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    TACO_CUDA(cudaMemcpyAsync(env->states_ab[env->cur], env->ring_states + ss * env->ring_cur, ss * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    env->ring_obs = env->ring_states = env->ring_rew = env->ring_done = nullptr; env->ring_tout = nullptr;
+    env->ring_slots = 0; env->ring_cur = 0;
+    return TACO_OK;
+}
+
+int taco_env_rollout_cursor(TacoEnv* env) { return (env && env->ring_slots) ? env->ring_cur : -1; }
 
 int taco_env_reset_all(TacoEnv* env, void* stream) {
     if (!env) return fail(TACO_E_INVALID, "taco_env_reset_all: null argument");
@@ -479,6 +560,11 @@ int taco_env_reset_all(TacoEnv* env, void* stream) {
     for (int k = 0; k < 2; ++k) {
         TACO_CUDA(cudaMemsetAsync(env->obs_ab[k], 0, np * env->cfg.len_obs * kObs * sizeof(float), s));
         TACO_CUDA(cudaMemsetAsync(env->states_ab[k], 0, np * env->cfg.len_states * kObs * sizeof(float), s));
+    }
+    if (env->ring_slots) {                                           // restart the attached ring from a zeroed slot 0
+        TACO_CUDA(cudaMemsetAsync(env->ring_obs, 0, (size_t)env->n * env->cfg.len_obs * kObs * sizeof(float), s));
+        TACO_CUDA(cudaMemsetAsync(env->ring_states, 0, (size_t)env->n * env->cfg.len_states * kObs * sizeof(float), s));
+        env->ring_cur = 0;
     }
     TACO_CUDA(cudaMemsetAsync(env->p.stats, 0, (size_t)kStatSlots * kStatStride * sizeof(double), s));
     init_state_kernel<<<(env->n_pad + 255) / 256, 256, 0, s>>>(env->p);

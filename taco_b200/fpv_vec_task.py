@@ -117,6 +117,9 @@ class FpvVecTask:
         self.extras = {}
         self.obs_dict = {}
         self._actions_keepalive = None
+        self.rollout_buffer = None          # RolloutBuffer whose ring the step kernel writes into (attach_rollout)
+        self._ring_cur = 0
+        self.step_count = 0                 # RL steps since construction / reset_all = the Philox step index of the next step
 
     # ------------------------------------------------------------------ buffers
     def _wrap_buffers(self):
@@ -134,10 +137,14 @@ class FpvVecTask:
 
     @property
     def obs_buf(self):
+        if self.rollout_buffer is not None:
+            return self.rollout_buffer.obs_ring[self._ring_cur]
         return self._obs_ab[self._cur]
 
     @property
     def states_buf(self):
+        if self.rollout_buffer is not None:
+            return self.rollout_buffer.states_ring[self._ring_cur]
         return self._states_ab[self._cur]
 
     @property
@@ -191,7 +198,7 @@ class FpvVecTask:
         self._actions_keepalive = actions
         stream = torch.cuda.current_stream(self.device_id).cuda_stream
         _capi.check(self._lib.taco_env_step(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(stream)), "taco_env_step")
-        self._cur ^= 1
+        self._advance()
         self.extras["time_outs"] = self.timeout_buf.to(self.rl_device)
         self.obs_dict["obs"] = self._clamped(self.obs_buf, self.clip_obs).to(self.rl_device)
         self.obs_dict["states"] = self._clamped(self.states_buf, self.clip_states).to(self.rl_device)
@@ -204,12 +211,52 @@ class FpvVecTask:
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
         _capi.check(self._lib.taco_env_step_host(self._h, ptr(actions_host), ptr(rew_host), ptr(reset_host),
                                                  ptr(time_outs_host), C.c_void_p(stream)), "taco_env_step_host")
-        self._cur ^= 1
+        self._advance()
+
+    def _advance(self):
+        if self.rollout_buffer is not None:
+            self._ring_cur += 1
+        else:
+            self._cur ^= 1
+        self.step_count += 1
+
+    # ------------------------------------------------------------------ zero-copy rollout storage
+    def attach_rollout(self, buffer):
+        """Let the step kernel write observation / state history, reward, done and time-out of every step straight into
+        ``buffer`` (a taco_b200.RolloutBuffer): what PPOReplayBuffer.store copies per step (buffer_asymmetry.py:49-68)."""
+        if (buffer.num_envs, buffer.obs_len, buffer.states_len, buffer.obs_dim, buffer.states_dim) != \
+                (self.num_envs, self.len_obs, self.len_states, self.num_obs, self.num_states):
+            raise ValueError("RolloutBuffer shape does not match the env")
+        if buffer.device_id != self.device_id:
+            raise ValueError("RolloutBuffer is on another device")
+        if self.rollout_buffer is not None:
+            self.detach_rollout()
+        stream = torch.cuda.current_stream(self.device_id).cuda_stream
+        p = lambda t: C.c_void_p(t.data_ptr())
+        _capi.check(self._lib.taco_env_attach_rollout(self._h, p(buffer.obs_ring), p(buffer.states_ring), buffer.horizon_len + 1,
+                                                      p(buffer.rew_buf), p(buffer.done_buf), p(buffer.timeout_buf), C.c_void_p(stream)),
+                    "taco_env_attach_rollout")
+        self.rollout_buffer = buffer
+        self._ring_cur = 0
+
+    def rewind_rollout(self):
+        """Start the next rollout: the newest slot becomes slot 0."""
+        stream = torch.cuda.current_stream(self.device_id).cuda_stream
+        _capi.check(self._lib.taco_env_rewind_rollout(self._h, C.c_void_p(stream)), "taco_env_rewind_rollout")
+        self._ring_cur = 0
+
+    def detach_rollout(self):
+        stream = torch.cuda.current_stream(self.device_id).cuda_stream
+        _capi.check(self._lib.taco_env_detach_rollout(self._h, C.c_void_p(stream)), "taco_env_detach_rollout")
+        self.rollout_buffer = None
+        self._ring_cur = 0
 
     def reset_all(self):
         stream = torch.cuda.current_stream(self.device_id).cuda_stream
         _capi.check(self._lib.taco_env_reset_all(self._h, C.c_void_p(stream)), "taco_env_reset_all")
         self._wrap_buffers()
+        self._ring_cur = 0
+        self.step_count = 0
 
     def set_seed(self, seed):
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF

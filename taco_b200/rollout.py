@@ -11,6 +11,11 @@ and ``batch_idx_generator``.  Differences, all on purpose:
     statistics of ALL envs of the job (buffer_asymmetry.py:132 semantics for the sharded rollout);
   * ``store`` accepts ``time_outs``: the bootstrap of truncated episodes (ppo_asymmetry.py:313-324) then happens inside
     the device pass with no ``nonzero().tolist()`` host round trip;
+  * obs / states live in a ring of ``horizon_len + 1`` slots (``obs_ring`` / ``states_ring``; ``obs_buf`` / ``states_buf`` are
+    the views of the first ``horizon_len`` slots).  ``FpvVecTask.attach_rollout(buffer)`` makes the step kernel write each
+    step's observation history, reward, done flag and time-out straight into slot / row ``k`` (``taco_env_attach_rollout``), so
+    the per-step ``store`` copies of the reference (2.7 GB per rollout at 262144 envs x 20 steps) disappear; ``store`` then
+    takes ``None`` for those fields;
   * ``reset`` only rewinds the write index (the reference re-allocates every buffer each epoch, buffer_asymmetry.py:70-91;
     every slot is overwritten by the next rollout before it is read).
 There is no CPU fallback: the buffer lives on a CUDA device.
@@ -37,8 +42,10 @@ class RolloutBuffer:
         self._lib = _capi.lib()
         H, N = self.horizon_len, self.num_envs
         z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=dev)
-        self.obs_buf = z(H, N, self.obs_len, self.obs_dim)
-        self.states_buf = z(H, N, self.states_len, self.states_dim)
+        self.obs_ring = z(H + 1, N, self.obs_len, self.obs_dim)
+        self.states_ring = z(H + 1, N, self.states_len, self.states_dim)
+        self.obs_buf = self.obs_ring[:H]
+        self.states_buf = self.states_ring[:H]
         self.act_buf = z(H, N, self.act_dim)
         self.rew_buf = z(H, N, 1)
         self.done_buf = z(H, N, 1)
@@ -59,16 +66,25 @@ class RolloutBuffer:
         if self.step >= self.horizon_len:
             raise AssertionError("Rollout buffer overflow")
         s = self.step
-        self.obs_buf[s].copy_(obs)
-        self.states_buf[s].copy_(states)
-        self.act_buf[s].copy_(act)
-        self.rew_buf[s].copy_(rew.view(-1, 1))
-        self.done_buf[s].copy_(done.view(-1, 1))
+        if obs is not None:                      # None: the attached env already wrote slot / row s (zero-copy path)
+            self.obs_buf[s].copy_(obs)
+        if states is not None:
+            self.states_buf[s].copy_(states)
+        if act is not None and act.data_ptr() != self.act_buf[s].data_ptr():
+            self.act_buf[s].copy_(act)
+        if rew is not None:
+            self.rew_buf[s].copy_(rew.view(-1, 1))
+        if done is not None:
+            self.done_buf[s].copy_(done.view(-1, 1))
         self.value_buf[s].copy_(value)
-        self.mu_buf[s].copy_(mu)
+        if mu is not None and mu.data_ptr() != self.mu_buf[s].data_ptr():
+            self.mu_buf[s].copy_(mu)
         self.sigma_buf[s].copy_(sigma)
-        self.logp_buf[s].copy_(log_prob.view(-1, 1))
-        if time_outs is not None:
+        if log_prob is not None and log_prob.data_ptr() != self.logp_buf[s].data_ptr():
+            self.logp_buf[s].copy_(log_prob.view(-1, 1))
+        if time_outs is True:                    # rows written by the attached env
+            self._have_timeouts = True
+        elif time_outs is not None:
             self.timeout_buf[s].copy_(time_outs.view(-1, 1))
             self._have_timeouts = True
         elif s == 0:
@@ -95,7 +111,43 @@ class RolloutBuffer:
                     "taco_gae_normalize")
         self._keep = last
 
+    def rows(self, s):
+        """Output tensors of step s for ActorMLP.act(out=...): (act_buf[s], scratch for the clipped action, logp_buf[s], mu_buf[s])."""
+        if not hasattr(self, "_clipped"):
+            self._clipped = torch.empty(self.num_envs, self.act_dim, dtype=torch.float32, device=self.device)
+        return self.act_buf[s], self._clipped, self.logp_buf[s].view(-1), self.mu_buf[s]
+
     def batch_idx_generator(self):
         """buffer_asymmetry.py:134-139."""
         n = self.num_envs * self.horizon_len
         return torch.randperm(n).reshape(self.mini_batch_num, -1).tolist()
+
+
+def collect_rollout(env, actor, buffer, value_fn, seed=0, tensor_cores=True, group=None):
+    """One rollout of ``buffer.horizon_len`` steps: the data-collection loop of ``PPO.run``
+    (IsaacGymEnvs/algorithms/ppo_asymmetry.py:305-342) with no host round trip inside it.
+
+    ``env``: FpvVecTask; ``actor``: ActorMLP (weights loaded); ``value_fn(obs, states) -> (N,1)``: the critic, which stays a
+    PyTorch module.  Per step: the actor kernel samples straight into the buffer rows, the step
+    kernel writes the next observation history into ring slot s+1 and reward / done / time-out into row s.  The time-out
+    bootstrap, GAE and the advantage normalisation (with the moments all-reduced under torch.distributed) run in
+    ``buffer.compute_returns_and_advantage``; episode statistics come from the env's device-side vector, all-reduced once.
+    Returns the (8,) float64 statistics tensor (see taco_b200.dist.STAT_NAMES)."""
+    from . import dist as tdist
+    if env.rollout_buffer is not buffer:
+        env.attach_rollout(buffer)
+    else:
+        env.rewind_rollout()
+    buffer.reset()
+    H = buffer.horizon_len
+    sigma = torch.from_numpy(actor.log_std).to(buffer.device).expand(buffer.num_envs, -1)     # act() returns log_std as `sigma`
+    for s in range(H):
+        obs, states = buffer.obs_ring[s], buffer.states_ring[s]
+        out = buffer.rows(s)
+        actor.act(obs, env.step_count, seed=seed, env_offset=env.env_offset, tensor_cores=tensor_cores, out=out)
+        value = value_fn(obs, states)
+        env.step(out[1])
+        buffer.store(None, None, out[0], None, out[2], None, value, out[3], sigma, time_outs=True)
+    last_value = value_fn(buffer.obs_ring[H], buffer.states_ring[H])
+    buffer.compute_returns_and_advantage(last_value, group=group)
+    return tdist.allreduce_rollout_stats(env.stats(), group=group)
