@@ -277,7 +277,9 @@ def main():
         sampler.start()
     for t in range(max(args.warmup, 3)):
         env.step(actions[t % n_act])
-    env.stats()
+    warm_stats = env.stats()
+    if world > 1:
+        dist.all_reduce(warm_stats)                  # NCCL communicator set-up happens here, outside the timed region
     t0 = sampler.mark()
     ms, stats = time_steps(env, actions, args.steps, torch, dist, world)
     t1 = sampler.mark()
