@@ -43,15 +43,15 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 // LC = compile-time L (fast paths for the README shapes L=5 / L=1), 0 = runtime L.  nv = valid rows of this CTA (only the
 // last CTA of a shard whose env count is not a multiple of 128 has nv < 128): rows >= nv are never touched, so the
 // buffers may be exactly (num_envs, L, 26) -- e.g. a slot of a caller-owned rollout ring.
-template <int LC>
-__device__ __forceinline__ void write_rows(const float* __restrict__ in, float* __restrict__ out, const float* frames,
-                                           int L_rt, size_t blk_env0, int tid, int nv) {
+template <int LC, bool FULL>
+__device__ __forceinline__ void write_rows_impl(const float* __restrict__ in, float* __restrict__ out, const float* frames,
+                                                int L_rt, size_t blk_env0, int tid, int nv) {
     const int L = LC ? LC : L_rt;
     const int row2 = 13 * L, keep2 = 13 * (L - 1);
     const float2* in2 = reinterpret_cast<const float2*>(in) + blk_env0 * row2;
     float2* out2 = reinterpret_cast<float2*>(out) + blk_env0 * row2;
     if (keep2 > 0) {
-        const int total = nv * keep2;
+        const int total = (FULL ? kBlock : nv) * keep2;       // FULL: compile-time trip count (multiple of kBlock)
         constexpr int U = 13;                                   // loads in flight per thread
         for (int k0 = tid; k0 < total; k0 += kBlock * U) {
             float2 v[U];
@@ -73,8 +73,14 @@ __device__ __forceinline__ void write_rows(const float* __restrict__ in, float* 
         const int k = tid + u * kBlock;
         const int e = k / 13, j = k - e * 13;
         const float* fr = frames + e * kFramePad + 2 * j;
-        if (e < nv) out2[e * row2 + keep2 + j] = make_float2(fr[0], fr[1]);
+        if (FULL || e < nv) out2[e * row2 + keep2 + j] = make_float2(fr[0], fr[1]);
     }
+}
+template <int LC>
+__device__ __forceinline__ void write_rows(const float* __restrict__ in, float* __restrict__ out, const float* frames,
+                                           int L_rt, size_t blk_env0, int tid, int nv) {
+    if (nv == kBlock) write_rows_impl<LC, true>(in, out, frames, L_rt, blk_env0, tid, nv);     // every CTA but (at most) the last
+    else write_rows_impl<LC, false>(in, out, frames, L_rt, blk_env0, tid, nv);
 }
 
 // TASK: task_mode (mix = per-env task from the global env id).  DR: per-env randomised model parameters live in the
