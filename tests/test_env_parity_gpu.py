@@ -198,3 +198,44 @@ def test_api_errors():
     with pytest.raises(RuntimeError, match="control_freq_inv"):
         taco_b200.FpvFlip(bad)
     env.close()
+
+
+@pytest.mark.parametrize("task,n,kw", [
+    ("flip", 1, {}),                                                    # a single env
+    ("mix", 127, {}),                                                   # ragged: below one CTA; mix thirds of 127
+    ("rotate", 129, {}),                                                # ragged: one env into the second CTA
+    ("pos", 1000, {"env.lenObservations": 5, "env.lenStates": 1}),      # history shapes other than the README's (1, 5)
+    ("flip", 640, {"env.lenObservations": 3, "env.lenStates": 7}),
+    ("flip", 512, {"delay_time": 0}),                                   # no delay: the run appended this step is read at once
+    ("mix", 512, {"delay_time": 90}),                                   # the largest delay the reference can hold (90 + 10 slots)
+    ("flip", 512, {"sim.substeps": 1}),
+    ("rotate", 512, {"sim.substeps": 3}),                               # run-time sub-step count (not an unrolled variant)
+    ("flip", 512, {"battery_consumption": False, "rotor_response": False}),
+    ("mix", 512, {"random_copter_pos": False, "random_copter_quat": False, "random_copter_vel": False, "random_target_pos": False,
+                  "random_target_yaw": False, "random_voltage": False, "random_rotor_speed": False, "random_command": False}),
+    ("pos", 512, {"env.clipActions": 0.5}),
+])
+def test_edge_shapes_and_switches(task, n, kw):
+    """Ragged / minimal env counts, other history lengths, delay extremes, sub-step counts and every reset switch off:
+    integer fields bit-exact on every step, floats within the single-step bar on steps 1-2 and the horizon bar after 12."""
+    pu, gpu, ref = _pair(task, n=n, **kw)
+    res = pu.run_lockstep(gpu, ref, 12)
+    for t, (errs, mism, dmis, nfin) in enumerate(res):
+        _assert_ints(mism, dmis, f"{task} n={n} {kw} step {t + 1}")
+        assert nfin == n
+    assert max(res[0][0].values()) <= SINGLE_STEP_TOL_STRICT, res[0][0]
+    assert max(res[1][0].values()) <= SINGLE_STEP_TOL_STRICT, res[1][0]
+    assert max(res[-1][0].values()) <= H50_TOL, res[-1][0]
+    gpu.close()
+
+
+def test_delay_beyond_the_reference_buffer_is_flagged():
+    """delay_time = 100: the first write already crosses slot 100 (fpv_asymmetry.py:329 truncates it silently); every env
+    is flagged and counted instead of compared."""
+    pu, gpu, ref = _pair("flip", n=256, delay_time=100)
+    a = gpu.random_actions(0)
+    gpu.step(a); ref.step(pu.oracle_actions(ref, 0))
+    st = gpu.export_state()
+    assert (st[:, 37] == 1).all() and bool(ref.overflow.all())
+    assert gpu.stats().cpu().numpy()[6] == 256
+    gpu.close()
