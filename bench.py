@@ -323,7 +323,7 @@ def main():
         for t in range(10):
             env_s.step(acts_s[t % n_act])
         ms_s, _ = time_steps(env_s, acts_s, 200, torch, dist, 1)
-        small = {"workload": f"{args.task}, 4096 envs (BASELINE config 2), L2-resident, launch-bound", "value": 4096 * 200 / (ms_s * 1e-3),
+        small = {"workload": f"{args.task}, 4096 envs (BASELINE config 2), L2-resident; 32 CTAs on 148 SMs = one warp per scheduler: bound by the latency of ~8.4k instructions per env-step, not by bandwidth", "value": 4096 * 200 / (ms_s * 1e-3),
                  "unit": "env-steps/s", "us_per_step": ms_s / 200 * 1e3}
         env_s.close()
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
