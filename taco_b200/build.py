@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 _MB = os.environ.get("TACO_MIN_BLOCKS")          # tuning builds: libtaco_b200_mb<N>.so next to the default library
+_XDEF = os.environ.get("TACO_XDEFS", "").split()  # extra -D flags for tuning builds (used with TACO_MIN_BLOCKS to get a separate .so)
 LIB_PATH = os.path.join(LIB_DIR, "libtaco_b200.so" if not _MB else f"libtaco_b200_mb{_MB}.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--threads", "4"]
@@ -54,7 +55,7 @@ def build(force=False, verbose=False):
         o = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + ARCH + COMMON + ([f"-DTACO_MIN_BLOCKS={_MB}"] if _MB else []) + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + ARCH + COMMON + ([f"-DTACO_MIN_BLOCKS={_MB}"] if _MB else []) + [f"-D{d}" for d in _XDEF] + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, pr in procs:
         out, _ = pr.communicate()
