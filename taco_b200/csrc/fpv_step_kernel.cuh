@@ -427,31 +427,40 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
                 tb.z = ((t0 + t1) + t2) + t3;
                 if (R) { fb = v3(0.f, 0.f, 0.f); tb = v3(0.f, 0.f, 0.f); }        // fpv_asymmetry.py:629-630
             }
-            // free rigid body, `substeps` x h (DESIGN.md "integrator"; oracle/rigid_body.py): force held in the world
-            // frame, torque in the body frame, angular velocity carried in body coordinates
+            // free rigid body, `substeps` x h (DESIGN.md "integrator"; oracle/rigid_body.c is the specification, operation for
+            // operation): force held in the world frame, torque in the body frame, angular velocity carried in body
+            // coordinates.  The integrator is ours, so its FMAs are part of the specification (explicit, also in the
+            // -fmad=false build); everything that restates the reference's torch expressions rounds every operation.
             {
-                const V3 fw = qrot(q, fb);
-                const V3 acc = v3(fw.x * p.inv_mass + 0.0f, fw.y * p.inv_mass + 0.0f, fw.z * p.inv_mass + -9.81f);
+                // F_w = F_b + w t + u x t,  t = 2 (u x F_b)
+                const V3 u = v3(q.x, q.y, q.z);
+                V3 t = cross_f(u, fb); t.x = t.x + t.x; t.y = t.y + t.y; t.z = t.z + t.z;
+                const V3 ut = cross_f(u, t);
+                const V3 fw = v3(__fmaf_rn(q.w, t.x, fb.x) + ut.x, __fmaf_rn(q.w, t.y, fb.y) + ut.y, __fmaf_rn(q.w, t.z, fb.z) + ut.z);
+                const V3 acc = v3(fw.x * p.inv_mass, fw.y * p.inv_mass, __fmaf_rn(fw.z, p.inv_mass, -9.81f));
                 const int nsub = SUB ? SUB : p.substeps;
 #pragma unroll
                 for (int s = 0; s < nsub; ++s) {
-                    vel.x = vel.x + h * acc.x; vel.y = vel.y + h * acc.y; vel.z = vel.z + h * acc.z;
+                    vel.x = __fmaf_rn(h, acc.x, vel.x); vel.y = __fmaf_rn(h, acc.y, vel.y); vel.z = __fmaf_rn(h, acc.z, vel.z);
                     const V3 iw = v3(5e-4f * wb.x, 7e-4f * wb.y, 8e-4f * wb.z);
-                    const V3 gy = cross(wb, iw);
-                    wb.x = wb.x + h * ((tb.x - gy.x) * 2000.0f);
-                    wb.y = wb.y + h * ((tb.y - gy.y) * (float)(1.0 / 7e-4));
-                    wb.z = wb.z + h * ((tb.z - gy.z) * 1250.0f);
-                    pos.x = pos.x + h * vel.x; pos.y = pos.y + h * vel.y; pos.z = pos.z + h * vel.z;
-                    // exp(h/2 w) by its 4th-order series (exact to float32 for |w| h/2 < 0.1 rad)
-                    const float w2 = (wb.x * wb.x + wb.y * wb.y) + wb.z * wb.z;
+                    const V3 gy = cross_f(wb, iw);
+                    wb.x = __fmaf_rn(h, (tb.x - gy.x) * 2000.0f, wb.x);
+                    wb.y = __fmaf_rn(h, (tb.y - gy.y) * (float)(1.0 / 7e-4), wb.y);
+                    wb.z = __fmaf_rn(h, (tb.z - gy.z) * 1250.0f, wb.z);
+                    pos.x = __fmaf_rn(h, vel.x, pos.x); pos.y = __fmaf_rn(h, vel.y, pos.y); pos.z = __fmaf_rn(h, vel.z, pos.z);
+                    const float w2 = __fmaf_rn(wb.z, wb.z, __fmaf_rn(wb.y, wb.y, wb.x * wb.x));
                     const float th2 = w2 * p.half_h2;
-                    const float kk = p.half_h * (1.0f + th2 * (p.c_sin3 + th2 * p.c_sin5));
-                    const float cs = 1.0f + th2 * (-0.5f + th2 * p.c_cos4);
-                    Q4 dq; dq.x = wb.x * kk; dq.y = wb.y * kk; dq.z = wb.z * kk; dq.w = cs;
-                    q = qmul(q, dq);
-                    const float n2 = ((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w;
-                    const float rn = 1.5f - 0.5f * n2;                                   // one Newton step of 1/sqrt about 1
-                    q.x = q.x * rn; q.y = q.y * rn; q.z = q.z * rn; q.w = q.w * rn;
+                    const float kk = p.half_h * __fmaf_rn(th2, __fmaf_rn(th2, p.c_sin5, p.c_sin3), 1.0f);
+                    const float cs = __fmaf_rn(th2, __fmaf_rn(th2, p.c_cos4, -0.5f), 1.0f);
+                    const float dx = wb.x * kk, dy = wb.y * kk, dz = wb.z * kk;
+                    Q4 r;                                                                   // Hamilton product q * (dx, dy, dz, cs)
+                    r.w = __fmaf_rn(-q.z, dz, __fmaf_rn(-q.y, dy, __fmaf_rn(-q.x, dx, q.w * cs)));
+                    r.x = __fmaf_rn(-q.z, dy, __fmaf_rn(q.y, dz, __fmaf_rn(q.x, cs, q.w * dx)));
+                    r.y = __fmaf_rn(-q.x, dz, __fmaf_rn(q.z, dx, __fmaf_rn(q.y, cs, q.w * dy)));
+                    r.z = __fmaf_rn(-q.y, dx, __fmaf_rn(q.x, dy, __fmaf_rn(q.z, cs, q.w * dz)));
+                    const float n2 = __fmaf_rn(r.w, r.w, __fmaf_rn(r.z, r.z, __fmaf_rn(r.y, r.y, r.x * r.x)));
+                    const float rn = __fmaf_rn(-0.5f, n2, 1.5f);                            // one Newton step of 1/sqrt about 1
+                    q.x = r.x * rn; q.y = r.y * rn; q.z = r.z * rn; q.w = r.w * rn;
                 }
             }
         }

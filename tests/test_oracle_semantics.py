@@ -48,3 +48,40 @@ def test_pow_3_is_repeated_multiplication_and_mvn_std():
     cov = torch.diag(log_std.exp() * log_std.exp())
     dist = torch.distributions.MultivariateNormal(torch.zeros(2), scale_tril=cov)
     assert torch.allclose(dist.stddev, torch.exp(2 * log_std))
+
+
+def test_fma32_is_an_exact_float32_fma():
+    """oracle.rigid_body.fma32 against exact rational arithmetic, on inputs built to cancel (where double rounding bites)."""
+    from fractions import Fraction
+    import numpy as np
+    from oracle.rigid_body import fma32
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal(1500).astype(np.float32)
+    b = rng.standard_normal(1500).astype(np.float32)
+    c = (-(a.astype(np.float64) * b.astype(np.float64))).astype(np.float32) + rng.standard_normal(1500).astype(np.float32) * np.float32(1e-7)
+    c[::3] = rng.standard_normal(500).astype(np.float32)
+    r = fma32(a, b, c)
+    for a_, b_, c_, r_ in zip(a, b, c, r):
+        ex = Fraction(float(a_)) * Fraction(float(b_)) + Fraction(float(c_))
+        f = np.float32(float(ex))
+        best = min([f, np.nextafter(f, np.float32(np.inf)), np.nextafter(f, np.float32(-np.inf))], key=lambda x: abs(Fraction(float(x)) - ex))
+        assert best == r_
+
+
+def test_c_integrator_equals_its_numpy_twin():
+    """oracle/rigid_body.c (the executable specification of the integrator, C fmaf) == _integrate_py (exact FMA emulation)."""
+    import torch
+    from oracle import rigid_body as rb
+    assert rb._c_lib() is not None, "oracle/librigid_body.so missing: run __graft_entry__.build() (needs gcc)"
+    g = torch.Generator().manual_seed(1)
+    n = 6000
+    pos = torch.randn(n, 3, generator=g) * 3
+    q = torch.randn(n, 4, generator=g); q = q / q.norm(dim=1, keepdim=True)
+    v, w = torch.randn(n, 3, generator=g) * 4, torch.randn(n, 3, generator=g) * 20
+    fb, tb = torch.randn(n, 3, generator=g) * 5, torch.randn(n, 3, generator=g) * 0.05
+    fb[:100] = 0; tb[:100] = 0                                  # the zero-wrench step after a reset
+    for sub in (1, 2, 3):
+        a = rb.integrate(pos, q, v, w, fb, tb, 0.001, sub, use_c=True)
+        b = rb.integrate(pos, q, v, w, fb, tb, 0.001, sub, use_c=False)
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
+        assert torch.all((a[1].norm(dim=1) - 1).abs() < 1e-6)
