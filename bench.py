@@ -293,25 +293,33 @@ def main():
         h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
         h_reset = torch.empty(n, dtype=torch.int64).pin_memory()
         h_tout = torch.empty(n, dtype=torch.uint8).pin_memory()
-        for t in range(2):
-            env.step_host(h_act[t % n_act], h_rew, h_reset, h_tout)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for t in range(k_e2e):
-            env.step_host(h_act[t % n_act], h_rew, h_reset, h_tout)
-        e1.record()
-        torch.cuda.synchronize()
-        ms_e = e0.elapsed_time(e1)
-        if world > 1:
-            tm = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            ms_e = float(tm.item())
-        e2e = {"value": float(world) * n * k_e2e / (ms_e * 1e-3), "unit": "env-steps/s", "steps": k_e2e,
-               "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * 13,
-               "note": "per GPU bytes; taco_env_step_host: pinned actions H2D + kernel + rew/reset/time_outs D2H + stream sync, every step"}
+        def time_host_steps(k):
+            for t in range(2):
+                env.step_host(h_act[t % n_act], h_rew, h_reset, h_tout)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for t in range(k):
+                env.step_host(h_act[t % n_act], h_rew, h_reset, h_tout)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_ = e0.elapsed_time(e1)
+            if world > 1:
+                tm = torch.tensor([ms_], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                ms_ = float(tm.item())
+            return float(world) * n * k / (ms_ * 1e-3)
+        os.environ["TACO_HOST_MODE"] = "copy"          # the chunked copy pipeline (what pageable buffers get), for comparison
+        v_copy = time_host_steps(min(k_e2e, 10))
+        os.environ["TACO_HOST_MODE"] = "mapped"        # default: the kernel reads / writes the pinned host buffers itself
+        v_map = time_host_steps(k_e2e)
+        e2e = {"value": v_map, "unit": "env-steps/s", "steps": k_e2e,
+               "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * 13, "copy_pipeline_value": v_copy,
+               "note": "per GPU bytes; taco_env_step_host with pinned host buffers, every step: one launch whose threads load their "
+                       "action from host memory and post rew/reset/time_outs into host memory across PCIe, then a stream sync; "
+                       "copy_pipeline_value = the same call with TACO_HOST_MODE=copy (chunked cudaMemcpyAsync pipeline)"}
     sampler.stop()
     clocks = sampler.summary(t0, t1) if rank == 0 else None
     # ---- small-N point of BASELINE config 2 (4096 envs, launch-latency bound)

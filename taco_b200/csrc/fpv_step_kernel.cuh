@@ -605,6 +605,10 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
             p.roll_done[i] = done ? 1.0f : 0.0f;
             p.roll_tout[i] = tout ? 1 : 0;
         }
+        // mapped host-buffer step (taco_env_step_host): results are posted straight into the caller's pinned host memory
+        if (p.host_reset) p.host_reset[i] = done ? 1ll : 0ll;
+        if (p.host_rew) p.host_rew[i] = rew;
+        if (p.host_tout) p.host_tout[i] = tout ? 1 : 0;
     } else {
 #pragma unroll
         for (int j = 0; j < 26; ++j) { fc[j] = 0.f; fn[j] = 0.f; }

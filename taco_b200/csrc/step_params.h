@@ -47,6 +47,9 @@ struct StepParams {
     float* roll_rew;               // row of the attached rollout buffer for this step (or null): rew, done as f32, time-outs
     float* roll_done;
     uint8_t* roll_tout;
+    float* host_rew;               // taco_env_step_host, mapped mode: the caller's pinned host buffers (device-visible addresses,
+    long long* host_reset;         // or null); the kernel posts rew / reset / time-outs across PCIe itself
+    uint8_t* host_tout;
     double* stats;                 // [kStatSlots][kStatStride]
     float4* dbg_delay;             // [cfi][n_pad] or null
 };

@@ -418,6 +418,14 @@ int taco_env_step(TacoEnv* env, const float* actions_dev, void* stream) {
     return TACO_OK;
 }
 
+// device-visible address of a pinned (cudaHostAlloc / cudaHostRegister) host buffer, or null for pageable memory
+static void* mapped_ptr(const void* host) {
+    if (!host) return nullptr;
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, const_cast<void*>(host), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return d;
+}
+
 static int pipe_init(TacoEnv* env) {
     if (env->pipe_ready) return TACO_OK;
     TACO_CUDA(cudaStreamCreateWithFlags(&env->s_h2d, cudaStreamNonBlocking));
@@ -446,6 +454,30 @@ int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host,
     int rc = pipe_init(env);
     if (rc != TACO_OK) return rc;
     StepParams& p = env->p;
+    // Mapped mode (default whenever the caller's buffers are pinned, i.e. have a device-visible address): ONE launch; the
+    // kernel loads each env's action from host memory and posts rew / reset / time-outs into host memory itself, so the
+    // PCIe transfers of a CTA overlap the arithmetic of the ~890 other resident CTAs and there is no fill / drain phase of
+    // a copy pipeline.  TACO_HOST_MODE=copy forces the chunked copy pipeline below (also the path for pageable memory).
+    const char* hm = getenv("TACO_HOST_MODE");                      // read per call: tests and tuning runs switch it
+    const int host_mode = (hm && !strcmp(hm, "copy")) ? 1 : 0;
+    if (host_mode == 0 && ((uintptr_t)actions_host & 15u) == 0) {
+        void* d_act = mapped_ptr(actions_host);
+        void* d_rew = mapped_ptr(rew_host); void* d_reset = mapped_ptr(reset_host); void* d_tout = mapped_ptr(time_outs_host);
+        if (d_act && (!rew_host || d_rew) && (!reset_host || d_reset) && (!time_outs_host || d_tout)) {
+            rc = bind_history(env);
+            if (rc != TACO_OK) return rc;
+            p.actions = (const float4*)d_act;
+            p.host_rew = (float*)d_rew; p.host_reset = (long long*)d_reset; p.host_tout = (uint8_t*)d_tout;
+            p.step_index = env->step_index;
+            if (env->cfg.flags & TACO_F_STRICT_FP) launch_fpv_step_strict(p, s); else launch_fpv_step_fast(p, s);
+            const cudaError_t le = cudaGetLastError();
+            p.host_rew = nullptr; p.host_reset = nullptr; p.host_tout = nullptr;
+            TACO_CUDA(le);
+            advance_history(env);
+            TACO_CUDA(cudaStreamSynchronize(s));
+            return TACO_OK;
+        }
+    }
     const int total_blocks = env->n_pad / kBlock;
     // 4 equal chunks of at least 512 CTAs (64 Ki envs): measured best of 4 / 8 / 12 / 16 equal chunks and of a graded
     // 1-2-4-5-3-1 schedule at 2 Mi envs (per-copy and per-launch overheads outweigh shorter fill / drain phases; the call

@@ -160,21 +160,28 @@ def test_shard_invariance_single_gpu():
     full.close(); shard.close()
 
 
+@pytest.mark.parametrize("mode", ["mapped", "copy", "pageable"])
 @pytest.mark.parametrize("n", [3000, 200_003])     # one chunk / three pipelined chunks; neither a multiple of 128 (tail block)
-def test_host_buffer_entry_point_matches_device_path(n):
+def test_host_buffer_entry_point_matches_device_path(n, mode, monkeypatch):
+    """taco_env_step_host: 'mapped' = the kernel reads / writes the pinned host buffers itself (default), 'copy' = the
+    chunked copy pipeline (TACO_HOST_MODE=copy), 'pageable' = unpinned buffers (falls back to the copy pipeline)."""
     import taco_b200
     from taco_b200 import make_cfg
+    monkeypatch.setenv("TACO_HOST_MODE", "copy" if mode == "copy" else "mapped")
+    pin = (lambda t: t) if mode == "pageable" else (lambda t: t.pin_memory())
     a_env = taco_b200.FpvVecTask(make_cfg("flip", n), "cuda:0", "cuda:0", -1, True, seed=3)
     b_env = taco_b200.FpvVecTask(make_cfg("flip", n), "cuda:0", "cuda:0", -1, True, seed=3)
-    h_rew = torch.empty(n).pin_memory(); h_reset = torch.empty(n, dtype=torch.int64).pin_memory()
-    h_tout = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_rew = pin(torch.empty(n)); h_reset = pin(torch.empty(n, dtype=torch.int64))
+    h_tout = pin(torch.empty(n, dtype=torch.uint8))
     for t in range(5):
         act = a_env.random_actions(t)
         o, r, x, e = a_env.step(act)
-        b_env.step_host(act.cpu().pin_memory(), h_rew, h_reset, h_tout)
+        h_rew.fill_(-7.0); h_reset.fill_(-7); h_tout.fill_(77)
+        b_env.step_host(pin(act.cpu()), h_rew, h_reset, h_tout)
         assert torch.equal(r.cpu(), h_rew) and torch.equal(x.cpu(), h_reset)
         assert torch.equal(e["time_outs"].cpu().to(torch.uint8), h_tout)
         assert torch.equal(o["states"], b_env.states_buf)
+        assert torch.equal(r, b_env.rew_buf) and torch.equal(x, b_env.reset_buf)
     assert torch.equal(a_env.stats(), b_env.stats())
     a_env.close(); b_env.close()
 
