@@ -28,6 +28,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: whatever native libraries print to file descriptor 1 (NCCL writes its version banner
+# there when NCCL_DEBUG is set) is sent to stderr, and emit() writes the line to the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 ALGO_BYTES_NO_DR = 1493      # 16 + 637 + 416 + 424 (len_obs=1, len_states=5, no per-env DR)
 ALGO_BYTES_DR = 1549
 TASK = "flip"
@@ -160,7 +170,7 @@ def run_reference(args, rank):
         "e2e": {"value": cb["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -380,7 +390,7 @@ def main():
             line["config3_mix_actor"] = actor_pt
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.task, args.cpu_envs, args.cpu_steps, 3, args.dr).items() if k != "ms_per_step"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     env.close()
     if world > 1:
         dist.destroy_process_group()

@@ -7,7 +7,7 @@ Run in the build container only (needs /root/reference):
 
 The reference ships no tests / golden vectors for this path, so these
 files are the pin for the oracle's leaf functions: tests/test_oracle_golden.py checks
-oracle/{leaf_math,dynamics,rewards,actor}.py against them on any machine.
+oracle/{leaf_math,dynamics,rewards,actor,critic}.py against them on any machine.
 """
 import os
 import math
@@ -198,6 +198,47 @@ def actor(ns):
     np.savez(os.path.join(OUT, "actor.npz"), **{k: np.asarray(t) for k, t in out.items()})
 
 
+def critic(ns):
+    """LSTMEncoder.forward + critic MLP + the critic branch of PPO_ActorCritic.act (nets_asymmetry.py:128-136,:23-39,:350-352)
+    run from the reference's own classes (use_critic_encoder=True, critic_encoder_type=LSTM: the README's training command)."""
+    import io, contextlib
+    import torch.nn as nn
+    out = {}
+    for tag, hid, nl, mlp_hidden in (("a", 48, 1, [64, 32]), ("b", 32, 2, [40])):
+        torch.manual_seed(4100 + nl)
+        para = {"actor_critic_mlp_dict": {"actor_input_dim": 26, "actor_output_dim": 4, "critic_input_dim": 26 * 5, "critic_output_dim": 1,
+                                          "actor_hidden_sizes": [32], "critic_hidden_sizes": mlp_hidden, "activation": nn.ReLU},
+                "use_actor_encoder": False, "use_critic_encoder": True, "share_encoder": False, "critic_encoder_type": "LSTM",
+                "critic_encoder_dict": {"encoder_type": "LSTM", "input_size": 26, "output_size": hid, "num_layers": nl, "bidirectional": False}}
+        with contextlib.redirect_stdout(io.StringIO()):
+            agent = ns.nets.PPO_ActorCritic(para)
+        lstm = agent.critic_encoder.layers
+        lin = [m for m in agent.critic_mlp.layers if isinstance(m, nn.Linear)]
+        with torch.no_grad():                               # para_init zeroes the LSTM biases: give them values so all four terms count
+            for name, prm in lstm.named_parameters():
+                if prm.dim() == 1:
+                    prm.uniform_(-0.3, 0.3)
+            for m in lin:
+                m.bias.uniform_(-0.2, 0.2)
+            lin[-1].weight.mul_(30.0)                       # gain 0.01 would make the value ~1e-2: scale it into O(1)
+        n = 80
+        obs = torch.randn(n, 1, 26) * 0.8
+        states = torch.randn(n, 5, 26) * 1.5
+        for l in range(nl):
+            for nm in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                out[f"{tag}_{nm}_l{l}"] = getattr(lstm, f"{nm}_l{l}").detach().clone()
+        for i, m in enumerate(lin):
+            out[f"{tag}_w{i}"] = m.weight.detach().clone()
+            out[f"{tag}_b{i}"] = m.bias.detach().clone()
+        out[f"{tag}_states"] = states
+        with torch.no_grad():
+            out[f"{tag}_enc"] = agent.critic_encoder(states)
+            out[f"{tag}_value"] = agent.critic_mlp(agent.critic_encoder(states))
+            _, _, value, _, _ = agent.act(obs, states)
+        out[f"{tag}_act_value"] = value
+    np.savez(os.path.join(OUT, "critic.npz"), **{k: np.asarray(t) for k, t in out.items()})
+
+
 def gae(ns):
     """PPOReplayBuffer.store / compute_returns_and_advantage (buffer_asymmetry.py:49-68,93-132) run from the reference's
     own class, with the time-out bootstrap of ppo_asymmetry.py:313-324 applied to the stored reward."""
@@ -234,6 +275,7 @@ def main():
     dynamics(ns)
     rewards(ns)
     actor(ns)
+    critic(ns)
     gae(ns)
     print("golden vectors written to", OUT)
     for f in sorted(os.listdir(OUT)):
