@@ -183,6 +183,30 @@ int taco_actor_act(TacoActor* actor, const float* obs_dev, int32_t n, const floa
                    uint64_t seed, uint32_t step_index, float* mean_dev, float* action_dev, float* clipped_dev,
                    float* logp_dev, int32_t use_tensor_cores, void* stream);
 
+/* -- critic inference in the rollout loop: the critic branch of PPO_ActorCritic.act (IsaacGymEnvs/algorithms/nets_asymmetry.py:350-352)
+ * in the configuration the reference trains with (README.md:60-66: use_critic_encoder, critic_encoder_type=LSTM, lenStates=5):
+ * value = MLP(LSTMEncoder(states)), LSTMEncoder = nn.LSTM(in_dim, lstm_hidden, lstm_layers, batch_first=True) with zero initial
+ * state, output = top layer's h after the last time step (nets_asymmetry.py:128-136); MLP = [Linear -> ReLU] x L -> Linear(-> 1)
+ * (nets_asymmetry.py:23-39, :318).  Two kernels compute the same function: an FP32 CUDA-core path (any shape; parity) and a
+ * tcgen05/TMEM bf16 path (one LSTM layer of width multiple of 16 up to 64, in_dim <= 32, seq_len <= 8, 1..3 MLP hidden layers of
+ * widths multiples of 64 up to 256). */
+typedef struct TacoCritic TacoCritic;
+/* mlp_sizes = [lstm_hidden, h1, ..., hL, 1] (n_mlp_sizes entries) */
+int taco_critic_create(int device, int32_t in_dim, int32_t seq_len, int32_t lstm_hidden, int32_t lstm_layers,
+                       const int32_t* mlp_sizes, int32_t n_mlp_sizes, TacoCritic** out);
+int taco_critic_destroy(TacoCritic* critic);
+/* lstm_host: 4 host float32 arrays per LSTM layer, bottom layer first, in torch's nn.LSTM layout and order: weight_ih (4H, in),
+ * weight_hh (4H, H), bias_ih (4H), bias_hh (4H); gate row blocks i, f, g, o.  mlp weights/biases as in taco_actor_load.
+ * Synchronises the stream (the host buffers are free on return). */
+int taco_critic_load(TacoCritic* critic, const float* const* lstm_host, const float* const* mlp_weights_host,
+                     const float* const* mlp_biases_host, void* stream);
+/* 1 when the tcgen05 path supports this critic's shape on this device */
+int taco_critic_tc_available(TacoCritic* critic);
+/* value_dev (n[, 1]) f32 = critic(states_dev (n, seq_len, in_dim) f32 contiguous).  use_tensor_cores as in taco_actor_forward.
+ * Asynchronous on `stream`. */
+int taco_critic_forward(TacoCritic* critic, const float* states_dev, float* value_dev, int32_t n, int32_t use_tensor_cores,
+                        void* stream);
+
 /* -- rollout-buffer post-processing: PPOReplayBuffer.compute_returns_and_advantage
  * (IsaacGymEnvs/algorithms/buffer_asymmetry.py:93-132) and the time-out bootstrap PPO applies to the reward it stores
  * (IsaacGymEnvs/algorithms/ppo_asymmetry.py:313-324).  All buffers are contiguous float32 (horizon, num_envs[, 1]) on

@@ -24,6 +24,7 @@ UNITS = [
     ("fpv_step_strict.cu", ["-fmad=false"]),
     ("taco_env.cu", []),
     ("taco_actor.cu", []),
+    ("taco_critic.cu", []),
     ("taco_gae.cu", ["-fmad=false"]),
 ]
 

@@ -246,6 +246,7 @@ __device__ __forceinline__ void load_obs_group(const float* x, int g, int in_dim
     }
 }
 
+#ifndef TACO_TC_NO_ACTOR_KERNEL      // critic_tc.cuh reuses the wrappers above and the weight packer below, not this kernel
 __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -451,10 +452,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
     }
 }
 
+#endif  // TACO_TC_NO_ACTOR_KERNEL
+
 // fp32 (out, in) row-major weights -> bf16 K-chunk images in the SWIZZLE_128B K-major layout the kernel copies verbatim:
 // chunk c holds W[:, 64c .. 64c+63] as n rows of 128 bytes (rows >= n_real are zero); the 16-byte piece q of row r sits
 // at r*128 + ((q ^ (r&7)) << 4).
-__global__ void pack_weights_kernel(const float* __restrict__ w, int n_real, int n, int k, uint8_t* __restrict__ img) {
+static __global__ void pack_weights_kernel(const float* __restrict__ w, int n_real, int n, int k, uint8_t* __restrict__ img) {
     const int kchunks = (k + kKC - 1) / kKC;
     const int total = kchunks * n * 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
