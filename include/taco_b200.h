@@ -188,7 +188,7 @@ int taco_actor_act(TacoActor* actor, const float* obs_dev, int32_t n, const floa
  * value = MLP(LSTMEncoder(states)), LSTMEncoder = nn.LSTM(in_dim, lstm_hidden, lstm_layers, batch_first=True) with zero initial
  * state, output = top layer's h after the last time step (nets_asymmetry.py:128-136); MLP = [Linear -> ReLU] x L -> Linear(-> 1)
  * (nets_asymmetry.py:23-39, :318).  Two kernels compute the same function: an FP32 CUDA-core path (any shape; parity) and a
- * tcgen05/TMEM bf16 path (one LSTM layer of width multiple of 16 up to 64, in_dim <= 32, seq_len <= 8, 1..3 MLP hidden layers of
+ * tcgen05/TMEM bf16 path (one LSTM layer of width multiple of 16 up to 64, even in_dim <= 30, seq_len <= 8, 1..3 MLP hidden layers of
  * widths multiples of 64 up to 256). */
 typedef struct TacoCritic TacoCritic;
 /* mlp_sizes = [lstm_hidden, h1, ..., hL, 1] (n_mlp_sizes entries) */

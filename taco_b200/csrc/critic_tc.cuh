@@ -12,12 +12,15 @@
 //   * one LSTM time step is ONE layer of the chain: gates[128 x 4H] = [h_{t-1} | x_t] (K = 64 + 64, zero padded) * Wcat^T,
 //     Wcat = [W_hh | W_ih] with its rows permuted so that every 16 accumulator columns hold the four gates (i, f, g, o; 4
 //     columns each) of the same 4 hidden units -- an epilogue thread reads 16 columns and owns those 4 units outright;
-//   * the cell state c never leaves the registers of the thread that owns (env row, hidden unit): 2 * H / 4 values per
-//     thread; h_t is written back over the A operand as packed bf16 pairs next to the freshly staged x_{t+1};
+//   * the cell state c lives in tensor memory too (fp32, in the 64 columns of the tile's A region the K = 128 LSTM operand leaves
+//     free), read and rewritten by the thread that owns (env row, hidden unit); h_t is written back over the A operand as
+//     packed bf16 pairs next to the freshly staged x_{t+1};
 //   * the T = len_states steps reuse one weight image; then the MLP layers and the 16-wide output part follow as in the actor.
-// Gate non-linearities use MUFU.TANH (tanh.approx; sigmoid(x) = 0.5 + 0.5 tanh(x / 2)): 5 MUFU per (env, unit, step).
+// Gate non-linearities use MUFU.TANH on packed half pairs (tanh.approx.f16x2; sigmoid(x) = 0.5 + 0.5 tanh(x / 2)): 2.5 MUFU slots
+// per (env, unit, step) -- the LSTM phase is bound by the 16 MUFU lanes of the SM, not by the tensor core.
 #pragma once
 #define TACO_TC_NO_ACTOR_KERNEL
+#include <cuda_fp16.h>
 #include "actor_tc.cuh"
 
 namespace taco {
@@ -25,11 +28,12 @@ namespace critic {
 using namespace taco::actor;
 
 constexpr int kMaxSeq = 8;             // len_states of the reference runs is 5 (README.md:60-66)
-constexpr int kTcMaxLstmHidden = 64;   // c lives in registers: H / 2 floats per epilogue thread
-constexpr int kTcMaxIn = 32;           // features per frame (26) padded to 32 = 16 packed TMEM columns
+constexpr int kTcMaxLstmHidden = 64;   // the cell state lives in the 64 spare TMEM columns of the tile's A operand
+constexpr int kTcMaxIn = 30;           // features per frame (26) + two constant-1 bias columns, padded to 32 = 16 packed TMEM columns
 constexpr int kMaxMlpHidden = 3;       // s_bias rows: LSTM gates + up to 3 hidden layers
 constexpr int kAColH = 0;              // A operand columns (packed bf16 pairs): h in [0, 32), x_t in [32, 48), zero pad [48, 64)
 constexpr int kAColX = 32;
+constexpr int kAColC = 64;              // cell state, fp32, one column per hidden unit (LSTM phase only)
 
 struct CriticTcParams {
     const float* states;   // (n_rows, seq_len, in_dim) f32
@@ -38,9 +42,10 @@ struct CriticTcParams {
     int lstm_hidden;       // H: multiple of 16, <= 64
     int n_hidden;          // MLP hidden layers, 1..3
     const uint8_t* wimg;   // pre-swizzled bf16 chunk images: LSTM [W_hh | W_ih] (gate-permuted rows), MLP layers, output (16 rows)
-    const float* bias;     // [kMaxHidden][kMaxN]: row 0 = b_ih + b_hh in the permuted column order, rows 1.. = MLP hidden biases
+    const float* bias;     // [kMaxHidden][kMaxN]: row 0 unused (the LSTM bias rides in the MMA), rows 1.. = MLP hidden biases
     const float* b_out;    // [kOutPad]
     TcLayer layer[2 + kMaxMlpHidden];   // [0] one LSTM step, [1 .. n_hidden] MLP hidden layers, [n_hidden + 1] output layer
+    unsigned long long* dbg;            // optional timeline of CTA 0 (TACO_CRITIC_TIMELINE=<file>), see TACO_DBG in actor_tc.cuh
 };
 
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
@@ -59,50 +64,123 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 __device__ __forceinline__ float tanh_mufu(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoid_mufu(float x) { return fmaf(0.5f, tanh_mufu(0.5f * x), 0.5f); }
 
-// 16 accumulator columns = [i(4) f(4) g(4) o(4)] of 4 hidden units: c' = sig(f) c + sig(i) tanh(g), h' = sig(o) tanh(c');
-// h' leaves as 2 packed bf16 pairs (unit 2j in the low half)
-__device__ __forceinline__ void lstm_group(const uint32_t (&v)[16], const float* bias, float* c, uint32_t* hp) {
+// TACO_CRITIC_GATES: 0 (default) = tanh.approx.f32; 1 = MUFU.TANH on packed half pairs (tanh.approx.f16x2; measured 6 % SLOWER --
+// the conversions cost more issue slots than the MUFU slots they save -- and twice the error); 2 = no transcendentals at all
+// (timing experiment only, wrong values: 3 % faster, i.e. the LSTM phase is bound by instruction issue / latency, not by MUFU)
+#ifndef TACO_CRITIC_GATES
+#define TACO_CRITIC_GATES 0
+#endif
+// tanh of two floats
+__device__ __forceinline__ float2 tanh_pair(float a, float b) {
+#if TACO_CRITIC_GATES == 1
+    return __half22float2(h2tanh_approx(__floats2half2_rn(a, b)));
+#elif TACO_CRITIC_GATES == 0
+    return make_float2(tanh_mufu(a), tanh_mufu(b));
+#else
+    return make_float2(fminf(fmaxf(a, -1.0f), 1.0f), fminf(fmaxf(b, -1.0f), 1.0f));
+#endif
+}
+// 16 accumulator columns = [i(4) f(4) g(4) o(4)] of 4 hidden units.  The accumulator already holds the complete argument of
+// each tanh: the bias rides in the MMA (two constant-1 input columns against bf16 hi / lo halves of b_ih + b_hh) and the rows of
+// the sigmoid gates are pre-scaled by 1/2 (exact in bf16), sigmoid(x) = 0.5 + 0.5 tanh(x / 2).
+// c' = sig(f) c + sig(i) tanh(g), h' = sig(o) tanh(c'); h' leaves as 2 packed bf16 pairs (unit 2j in the low half)
+__device__ __forceinline__ void lstm_group(const uint32_t (&v)[16], uint32_t (&c)[4], uint32_t* hp) {
 #pragma unroll
     for (int u = 0; u < 4; u += 2) {
-        float h2[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int k = u + e;
-            const float ig = sigmoid_mufu(__uint_as_float(v[k]) + bias[k]);
-            const float fg = sigmoid_mufu(__uint_as_float(v[4 + k]) + bias[4 + k]);
-            const float gg = tanh_mufu(__uint_as_float(v[8 + k]) + bias[8 + k]);
-            const float og = sigmoid_mufu(__uint_as_float(v[12 + k]) + bias[12 + k]);
-            c[k] = fmaf(fg, c[k], ig * gg);
-            h2[e] = og * tanh_mufu(c[k]);
-        }
-        hp[u >> 1] = pack_bf16x2(h2[0], h2[1]);
+        const float2 ti = tanh_pair(__uint_as_float(v[u]), __uint_as_float(v[u + 1]));
+        const float2 tf = tanh_pair(__uint_as_float(v[4 + u]), __uint_as_float(v[5 + u]));
+        const float2 tg = tanh_pair(__uint_as_float(v[8 + u]), __uint_as_float(v[9 + u]));
+        const float2 to = tanh_pair(__uint_as_float(v[12 + u]), __uint_as_float(v[13 + u]));
+        const float c0 = fmaf(fmaf(0.5f, tf.x, 0.5f), __uint_as_float(c[u]), fmaf(0.5f, ti.x, 0.5f) * tg.x);
+        const float c1 = fmaf(fmaf(0.5f, tf.y, 0.5f), __uint_as_float(c[u + 1]), fmaf(0.5f, ti.y, 0.5f) * tg.y);
+        c[u] = __float_as_uint(c0); c[u + 1] = __float_as_uint(c1);
+        const float2 tc = tanh_pair(c0, c1);
+        hp[u >> 1] = pack_bf16x2(fmaf(0.5f, to.x, 0.5f) * tc.x, fmaf(0.5f, to.y, 0.5f) * tc.y);
     }
 }
-// one 64-column half of a gate part = 4 groups = 16 hidden units of this thread's env row; `early` = arrive on the tile's
-// A/D barrier as soon as the last accumulator columns are in registers (the next part of the layer may then overwrite D)
-__device__ __forceinline__ void lstm_half(uint32_t t_d, const float* bias, float* c, uint32_t* hp, bool early, uint32_t bar) {
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+// one 64-column half of a gate part = 4 groups = 16 hidden units of this thread's env row; t_c = TMEM address of their cell
+// states; `early` = arrive on the tile's A/D barrier as soon as the last accumulator columns are in registers (the next part of
+// the layer may then overwrite D)
+__device__ __forceinline__ void lstm_half(uint32_t t_d, uint32_t t_c, uint32_t* hp, bool early, uint32_t bar) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        uint32_t v[16];
-        tmem_ld16(t_d + (uint32_t)(g * 16), v); tmem_ld_wait();
+    for (int g = 0; g < 4; ++g) {                    // (two groups per TMEM round trip, LDTM.x32 + x8, measured no faster)
+        uint32_t v[16], c[4];
+        tmem_ld16(t_d + (uint32_t)(g * 16), v);
+        tmem_ld4(t_c + (uint32_t)(g * 4), c);
+        tmem_ld_wait();
         if (g == 3 && early) { tc_fence_before(); mbar_arrive(bar); }
-        lstm_group(v, bias + g * 16, c + g * 4, hp + g * 2);
+        lstm_group(v, c, hp + g * 2);
+        tmem_st4(t_c + (uint32_t)(g * 4), c);
     }
 }
 
-// features [16 ch, 16 ch + 16) of one state frame as 8 packed bf16 pairs (zero beyond in_dim / for invalid rows)
-__device__ __forceinline__ void load_x16(const float* x, int ch, int in_dim, bool valid, uint32_t* pk) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int k = ch * 16 + 2 * j;
-        const float f0 = (valid && k < in_dim) ? __ldg(x + k) : 0.0f;
-        const float f1 = (valid && k + 1 < in_dim) ? __ldg(x + k + 1) : 0.0f;
-        pk[j] = pack_bf16x2(f0, f1);
+// One state frame x_t of a whole tile (128 rows x in_dim floats) crosses from global memory COALESCED: the 256 epilogue threads
+// of the tile walk the (row, feature pair) grid in memory order with 8-byte loads, so a warp-wide request touches ~3 cache
+// lines.  (One thread reading its own row's 26 floats costs 32 L1 wavefronts per load instruction -- measured, that alone was
+// 80 % of an LSTM step; 4-byte cp.async copies are no better, the LSU serialises them per lane.  And with 220 KB of the SM's
+// 228 KB configured as shared memory there is no L1 left to absorb register spills, so this kernel must not spill: that is why
+// the cell state lives in tensor memory.)  The values wait in registers while the step's MMAs and gate math run, then go through
+// a shared-memory transpose (packed bf16 pairs, row stride kXStride words) to the thread that owns the row.  Pair in_dim / 2 of
+// every row is the constant (1, 1) the two bias columns of the weight image multiply; the rest of the 16 pairs is zero (written
+// once at kernel start).
+constexpr int kXRaw = 8;                       // ceil(128 * 15 / 256) feature pairs per thread
+constexpr int kXStride = 20;                   // words per row in shared memory: 16 used, 80-byte rows keep LDS.128 conflict-free
+constexpr int kXBytes = 2 * kTileM * kXStride * 4;
+constexpr int kCriticSmemBytes = kTcSmemBytes + kXBytes;
+
+// idx = tt + 256 k -> (row, pair), walked incrementally (256 = q pairs + rem)
+struct FrameWalk {
+    int row, j, q, rem, pairs;
+    __device__ __forceinline__ FrameWalk(int tt, int pairs_, float inv_pairs) : pairs(pairs_) {
+        row = (int)(((float)tt + 0.5f) * inv_pairs); j = tt - row * pairs;
+        q = (int)(256.5f * inv_pairs); rem = 256 - q * pairs;
     }
+    __device__ __forceinline__ void next() { row += q; j += rem; if (j >= pairs) { j -= pairs; row += 1; } }
+};
+// loads this thread's feature pairs of frame ts and packs them to bf16 at once (8 registers stay live across the gate math; the
+// load latency overlaps the wait for the step's accumulator); also pulls frame ts + 1 into L2
+__device__ __forceinline__ void frame_load(const float* states, long long tile_row0, int ts, int T, int in_dim, size_t row_floats, int n_rows,
+                                           int tt, float inv_pairs, uint32_t (&xp)[kXRaw]) {
+    FrameWalk w(tt, in_dim >> 1, inv_pairs);
+    const float* base = states + tile_row0 * row_floats + (size_t)ts * in_dim;
+    const int rows_left = (int)min((long long)kTileM, (long long)n_rows - tile_row0);
+    float2 raw[kXRaw];
+#pragma unroll
+    for (int k = 0; k < kXRaw; ++k) {
+        const float2* src = reinterpret_cast<const float2*>(base + (size_t)w.row * row_floats) + w.j;
+        raw[k] = make_float2(0.f, 0.f);
+        if (w.row < rows_left) {
+            raw[k] = __ldg(src);
+            if (ts + 1 < T && (k & 1) == 0) prefetch_l2(reinterpret_cast<const float*>(src) + in_dim);
+        }
+        w.next();
+    }
+#pragma unroll
+    for (int k = 0; k < kXRaw; ++k) xp[k] = pack_bf16x2(raw[k].x, raw[k].y);
+}
+__device__ __forceinline__ void frame_store(uint32_t* s_xt, int in_dim, int tt, float inv_pairs, const uint32_t (&xp)[kXRaw]) {
+    FrameWalk w(tt, in_dim >> 1, inv_pairs);
+#pragma unroll
+    for (int k = 0; k < kXRaw; ++k) {
+        if (w.row < kTileM) s_xt[w.row * kXStride + w.j] = xp[k];
+        w.next();
+    }
+}
+// all 256 epilogue threads of tile slot t
+__device__ __forceinline__ void tile_barrier(int t) { asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "r"(256) : "memory"); }
+// features [16 ch, 16 ch + 16) of row r as 8 packed bf16 pairs
+__device__ __forceinline__ void frame_read(const uint32_t* s_xt, int r, int ch, uint32_t* pk) {
+    const uint4 a = *reinterpret_cast<const uint4*>(s_xt + r * kXStride + ch * 8);
+    const uint4 b = *reinterpret_cast<const uint4*>(s_xt + r * kXStride + ch * 8 + 4);
+    pk[0] = a.x; pk[1] = a.y; pk[2] = a.z; pk[3] = a.w; pk[4] = b.x; pk[5] = b.y; pk[6] = b.z; pk[7] = b.w;
 }
 
 // A operand of a fresh tile: h_0 = 0 in columns [0, 32), x_0 in [32, 48), zeros in [48, 64) (TMEM is never read uninitialised:
-// the weight rows of the padding are zero, but 0 * NaN is NaN)
+// the weight rows of the padding are zero, but 0 * NaN is NaN), and the cell state c_0 = 0 as fp32 in the columns [64, 128) the
+// LSTM phase does not use as an operand (unit k -> column 64 + k)
 __device__ __forceinline__ void stage_new_tile(uint32_t t_a, int ch, const uint32_t* x0) {
     uint32_t z[16];
 #pragma unroll
@@ -110,6 +188,8 @@ __device__ __forceinline__ void stage_new_tile(uint32_t t_a, int ch, const uint3
     tmem_st16(t_a + (uint32_t)(kAColH + ch * 16), z);
     tmem_st8(t_a + (uint32_t)(kAColX + ch * 8), x0);
     tmem_st8(t_a + (uint32_t)(kAColX + 16 + ch * 8), z);
+    tmem_st16(t_a + (uint32_t)(kAColC + ch * 32), z);
+    tmem_st16(t_a + (uint32_t)(kAColC + ch * 32 + 16), z);
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTcParams p) {
@@ -125,12 +205,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
     const uint32_t bar_a = bar_empty + 8 * kSlots;
     const uint32_t bar_d = bar_a + 16;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 4);
+    uint32_t* s_x = reinterpret_cast<uint32_t*>(sm + kTcSmemBytes - 1024);       // [2 tiles][128 rows][kXStride] staged state frames (bf16 pairs)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_pairs = (p.num_tiles + 1) >> 1;
     const int T = p.seq_len;
     const int n_sched = T + p.n_hidden + 1;            // T LSTM steps, the MLP hidden layers, the output part
 
+    // constant part of the staged frames: pair in_dim / 2 = (1, 1) (the bias columns), zero elsewhere
+    for (int i = threadIdx.x; i < 2 * kTileM * kXStride; i += kTcThreads) s_x[i] = (i % kXStride == (p.in_dim >> 1)) ? 0x3F803F80u : 0u;
     for (int i = threadIdx.x; i < kMaxHidden * kMaxN; i += kTcThreads) s_bias[i] = p.bias[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < kSlots; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -167,6 +250,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
     } else if (warp == 1) {
         // ===================== MMA issuer (see actor_tc.cuh): the two tiles alternate part by part and share every weight slot
         uint32_t slot = 0, phase = 0, a_phase = 0;
+        int dbg_n = lane == 0 ? 0 : kDbgCap;
         const uint64_t bdesc0 = umma_desc_sw128(s_ring);
         for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
             const int nt = (2 * pair + 1 < p.num_tiles) ? 2 : 1;
@@ -182,6 +266,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
                             mbar_wait(bar_a + 8 * t, (a_phase >> t) & 1u); a_phase ^= (1u << t);
                             if (t == 0) mbar_wait(bar_full + 8 * slot, phase);
                             tc_fence_after();
+                            TACO_DBG(0, dbg_n, 0x20 | t);
                             if (elect_one_sync()) {
                                 const uint32_t a_addr = tmem0 + (uint32_t)(t * kTmemSlot);
                                 const uint32_t d_addr = a_addr + (uint32_t)kTmemD;
@@ -197,6 +282,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
                                 umma_commit(bar_d + 8 * t);
                             }
                             __syncwarp();
+                            TACO_DBG(0, dbg_n, 0x30 | t);
                         }
                     }
                     if (++slot == kSlots) { slot = 0; phase ^= 1u; }
@@ -211,13 +297,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
         const uint32_t t_a = tmem0 + ((uint32_t)(quad << 5) << 16) + (uint32_t)(t * kTmemSlot);
         const uint32_t t_d = t_a + (uint32_t)kTmemD + (uint32_t)(ch * 64);
         uint32_t d_phase = 0;
+        int dbg_n = (ch == 0 && quad == 0 && lane == 0) ? 0 : kDbgCap;
         const size_t row_floats = (size_t)T * p.in_dim;
         int tile = 2 * (int)blockIdx.x + t;
         const int tile_step = 2 * (int)gridDim.x;
+        const int tt = ((e & 7) << 5) | lane;                       // index among the 256 epilogue threads of this tile
+        const float inv_in = 1.0f / (float)(p.in_dim >> 1);           // 1 / feature pairs per frame
+        uint32_t* s_xt = s_x + t * (kTileM * kXStride);
         if (tile < p.num_tiles) {
-            const long long row0 = (long long)tile * kTileM + r;
             uint32_t x0[8];
-            load_x16(p.states + row0 * row_floats, ch, p.in_dim, row0 < p.n_rows, x0);
+            uint32_t raw[kXRaw];
+            frame_load(p.states, (long long)tile * kTileM, 0, T, p.in_dim, row_floats, p.n_rows, tt, inv_in, raw);
+            frame_store(s_xt, p.in_dim, tt, inv_in, raw);
+            tile_barrier(t);
+            frame_read(s_xt, r, ch, x0);
             stage_new_tile(t_a, ch, x0);
             tmem_st_wait();
             tc_fence_before();
@@ -233,33 +326,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
             const bool valid = row < p.n_rows;
             const bool has_next = tile + tile_step < p.num_tiles;
             const long long row_next = row + (long long)tile_step * kTileM;
-            const float* xs = p.states + row * row_floats;
             const float* xs_next = p.states + row_next * row_floats;
             if (has_next && row_next < p.n_rows) prefetch_l2(xs_next + ch * 16);
-            float c[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) c[j] = 0.0f;
             // ---- T LSTM steps
             for (int ts = 0; ts < T; ++ts) {
                 const bool have_x = ts + 1 < T;
-                uint32_t xn[8], hp[16];
-                if (have_x) load_x16(xs + (size_t)(ts + 1) * p.in_dim, ch, p.in_dim, valid, xn);
+                uint32_t hp[16];
+                uint32_t raw[kXRaw];
+                TACO_DBG(1 + t, dbg_n, 0x08);
+                // x_{t+1}: with one gate part the loads fly while the step's MMAs run; with two they are issued between the parts
+                // (their latency then overlaps part 1's MMAs instead of delaying the drain of part 0)
+                if (have_x && !g_two) frame_load(p.states, (long long)tile * kTileM, ts + 1, T, p.in_dim, row_floats, p.n_rows, tt, inv_in, raw);
                 mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
                 tc_fence_after();
-                if (g_mine0) lstm_half(t_d, s_bias + ch * 64, c, hp, g_two, bar_a + 8 * t);      // D drained: part 1 may start
+                TACO_DBG(1 + t, dbg_n, 0x02);
+                if (g_mine0) lstm_half(t_d, t_a + (uint32_t)(kAColC + ch * 16), hp, g_two, bar_a + 8 * t);      // D drained: part 1 may start
                 else if (g_two) { tc_fence_before(); mbar_arrive(bar_a + 8 * t); }
+                TACO_DBG(1 + t, dbg_n, 0x0A);
+                if (have_x && g_two) frame_load(p.states, (long long)tile * kTileM, ts + 1, T, p.in_dim, row_floats, p.n_rows, tt, inv_in, raw);
+                TACO_DBG(1 + t, dbg_n, 0x09);
                 if (g_two) {
                     mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
                     tc_fence_after();
+                    TACO_DBG(1 + t, dbg_n, 0x04);
                 }
-                if (g_mine1) lstm_half(t_d, s_bias + kPartN + ch * 64, c + 16, hp + 8, false, 0u);
+                if (g_mine1) lstm_half(t_d, t_a + (uint32_t)(kAColC + 32 + ch * 16), hp + 8, false, 0u);
                 // every MMA of this step on this tile is complete: h_t over h_{t-1} (unit k -> packed column k / 2), x_{t+1} over x_t
                 if (g_mine0) tmem_st8(t_a + (uint32_t)(kAColH + ch * 8), hp);
                 if (g_mine1) tmem_st8(t_a + (uint32_t)(kAColH + 16 + ch * 8), hp + 8);
-                if (have_x) tmem_st8(t_a + (uint32_t)(kAColX + ch * 8), xn);
+                TACO_DBG(1 + t, dbg_n, 0x0B);
+                if (have_x) {                                         // x_{t+1}: registers -> shared-memory transpose -> own row -> A operand
+                    // every thread of the tile read x_t out of the staging buffer before it arrived on bar_a at the end of the
+                    // previous step, and this step's MMAs needed all those arrivals: the buffer is free
+                    uint32_t xn[8];
+                    frame_store(s_xt, p.in_dim, tt, inv_in, raw);
+                    tile_barrier(t);
+                    frame_read(s_xt, r, ch, xn);
+                    tmem_st8(t_a + (uint32_t)(kAColX + ch * 8), xn);
+                }
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(bar_a + 8 * t);
+                TACO_DBG(1 + t, dbg_n, 0x05);
             }
             // ---- MLP hidden layers (as in the actor kernel)
             for (int l = 1; l <= p.n_hidden; ++l) {
@@ -298,13 +406,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
                 mbar_arrive(bar_a + 8 * t);
             }
             // ---- output part (column 0 of 16): the next tile's A operand is staged before the value leaves
-            uint32_t x0[8];
-            if (has_next) load_x16(xs_next, ch, p.in_dim, row_next < p.n_rows, x0);
+            uint32_t raw[kXRaw];
+            if (has_next) frame_load(p.states, (long long)(tile + tile_step) * kTileM, 0, T, p.in_dim, row_floats, p.n_rows, tt, inv_in, raw);
             mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
             tc_fence_after();
             uint32_t v[4];
             if (ch == 0) { tmem_ld4(t_d, v); tmem_ld_wait(); }
             if (has_next) {
+                uint32_t x0[8];
+                frame_store(s_xt, p.in_dim, tt, inv_in, raw);
+                tile_barrier(t);
+                frame_read(s_xt, r, ch, x0);
                 stage_new_tile(t_a, ch, x0);
                 tmem_st_wait();
                 tc_fence_before();
@@ -323,30 +435,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
 
 // LSTM weights (torch layout: w_ih (4H, In), w_hh (4H, H), gate row blocks i, f, g, o) -> two bf16 K-chunk images of n = 4H
 // rows each in the SWIZZLE_128B K-major layout: chunk 0 = W_hh (K padded to 64), chunk 1 = W_ih (K padded to 64).  Image row
-// r = 128 part + j holds gate (j % 16) / 4 of hidden unit 32 part + 4 (j / 16) + j % 4.  bias_perm[r] = b_ih + b_hh of that row.
+// r = 128 part + j holds gate (j % 16) / 4 of hidden unit 32 part + 4 (j / 16) + j % 4.  Columns in_dim / in_dim + 1 of the W_ih chunk
+// hold b_ih + b_hh split into two bf16 halves (the kernel feeds 1.0 there); rows of the i, f, o gates are scaled by 1/2.
 __device__ __forceinline__ int lstm_src_row(int r, int hidden) {
     const int part = r >> 7, j = r & 127;
     const int unit = part * 32 + (j >> 4) * 4 + (j & 3), gate = (j & 15) >> 2;
     return unit < hidden ? gate * hidden + unit : -1;
 }
 __global__ void pack_lstm_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
-                                 const float* __restrict__ b_hh, int hidden, int in_dim, int n, uint8_t* __restrict__ img,
-                                 float* __restrict__ bias_perm) {
+                                 const float* __restrict__ b_hh, int hidden, int in_dim, int n, uint8_t* __restrict__ img) {
     const int total = 2 * n * 8;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int q = i & 7, r = (i >> 3) % n, c = (i >> 3) / n;
         const int src = lstm_src_row(r, hidden);
         const float* w = c == 0 ? w_hh : w_ih;
         const int k = c == 0 ? hidden : in_dim;
+        const float scale = (src >= 0 && src / hidden == 2) ? 1.0f : 0.5f;      // i, f, o rows: sigmoid(x) = 0.5 + 0.5 tanh(x / 2)
         float f[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int kk = q * 8 + j;
-            f[j] = (src >= 0 && kk < k) ? w[(size_t)src * k + kk] : 0.0f;
+            f[j] = (src >= 0 && kk < k) ? scale * w[(size_t)src * k + kk] : 0.0f;
+            if (c == 1 && src >= 0 && (kk == in_dim || kk == in_dim + 1)) {     // bias columns: bf16 hi part, then the bf16 of the rest
+                const float b = scale * (b_ih[src] + b_hh[src]);
+                const float hi = __bfloat162float(__float2bfloat16_rn(b));
+                f[j] = kk == in_dim ? hi : b - hi;
+            }
         }
         const uint4 pk = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
         *reinterpret_cast<uint4*>(img + (size_t)c * n * 128 + sw128_off(r, q)) = pk;
-        if (c == 0 && q == 0) bias_perm[r] = src >= 0 ? b_ih[src] + b_hh[src] : 0.0f;
     }
 }
 

@@ -225,7 +225,7 @@ int taco_critic_create(int device, int32_t in_dim, int32_t seq_len, int32_t lstm
     if (prop.major != 10) { c->tc_ok = false; c->tc_why = "device is not sm_100"; }
     else if (lstm_layers != 1) { c->tc_ok = false; c->tc_why = "needs a single LSTM layer"; }
     else if (H % 16 != 0 || H > kTcMaxLstmHidden) { c->tc_ok = false; c->tc_why = "LSTM width must be a multiple of 16, <= 64"; }
-    else if (in_dim > kTcMaxIn) { c->tc_ok = false; c->tc_why = "input width > 32"; }
+    else if (in_dim > kTcMaxIn || (in_dim & 1)) { c->tc_ok = false; c->tc_why = "input width must be even, <= 30"; }
     else if (seq_len > kMaxSeq) { c->tc_ok = false; c->tc_why = "sequence length > 8"; }
     else if (n_hidden < 1 || n_hidden > kMaxMlpHidden) { c->tc_ok = false; c->tc_why = "needs 1..3 MLP hidden layers"; }
     else {
@@ -249,7 +249,7 @@ int taco_critic_create(int device, int32_t in_dim, int32_t seq_len, int32_t lstm
         ce = cudaMalloc(&c->wimg, img);
         if (ce == cudaSuccess) ce = cudaMalloc(&c->bias_pad, taco::actor::kMaxHidden * taco::actor::kMaxN * sizeof(float));
         if (ce == cudaSuccess) ce = cudaMalloc(&c->b_out, taco::actor::kOutPad * sizeof(float));
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(critic_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, taco::actor::kTcSmemBytes);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(critic_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCriticSmemBytes);
     }
     if (ce == cudaSuccess && c->fp_smem > 48 * 1024)
         ce = cudaFuncSetAttribute(critic_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->fp_smem);
@@ -296,7 +296,7 @@ int taco_critic_load(TacoCritic* c, const float* const* lstm_host, const float* 
         const int n_hidden = c->n_mlp - 1;
         CRT_CUDA(cudaMemsetAsync(c->bias_pad, 0, taco::actor::kMaxHidden * taco::actor::kMaxN * sizeof(float), s));
         pack_lstm_kernel<<<64, 256, 0, s>>>(c->lstm_f32 + c->lstm_off[0], c->lstm_f32 + c->lstm_off[1], c->lstm_f32 + c->lstm_off[2],
-                                            c->lstm_f32 + c->lstm_off[3], H, c->in_dim, 4 * H, c->wimg, c->bias_pad);
+                                            c->lstm_f32 + c->lstm_off[3], H, c->in_dim, 4 * H, c->wimg);
         for (int l = 0; l <= n_hidden; ++l) {
             const int in = c->mlp_sizes[l], out = c->mlp_sizes[l + 1];
             taco::actor::pack_weights_kernel<<<64, 256, 0, s>>>(c->w_f32 + c->w_off[l], out, c->tc_layer[1 + l].n, in, c->wimg + c->tc_layer[1 + l].img_off);
@@ -332,7 +332,20 @@ int taco_critic_forward(TacoCritic* c, const float* states_dev, float* value_dev
         for (int l = 0; l <= p.n_hidden + 1; ++l) p.layer[l] = c->tc_layer[l];
         const int num_pairs = (p.num_tiles + 1) / 2;
         const int grid = num_pairs < c->num_sms ? num_pairs : c->num_sms;
-        critic_tc_kernel<<<grid, taco::actor::kTcThreads, taco::actor::kTcSmemBytes, s>>>(p);
+        // developer aid: TACO_CRITIC_TIMELINE=<file> records clock64 stamps of CTA 0's MMA issuer / epilogue (synchronous)
+        const char* tl = getenv("TACO_CRITIC_TIMELINE");
+        if (tl && *tl) {
+            CRT_CUDA(cudaMalloc(&p.dbg, 3 * taco::actor::kDbgCap * sizeof(unsigned long long)));
+            CRT_CUDA(cudaMemsetAsync(p.dbg, 0, 3 * taco::actor::kDbgCap * sizeof(unsigned long long), s));
+        }
+        critic_tc_kernel<<<grid, taco::actor::kTcThreads, kCriticSmemBytes, s>>>(p);
+        if (p.dbg) {
+            std::vector<unsigned long long> h(3 * taco::actor::kDbgCap);
+            CRT_CUDA(cudaStreamSynchronize(s));
+            CRT_CUDA(cudaMemcpy(h.data(), p.dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            cudaFree(p.dbg);
+            if (FILE* f = fopen(tl, "wb")) { fwrite(h.data(), sizeof(unsigned long long), h.size(), f); fclose(f); }
+        }
     } else {
         FpParams p;
         memset(&p, 0, sizeof(p));
