@@ -244,11 +244,53 @@ def actor_rollout_point(torch, taco_b200, dev, n, hidden, strict_fp, peaks, iter
 
     ms_env = _timed(torch, env_only, iters)
     ms_loop = _timed(torch, loop, iters)
+    # ---- the critic of the reference's training command (README.md:60-66: LSTM encoder over the 5 x 26 state history + MLP) joins
+    # the loop: agent.act = actor sample + critic value (nets_asymmetry.py:326-352), then env.step
+    crit = None
+    try:
+        c_hid, c_mlp = 64, list(hidden)
+        cs = [c_hid] + c_mlp + [1]
+        lstm = []
+        w_ih = torch.empty(4 * c_hid, 26); w_hh = torch.empty(4 * c_hid, c_hid)
+        torch.nn.init.xavier_uniform_(w_ih, generator=gen); torch.nn.init.xavier_uniform_(w_hh, generator=gen)      # LSTMEncoder.para_init
+        lstm.append((w_ih, w_hh, torch.zeros(4 * c_hid), torch.zeros(4 * c_hid)))
+        cw, cb = [], []
+        for l in range(len(cs) - 1):
+            w = torch.empty(cs[l + 1], cs[l])
+            torch.nn.init.orthogonal_(w, gain=(2 ** 0.5 if l + 2 < len(cs) else 0.01), generator=gen)
+            cw.append(w); cb.append(torch.zeros(cs[l + 1]))
+        critic = taco_b200.CriticLSTM(26, 5, c_hid, c_mlp, device=dev)
+        critic.load(lstm, cw, cb)
+        value = torch.empty(n, 1, device=dev)
+        ctc = critic.tensor_cores_available
+        ms_c_fp32 = _timed(torch, lambda: critic.forward(env.states_buf, tensor_cores=False, out=value), 3, warm=1)
+        ms_c_tc = _timed(torch, lambda: critic.forward(env.states_buf, tensor_cores=True, out=value), iters) if ctc else None
+
+        def loop_ac():
+            _, clipped, _, _ = actor.act(env.obs_buf, k[0], seed=SEED, tensor_cores=tc)
+            critic.forward(env.states_buf, tensor_cores=ctc, out=value)
+            env.step(clipped); k[0] += 1
+
+        ms_loop_ac = _timed(torch, loop_ac, iters)
+        c_flops = 5 * 2.0 * (26 + c_hid) * 4 * c_hid + 2.0 * sum(cs[i] * cs[i + 1] for i in range(len(cs) - 1))
+        crit = {"workload": f"critic = LSTM(26 -> {c_hid}) over the 5-frame state history + MLP {'x'.join(map(str, cs))} (sizes are OUR stated default: "
+                            "the reference YAML is missing), agent.act = actor sample + critic value, then env.step, every step",
+                "value": n / (ms_loop_ac * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_loop_ac, "critic_fp32_ms": ms_c_fp32,
+                "critic_tc_ms": ms_c_tc, "critic_flops_per_env": c_flops, "gpu_launches_per_step": 3}
+        if ms_c_tc:
+            ach = c_flops * n / (ms_c_tc * 1e-3) / 1e12
+            peak = float(peaks.get("bf16_tflops", 1590.0))
+            crit["critic_roofline"] = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                                       "kernel": "critic_tc_kernel", "speedup_vs_fp32_kernel": ms_c_fp32 / ms_c_tc}
+        critic.close()
+    except Exception as exc:      # the config-3 line must not be lost to the (newer) critic point
+        crit = {"error": repr(exc)}
     flops = 2.0 * sum(sizes[i] * sizes[i + 1] for i in range(len(sizes) - 1))        # per env, SURVEY.md section 8(d)
     out = {"workload": f"mix task, {n} envs, actor {'x'.join(map(str, sizes))} (hidden sizes are OUR stated default: the reference YAML is missing), "
                        "random-init policy, spectral projection c=4 once per update, act -> clip -> step every step",
            "value": n / (ms_loop * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_loop, "env_step_ms": ms_env,
-           "actor_fp32_ms": ms_fp32, "actor_tc_ms": ms_tc, "actor_flops_per_env": flops, "gpu_launches_per_step": 2}
+           "actor_fp32_ms": ms_fp32, "actor_tc_ms": ms_tc, "actor_flops_per_env": flops, "gpu_launches_per_step": 2,
+           "with_critic": crit}
     if ms_tc:
         ach = flops * n / (ms_tc * 1e-3) / 1e12
         peak = float(peaks.get("bf16_tflops", 1590.0))

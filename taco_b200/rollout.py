@@ -76,7 +76,8 @@ class RolloutBuffer:
             self.rew_buf[s].copy_(rew.view(-1, 1))
         if done is not None:
             self.done_buf[s].copy_(done.view(-1, 1))
-        self.value_buf[s].copy_(value)
+        if value.data_ptr() != self.value_buf[s].data_ptr():
+            self.value_buf[s].copy_(value)
         if mu is not None and mu.data_ptr() != self.mu_buf[s].data_ptr():
             self.mu_buf[s].copy_(mu)
         self.sigma_buf[s].copy_(sigma)
@@ -127,13 +128,15 @@ def collect_rollout(env, actor, buffer, value_fn, seed=0, tensor_cores=True, gro
     """One rollout of ``buffer.horizon_len`` steps: the data-collection loop of ``PPO.run``
     (IsaacGymEnvs/algorithms/ppo_asymmetry.py:305-342) with no host round trip inside it.
 
-    ``env``: FpvVecTask; ``actor``: ActorMLP (weights loaded); ``value_fn(obs, states) -> (N,1)``: the critic, which stays a
-    PyTorch module.  Per step: the actor kernel samples straight into the buffer rows, the step
-    kernel writes the next observation history into ring slot s+1 and reward / done / time-out into row s.  The time-out
-    bootstrap, GAE and the advantage normalisation (with the moments all-reduced under torch.distributed) run in
-    ``buffer.compute_returns_and_advantage``; episode statistics come from the env's device-side vector, all-reduced once.
-    Returns the (8,) float64 statistics tensor (see taco_b200.dist.STAT_NAMES)."""
+    ``env``: FpvVecTask; ``actor``: ActorMLP (weights loaded); ``value_fn``: a ``CriticLSTM`` (the critic kernels write the value
+    straight into ``buffer.value_buf[s]``) or any callable ``value_fn(obs, states) -> (N,1)`` (e.g. a PyTorch critic module).
+    Per step -- ``agent.act`` of the reference (nets_asymmetry.py:326-352): the actor kernel samples straight into the buffer
+    rows, the critic kernel values the state history, the step kernel writes the next observation history into ring slot s+1
+    and reward / done / time-out into row s.  The time-out bootstrap, GAE and the advantage normalisation (with the moments
+    all-reduced under torch.distributed) run in ``buffer.compute_returns_and_advantage``; episode statistics come from the
+    env's device-side vector, all-reduced once.  Returns the (8,) float64 statistics tensor (see taco_b200.dist.STAT_NAMES)."""
     from . import dist as tdist
+    from .critic import CriticLSTM
     if env.rollout_buffer is not buffer:
         env.attach_rollout(buffer)
     else:
@@ -141,13 +144,21 @@ def collect_rollout(env, actor, buffer, value_fn, seed=0, tensor_cores=True, gro
     buffer.reset()
     H = buffer.horizon_len
     sigma = torch.from_numpy(actor.log_std).to(buffer.device).expand(buffer.num_envs, -1)     # act() returns log_std as `sigma`
+    native_critic = isinstance(value_fn, CriticLSTM)
+    critic_tc = native_critic and tensor_cores and value_fn.tensor_cores_available
     for s in range(H):
         obs, states = buffer.obs_ring[s], buffer.states_ring[s]
         out = buffer.rows(s)
         actor.act(obs, env.step_count, seed=seed, env_offset=env.env_offset, tensor_cores=tensor_cores, out=out)
-        value = value_fn(obs, states)
+        if native_critic:
+            value = value_fn.forward(states, tensor_cores=critic_tc, out=buffer.value_buf[s])
+        else:
+            value = value_fn(obs, states)
         env.step(out[1])
         buffer.store(None, None, out[0], None, out[2], None, value, out[3], sigma, time_outs=True)
-    last_value = value_fn(buffer.obs_ring[H], buffer.states_ring[H])
+    if native_critic:
+        last_value = value_fn.forward(buffer.states_ring[H], tensor_cores=critic_tc)
+    else:
+        last_value = value_fn(buffer.obs_ring[H], buffer.states_ring[H])
     buffer.compute_returns_and_advantage(last_value, group=group)
     return tdist.allreduce_rollout_stats(env.stats(), group=group)

@@ -89,3 +89,38 @@ def test_collect_rollout_matches_reference_style_loop():
         assert (tout.bool() & (done != 0)).any(), "window must contain truncated episodes"
         assert stats[1].item() == done.sum().item() and stats[2].item() == (tout.bool() & (done != 0)).sum().item()
     env.close(); actor.close()
+
+
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_collect_rollout_with_native_critic(tensor_cores):
+    """agent.act of the reference (actor sample + critic value, nets_asymmetry.py:326-352) entirely in the library: the critic
+    kernels write value_buf rows in place; values equal a separate CriticLSTM.forward on the stored state histories."""
+    from taco_b200 import ActorMLP, CriticLSTM, FpvVecTask, RolloutBuffer, collect_rollout, make_cfg
+    from oracle import critic as oc, gae as og
+    n, H, gamma, lam = 1500, 6, 0.99, 0.95
+    env = FpvVecTask(make_cfg("flip", n), seed=5)
+    gen = torch.Generator().manual_seed(1)
+    sizes = [26, 64, 64, 4]
+    actor = ActorMLP(26, [64, 64], 4)
+    actor.load([torch.randn(sizes[i + 1], sizes[i], generator=gen) * 0.2 for i in range(3)], [torch.zeros(sizes[i + 1]) for i in range(3)])
+    hid, mlp = 32, [64, 64]
+    lstm = [(torch.randn(4 * hid, 26, generator=gen) * 0.3, torch.randn(4 * hid, hid, generator=gen) * 0.2,
+             torch.randn(4 * hid, generator=gen) * 0.1, torch.randn(4 * hid, generator=gen) * 0.1)]
+    cs = [hid] + mlp + [1]
+    cw = [torch.randn(cs[i + 1], cs[i], generator=gen) / cs[i] ** 0.5 for i in range(3)]
+    cb = [torch.randn(cs[i + 1], generator=gen) * 0.1 for i in range(3)]
+    critic = CriticLSTM(26, 5, hid, mlp)
+    critic.load(lstm, cw, cb)
+    buf = RolloutBuffer(n, 26, 1, 26, 5, 4, H, 1, gamma, lam, "cuda:0")
+    collect_rollout(env, actor, buf, critic, seed=3, tensor_cores=tensor_cores)
+    val = torch.stack([critic.forward(buf.states_ring[s], tensor_cores=tensor_cores) for s in range(H)])
+    assert torch.equal(buf.value_buf, val)
+    ref = torch.stack([oc.critic_forward(buf.states_ring[s].cpu(), lstm, cw, cb) for s in range(H)])
+    tol = 3e-2 if tensor_cores else 5e-6
+    assert (val.cpu() - ref).abs().max().item() <= tol
+    last = critic.forward(buf.states_ring[H], tensor_cores=tensor_cores).cpu()
+    rew, done, tout = buf.rew_buf.cpu().squeeze(-1), buf.done_buf.cpu().squeeze(-1), buf.timeout_buf.cpu().squeeze(-1)
+    aug = og.bootstrap_timeouts(rew, val.cpu().squeeze(-1), done, tout, gamma)
+    adv, ret = og.gae(aug.unsqueeze(-1), done.unsqueeze(-1), val.cpu(), last, gamma, lam)
+    assert torch.equal(buf.ret_buf.cpu(), ret)
+    env.close(); actor.close(); critic.close()
