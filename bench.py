@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-small", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="multi-GPU runs: do not pin each rank to its GPU's NUMA node (comparison runs)")
     ap.add_argument("--no-actor", action="store_true", help="skip the BASELINE config 3 point (mix task + actor MLP in the rollout loop)")
     ap.add_argument("--actor-envs", type=int, default=262144)
     ap.add_argument("--actor-hidden", default="256,256,256", help="actor hidden sizes (not pinned by the reference: the YAML is missing; our stated default)")
@@ -312,6 +313,8 @@ def main():
     import torch
     import torch.distributed as dist
     import taco_b200
+    from taco_b200 import dist as tdist
+    numa_cpus = tdist.bind_to_gpu_numa(local_rank) if (world > 1 and not args.no_numa) else None    # pinned host buffers next to the rank's GPU
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
     torch.cuda.set_device(local_rank)
@@ -414,7 +417,7 @@ def main():
             "config": {"workload": f"{args.task} task fused env step (BASELINE configs[1] scaled to {n} envs/GPU so the working set exceeds L2), "
                                    f"len_obs=1, len_states=5, delay_time=20, rotor_response_time=0.017, substeps=2, "
                                    f"{'per-env DR on' if args.dr else 'no per-env DR'}, U(-1,1) Philox actions",
-                       "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-sharded x{world}",
+                       "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-sharded x{world}", "rank0_numa_bound_cpus": (len(numa_cpus) if numa_cpus else None),
                        "l2": "inputs larger than L2 (working set ~%.1f GB/GPU)" % (n * 1900 / 1e9),
                        "fp_mode": "fast (FMA contraction)" if args.fast_fp else "strict (-fmad=false, the parity-tested build)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -171,6 +171,11 @@ int taco_actor_sigmas(TacoActor* actor, double* out_host);
 int taco_actor_weights(TacoActor* actor, int32_t layer, float* w_host, float* b_host);
 /* 1 when the tcgen05 path supports this actor's shape on this device */
 int taco_actor_tc_available(TacoActor* actor);
+/* PPO.spectral_normalize_actors (ppo_asymmetry.py:398-404) for one (rows, cols) row-major float32 matrix that already lives on the
+ * device -- e.g. the storage of an nn.Linear weight between optimiser steps (ppo_asymmetry.py:248-249): sigma = largest singular
+ * value (power iteration in double precision) is written to sigma_dev (one double, device); when lipschitz_const > 0 and
+ * sigma > lipschitz_const the matrix is scaled in place by lipschitz_const / sigma.  Asynchronous on `stream`, no host sync. */
+int taco_spectral_project(int device, float* w_dev, int32_t rows, int32_t cols, float lipschitz_const, double* sigma_dev, void* stream);
 /* mean = tanh(MLP(obs)); obs_dev (n, in) f32 contiguous, mean_dev (n, out) f32.  use_tensor_cores = 0 selects the FP32
  * CUDA-core path, 1 the tcgen05 bf16 path (TACO_E_INVALID when unavailable).  Asynchronous on `stream`. */
 int taco_actor_forward(TacoActor* actor, const float* obs_dev, float* mean_dev, int32_t n, int32_t use_tensor_cores,

@@ -128,3 +128,27 @@ class ActorMLP:
             self.close()
         except Exception:
             pass
+
+
+def spectral_normalize_(params, lipschitz_const):
+    """``PPO.spectral_normalize_actors`` (ppo_asymmetry.py:398-404) on the device, in place and without a host sync: every
+    parameter with >= 2 dimensions whose spectral norm exceeds ``lipschitz_const`` is scaled back onto the ball.  ``params``: an
+    iterable of CUDA float32 tensors (e.g. ``agent.actor_mlp.parameters()``); biases are skipped like in the reference.
+    Returns the (n_matrices,) float64 device tensor of the spectral norms found (before scaling)."""
+    mats = [p for p in params if p.dim() >= 2]
+    if not mats:
+        return torch.zeros(0, dtype=torch.float64)
+    dev = mats[0].device
+    if dev.type != "cuda":
+        raise RuntimeError("spectral_normalize_ runs on CUDA tensors only (no CPU fallback)")
+    lib = _capi.lib()
+    sig = torch.zeros(len(mats), dtype=torch.float64, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    for i, p in enumerate(mats):
+        w = p.data
+        if w.dtype != torch.float32 or not w.is_contiguous() or w.device != dev:
+            raise ValueError("spectral_normalize_: parameters must be contiguous float32 tensors on one CUDA device")
+        rows = w.shape[0]
+        _capi.check(lib.taco_spectral_project(dev.index or 0, C.c_void_p(w.data_ptr()), rows, w.numel() // rows, float(lipschitz_const),
+                                              C.c_void_p(sig[i:].data_ptr()), stream), "taco_spectral_project")
+    return sig

@@ -364,6 +364,20 @@ int taco_actor_weights(TacoActor* a, int32_t layer, float* w_host, float* b_host
 
 int taco_actor_tc_available(TacoActor* a) { return (a && a->tc_ok) ? 1 : 0; }
 
+// PPO.spectral_normalize_actors for ONE parameter that already lives on the device (e.g. the storage of a torch nn.Linear weight
+// during PPO.update, ppo_asymmetry.py:248-249): in place, asynchronous, no SVD and no host round trip.
+int taco_spectral_project(int device, float* w_dev, int32_t rows, int32_t cols, float lipschitz_const, double* sigma_dev, void* stream) {
+    if (!w_dev || !sigma_dev) return afail(TACO_E_INVALID, "taco_spectral_project: null argument");
+    if (rows < 1 || cols < 1 || (size_t)(rows + cols) * sizeof(double) > 200 * 1024)
+        return afail(TACO_E_INVALID, "taco_spectral_project: rows + cols must be in [2, 25600]");
+    DevGuard guard(device);
+    const size_t smem = (size_t)(rows + cols) * sizeof(double);
+    if (smem > 48 * 1024) ACT_CUDA(cudaFuncSetAttribute(spectral_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spectral_norm_kernel<<<1, kSnThreads, smem, (cudaStream_t)stream>>>(w_dev, rows, cols, lipschitz_const, sigma_dev, 20000, 1e-12);
+    ACT_CUDA(cudaGetLastError());
+    return TACO_OK;
+}
+
 int taco_actor_forward(TacoActor* a, const float* obs_dev, float* mean_dev, int32_t n, int32_t use_tensor_cores, void* stream) {
     SampleParams sp;
     memset(&sp, 0, sizeof(sp));

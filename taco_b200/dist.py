@@ -42,3 +42,31 @@ def summarise(stats):
     return {"mean_reward": s["sum_reward"] / steps, "mean_episode_return": s["sum_episode_return"] / eps,
             "mean_episode_length": s["sum_episode_length"] / eps, "done_rate": s["n_done"] / steps,
             "timeout_fraction": s["n_timeout"] / eps, **s}
+
+
+def bind_to_gpu_numa(gpu_index):
+    """Pin the calling process to the CPUs NVML reports as local to GPU ``gpu_index`` (its NUMA node), so that pinned host
+    buffers allocated afterwards -- the action / result buffers of ``step_host`` -- live in memory next to that GPU's PCIe root
+    port instead of on whichever socket torchrun happened to start the rank.  Returns the CPU set, or None when NVML or the
+    affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v.strip() for v in vis.split(",") if v.strip()]
+        if ids:                                              # CUDA index -> NVML index (or UUID) through the visibility list
+            ident = ids[int(gpu_index)]
+            handle = pynvml.nvmlDeviceGetHandleByIndex(int(ident)) if ident.isdigit() else pynvml.nvmlDeviceGetHandleByUUID(ident)
+        else:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None

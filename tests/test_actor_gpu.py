@@ -138,3 +138,21 @@ def test_shape_errors_are_loud():
     with pytest.raises(ValueError):
         a.forward(torch.zeros(8, 27, device="cuda"))
     a.close()
+
+
+def test_device_side_projection_of_torch_parameters(golden_dir):
+    """spectral_normalize_ == PPO.spectral_normalize_actors on nn.Linear weights that live on the GPU (golden: the reference's own
+    method), in place, biases untouched."""
+    from taco_b200 import spectral_normalize_
+    g, w, b = _golden(golden_dir)
+    lin = [torch.nn.Linear(x.shape[1], x.shape[0]).cuda() for x in w]
+    with torch.no_grad():
+        for m, wl, bl in zip(lin, w, b):
+            m.weight.copy_(wl); m.bias.copy_(bl)
+    params = [p for m in lin for p in m.parameters()]
+    sig = spectral_normalize_(params, float(g["lipschitz"]))
+    torch.testing.assert_close(sig.cpu().float(), g["sigma_before"], rtol=1e-5, atol=0)
+    for l, m in enumerate(lin):
+        ref = g[f"w{l}_proj"]
+        assert (m.weight.detach().cpu() - ref).abs().max().item() <= 2e-6 * ref.abs().max().item() + 1e-9, l
+        assert torch.equal(m.bias.detach().cpu(), b[l])

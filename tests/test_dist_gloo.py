@@ -78,3 +78,15 @@ def test_shard_and_groups_and_summary():
     with pytest.raises(ValueError):
         tdist.allreduce_rollout_stats(torch.zeros(8))
     assert tdist.allreduce_rollout_stats(torch.ones(8, dtype=torch.float64)).sum() == 8     # no process group: no-op
+
+
+def test_bind_to_gpu_numa_is_harmless_without_nvml():
+    """No GPU / no NVML here: the helper must return None and leave the affinity alone."""
+    import os
+    from taco_b200 import dist as tdist
+    before = os.sched_getaffinity(0)
+    cpus = tdist.bind_to_gpu_numa(0)
+    assert cpus is None or cpus <= before
+    if cpus is None:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
