@@ -13,7 +13,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum", "sm__inst_executed.avg.per_cycle_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fma", "sm__inst_executed_pipe_alu", "sm__inst_executed_pipe_xu", "sm__inst_executed_pipe_lsu",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__pipe_fmaheavy", "sm__pipe_fmalite", "sm__pipe_xu_cycles_active",
+        "sm__pipe_fmaheavy", "sm__pipe_fmalite", "sm__pipe_xu_cycles_active", "sm__pipe_tensor_cycles_active", "sm__ops_path_tensor_src_bf16_dst_fp32", "sm__inst_executed_pipe_tmem", "sass__inst_executed_local",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
         "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum", "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum",
         "smsp__sass_thread_inst_executed_op_fp32_pred_on.sum", "lts__t_bytes.sum", "l1tex__t_bytes.sum", "lts__t_sector_hit_rate.pct",
