@@ -239,6 +239,67 @@ def critic(ns):
     np.savez(os.path.join(OUT, "critic.npz"), **{k: np.asarray(t) for k, t in out.items()})
 
 
+def ppo_update(ns):
+    """PPO.update (ppo_asymmetry.py:137-258) run from the reference's own class on a small fixed buffer: the PPO object is built
+    without __init__ (which needs an env and TensorBoard) and given exactly the attributes update() reads; the agent is the
+    reference's PPO_ActorCritic (MLP actor, LSTM critic encoder); minibatch indices are fixed.  Two cases: plain, and with the
+    spectral projection after every optimiser step."""
+    import io, contextlib, types
+    import torch.nn as nn
+    out = {}
+    H, N, mb = 6, 16, 3
+    for tag, use_lip in (("plain", False), ("lip", True)):
+        torch.manual_seed(900)
+        para = {"actor_critic_mlp_dict": {"actor_input_dim": 26, "actor_output_dim": 4, "critic_input_dim": 26 * 5, "critic_output_dim": 1,
+                                          "actor_hidden_sizes": [32, 24], "critic_hidden_sizes": [20], "activation": nn.ReLU},
+                "use_actor_encoder": False, "use_critic_encoder": True, "share_encoder": False, "critic_encoder_type": "LSTM",
+                "critic_encoder_dict": {"encoder_type": "LSTM", "input_size": 26, "output_size": 16, "num_layers": 1, "bidirectional": False}}
+        with contextlib.redirect_stdout(io.StringIO()):
+            agent = ns.nets.PPO_ActorCritic(para)
+        with torch.no_grad():                                   # gains that make the projection bite on some layers only
+            for i, m in enumerate(mm for mm in agent.actor_mlp.layers if isinstance(mm, nn.Linear)):
+                m.weight.mul_(1.0 + 0.6 * i)
+        for k, v in agent.state_dict().items():
+            out[f"{tag}_init__{k}"] = v.detach().clone()
+        g = torch.Generator().manual_seed(901)
+        buf = types.SimpleNamespace(
+            obs_buf=torch.randn(H, N, 1, 26, generator=g) * 0.7, states_buf=torch.randn(H, N, 5, 26, generator=g) * 0.7,
+            act_buf=torch.randn(H, N, 4, generator=g).clamp(-1.5, 1.5), value_buf=torch.randn(H, N, 1, generator=g) * 0.3,
+            ret_buf=torch.randn(H, N, 1, generator=g) * 0.5, done_buf=torch.zeros(H, N, 1), logp_buf=torch.randn(H, N, 1, generator=g) * 0.3 - 4.0,
+            adv_buf=torch.randn(H, N, 1, generator=g), mu_buf=torch.zeros(H, N, 4), sigma_buf=torch.zeros(H, N, 4))
+        with torch.no_grad():                                   # old log-probs of the initial policy + noise, so ratios stay near 1
+            lp, _, _, _, _ = agent.evaluate(buf.obs_buf.view(-1, 1, 26), buf.states_buf.view(-1, 5, 26), buf.act_buf.view(-1, 4))
+            buf.logp_buf = (lp + 0.02 * torch.randn(lp.shape, generator=g)).view(H, N, 1)
+        idx = torch.randperm(H * N, generator=g).reshape(mb, -1).tolist()
+        buf.batch_idx_generator = lambda: idx
+        ppo = object.__new__(ns.ppo.PPO)
+        cfg = dict(clip=0.2, target_kl=0.5, max_grad=0.5, use_clipped_value_loss=False, epochs=40, train_iters=2, lr=1e-3, pi_coef=1.0, vf_coef=0.5,
+                   ent_coef=0.01, learning_rate_schedule=True, lr_ratio=0.3, lr_lp_index=0.7, lr_epoch_index=30, use_lipschitz=use_lip,
+                   lipschitz_para=2.0, lipschitz_schedule=True, lip_ratio=[1.0, 0.3], lip_lp_index=[0.3, 0.7], lip_epoch_index=[5, 30],
+                   difficulty_schedule=True, diff_value=[0.1, 1.0], diff_lp_index=[0.3, 0.7], diff_epoch_index=[5, 30])
+        for k, v in cfg.items():
+            setattr(ppo, k, v)
+        ppo.agent, ppo.replay_buffer, ppo.env = agent, buf, types.SimpleNamespace(difficulty=0.0)
+        ppo.optimizer = torch.optim.Adam(filter(lambda p: p.requires_grad, agent.parameters()), lr=cfg["lr"], eps=1e-5)
+        ppo.optim_step = 0
+        logged = {}
+        ppo.writer = types.SimpleNamespace(add_scalar=lambda name, val, step: logged.__setitem__(name, float(val)))
+        epoch = 12
+        with contextlib.redirect_stdout(io.StringIO()):
+            ppo.update(epoch)
+        for k, v in agent.state_dict().items():
+            out[f"{tag}_final__{k}"] = v.detach().clone()
+        for k in ("obs_buf", "states_buf", "act_buf", "value_buf", "ret_buf", "logp_buf", "adv_buf"):
+            out[f"{tag}_buf__{k}"] = getattr(buf, k)
+        out[f"{tag}_idx"] = torch.tensor(idx)
+        out[f"{tag}_epoch"] = torch.tensor(epoch)
+        out[f"{tag}_optim_step"] = torch.tensor(ppo.optim_step)
+        out[f"{tag}_difficulty"] = torch.tensor(ppo.env.difficulty)
+        for name, val in logged.items():
+            out[f"{tag}_log__{name.split('/')[1].rstrip(':')}"] = torch.tensor(val)
+    np.savez(os.path.join(OUT, "ppo_update.npz"), **{k: np.asarray(t) for k, t in out.items()})
+
+
 def gae(ns):
     """PPOReplayBuffer.store / compute_returns_and_advantage (buffer_asymmetry.py:49-68,93-132) run from the reference's
     own class, with the time-out bootstrap of ppo_asymmetry.py:313-324 applied to the stored reward."""
@@ -276,6 +337,7 @@ def main():
     rewards(ns)
     actor(ns)
     critic(ns)
+    ppo_update(ns)
     gae(ns)
     print("golden vectors written to", OUT)
     for f in sorted(os.listdir(OUT)):

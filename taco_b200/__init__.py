@@ -7,6 +7,7 @@ from .config import make_cfg, TASK_MODES  # noqa: F401
 from .actor import ActorMLP, spectral_normalize_  # noqa: F401
 from .critic import CriticLSTM  # noqa: F401
 from .rollout import RolloutBuffer, collect_rollout  # noqa: F401
+from . import ppo  # noqa: F401
 from .fpv_vec_task import FpvVecTask, FpvPos, FpvRotate, FpvFlip, FpvMix, isaacgym_task_map, Box  # noqa: F401
 
 __all__ = ["make_cfg", "TASK_MODES", "FpvVecTask", "FpvPos", "FpvRotate", "FpvFlip", "FpvMix", "isaacgym_task_map", "Box", "ActorMLP", "spectral_normalize_", "CriticLSTM", "RolloutBuffer", "collect_rollout"]
