@@ -79,3 +79,54 @@ def test_product_does_not_import_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("oracle/", "").replace("oracle.philox", "").replace("oracle/philox.py", "").lower() or True
+
+
+# ---------------------------------------------------------------------------------------------- a plain-C consumer
+def _build_consumer(tmp_path):
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    lib_dir = os.path.join(ROOT, "taco_b200", "lib")
+    exe = str(tmp_path / "consumer")
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cabi", "consumer.c"),
+           "-L", lib_dir, "-ltaco_b200", f"-Wl,-rpath,{lib_dir}", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_header_is_plain_c_and_a_c_program_links(lib, tmp_path):
+    """include/taco_b200.h compiles as C99 with -Wall -Werror and a consumer without CUDA headers or torch links against the .so."""
+    assert os.path.exists(_build_consumer(tmp_path))
+
+
+@pytest.mark.gpu
+def test_c_consumer_reproduces_the_python_binding(tmp_path):
+    """tests/cabi/consumer.c steps a flip env through taco_env_step_host with malloc'ed buffers; FpvVecTask with the same
+    configuration, seed and action pattern must produce the same rewards, resets and time-outs."""
+    import re
+    import subprocess
+    import torch
+    import taco_b200
+    n, steps = 1000, 12
+    exe = _build_consumer(tmp_path)
+    r = subprocess.run([exe, str(n), str(steps)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"sum_rew=(\S+) n_reset=(\d+) n_tout=(\d+) stats_sum_rew=(\S+) stats_n_done=(\d+) stats_env_steps=(\d+)", r.stdout)
+    assert m, r.stdout
+    cfg = taco_b200.make_cfg("flip", n, random_voltage=False, random_rotor_speed=False, **{"env.clipActions": 1.0})
+    env = taco_b200.FpvVecTask(cfg, "cuda:0", "cuda:0", -1, True, seed=5)
+    i = torch.arange(n)                                  # the pattern is built on the CPU: torch's CUDA division by a scalar multiplies by the reciprocal
+    sum_rew, n_reset, n_tout = 0.0, 0, 0
+    for t in range(steps):
+        act = torch.stack([((i * 7 + t * 3) % 17).float() / 16.0 - 0.5, ((i * 5 + t) % 13).float() / 24.0 - 0.25,
+                           ((i * 3 + t * 2) % 11).float() / 20.0 - 0.25, ((i + t * 5) % 7).float() / 12.0 - 0.25], dim=1).contiguous().cuda()
+        _, rew, reset, extras = env.step(act)
+        sum_rew += float(rew.double().sum()); n_reset += int((reset != 0).sum()); n_tout += int(extras["time_outs"].sum())
+    assert int(m.group(2)) == n_reset and int(m.group(3)) == n_tout
+    assert float(m.group(1)) == pytest.approx(sum_rew, rel=1e-10)     # identical float32 rewards, summed in double in two orders
+    stats = env.stats().cpu()
+    assert float(m.group(4)) == pytest.approx(float(stats[0]), rel=1e-6) and int(m.group(5)) == int(stats[1]) and int(m.group(6)) == n * steps
+    env.close()
