@@ -31,6 +31,7 @@ constexpr int kMaxSeq = 8;             // len_states of the reference runs is 5 
 constexpr int kTcMaxLstmHidden = 64;   // the cell state lives in the 64 spare TMEM columns of the tile's A operand
 constexpr int kTcMaxIn = 30;           // features per frame (26) + two constant-1 bias columns, padded to 32 = 16 packed TMEM columns
 constexpr int kMaxMlpHidden = 3;       // s_bias rows: LSTM gates + up to 3 hidden layers
+constexpr int kRing = kSlots - 1;        // ring slots of the MLP weights; the last 64 KB slot holds the LSTM image for the whole kernel
 constexpr int kAColH = 0;              // A operand columns (packed bf16 pairs): h in [0, 32), x_t in [32, 48), zero pad [48, 64)
 constexpr int kAColX = 32;
 constexpr int kAColC = 64;              // cell state, fp32, one column per hidden unit (LSTM phase only)
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
     const uint32_t bar_empty = bar_full + 8 * kSlots;
     const uint32_t bar_a = bar_empty + 8 * kSlots;
     const uint32_t bar_d = bar_a + 16;
+    const uint32_t bar_lstm = bar_d + 16 + 8;                       // the resident LSTM weight image has landed (the word after bar_d holds the TMEM address)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 4);
     uint32_t* s_x = reinterpret_cast<uint32_t*>(sm + kTcSmemBytes - 1024);       // [2 tiles][128 rows][kXStride] staged state frames (bf16 pairs)
 
@@ -218,6 +220,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
     if (threadIdx.x == 0) {
         for (int s = 0; s < kSlots; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int t = 0; t < 2; ++t) { mbar_init(bar_a + 8 * t, (kEpiWarps / 2) * 32); mbar_init(bar_d + 8 * t, 1); }
+        mbar_init(bar_lstm, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(s_tmem), kTmemCols);
@@ -227,11 +230,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
     const uint32_t tmem0 = *s_tmem;
 
     if (warp == 0) {
-        // ===================== weight producer: per pair, per schedule step, per 128-row part: one ring slot
+        // ===================== weight producer.  The LSTM image (<= 64 KB: [W_hh | W_ih] for 4H <= 256 gate rows) is the same for
+        // every time step of every tile: it is loaded ONCE into the last 64 KB slot and stays there instead of being re-streamed five
+        // times per pair (5x less L2 -> SM traffic in the LSTM phase; time-neutral at the measured sizes).  The MLP layers
+        // stream through the remaining kRing slots: per pair, per layer, per 128-row part one slot.
+        {
+            const int n = p.layer[0].n;
+            const uint8_t* img = p.wimg + p.layer[0].img_off;
+            if (elect_one_sync()) {
+                mbar_arrive_expect_tx(bar_lstm, (uint32_t)n * 128u * 2u);
+                for (int h0 = 0, part = 0; h0 < n; h0 += kPartN, ++part)
+                    for (int c = 0; c < 2; ++c)
+                        bulk_g2s(s_ring + kRing * kSlotBytes + (part * 2 + c) * kChunkBytes, img + ((size_t)c * n + h0) * 128u,
+                                 (uint32_t)min(kPartN, n - h0) * 128u, bar_lstm);
+            }
+            __syncwarp();
+        }
         uint32_t slot = 0, phase = 0;
         for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-            for (int s = 0; s < n_sched; ++s) {
-                const int l = s < T ? 0 : s - T + 1;
+            for (int l = 1; l <= p.n_hidden + 1; ++l) {
                 const int n = p.layer[l].n, kch = p.layer[l].kchunks;
                 const uint8_t* img = p.wimg + p.layer[l].img_off;
                 for (int h0 = 0; h0 < n; h0 += kPartN) {
@@ -243,7 +260,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
                             bulk_g2s(s_ring + slot * kSlotBytes + c * kChunkBytes, img + ((size_t)c * n + h0) * 128u, bytes, bar_full + 8 * slot);
                     }
                     __syncwarp();
-                    if (++slot == kSlots) { slot = 0; phase ^= 1u; }
+                    if (++slot == kRing) { slot = 0; phase ^= 1u; }
                 }
             }
         }
@@ -252,6 +269,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
         uint32_t slot = 0, phase = 0, a_phase = 0;
         int dbg_n = lane == 0 ? 0 : kDbgCap;
         const uint64_t bdesc0 = umma_desc_sw128(s_ring);
+        mbar_wait(bar_lstm, 0u);                                       // the resident LSTM image
         for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
             const int nt = (2 * pair + 1 < p.num_tiles) ? 2 : 1;
             for (int s = 0; s < n_sched; ++s) {
@@ -259,12 +277,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
                 const int n = p.layer[l].n, kch = p.layer[l].kchunks;
                 for (int h0 = 0; h0 < n; h0 += kPartN) {
                     const uint32_t idesc = umma_idesc_bf16(kTileM, min(kPartN, n - h0));
-                    const uint64_t bdesc = bdesc0 + (uint64_t)(slot * (kSlotBytes >> 4));
+                    const bool ring = l != 0;                              // LSTM parts sit in the resident slot
+                    const uint64_t bdesc = ring ? bdesc0 + (uint64_t)(slot * (kSlotBytes >> 4))
+                                                : bdesc0 + (uint64_t)((kRing * kSlotBytes + (h0 / kPartN) * 2 * kChunkBytes) >> 4);
 #pragma unroll
                     for (int t = 0; t < 2; ++t) {
                         if (t < nt) {
                             mbar_wait(bar_a + 8 * t, (a_phase >> t) & 1u); a_phase ^= (1u << t);
-                            if (t == 0) mbar_wait(bar_full + 8 * slot, phase);
+                            if (t == 0 && ring) mbar_wait(bar_full + 8 * slot, phase);
                             tc_fence_after();
                             TACO_DBG(0, dbg_n, 0x20 | t);
                             if (elect_one_sync()) {
@@ -278,14 +298,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
                                     umma_bf16_ts(d_addr, a_c + 16u, b_c + 4u, idesc, 1u);
                                     umma_bf16_ts(d_addr, a_c + 24u, b_c + 6u, idesc, 1u);
                                 }
-                                if (t == nt - 1) umma_commit(bar_empty + 8 * slot);
+                                if (t == nt - 1 && ring) umma_commit(bar_empty + 8 * slot);
                                 umma_commit(bar_d + 8 * t);
                             }
                             __syncwarp();
                             TACO_DBG(0, dbg_n, 0x30 | t);
                         }
                     }
-                    if (++slot == kSlots) { slot = 0; phase ^= 1u; }
+                    if (ring && ++slot == kRing) { slot = 0; phase ^= 1u; }
                 }
             }
         }
