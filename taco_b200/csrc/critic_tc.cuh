@@ -154,7 +154,7 @@ __device__ __forceinline__ void frame_load(const float* states, long long tile_r
         const float2* src = reinterpret_cast<const float2*>(base + (size_t)w.row * row_floats) + w.j;
         raw[k] = make_float2(0.f, 0.f);
         if (w.row < rows_left) {
-            raw[k] = __ldg(src);
+            raw[k] = __ldcg(src);               // read once: no point allocating in the ~10 KB of L1 left next to 217 KB of shared memory
             if (ts + 1 < T && (k & 1) == 0) prefetch_l2(reinterpret_cast<const float*>(src) + in_dim);
         }
         w.next();
