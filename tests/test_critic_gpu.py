@@ -90,6 +90,37 @@ def test_tensor_core_path(hid, mlp_hidden, n):
     c.close()
 
 
+@pytest.mark.parametrize("in_dim,seq_len,hid", [(26, 1, 64), (26, 8, 32), (30, 5, 64), (2, 3, 16), (26, 5, 64)])
+def test_tensor_core_path_other_sequence_shapes(in_dim, seq_len, hid):
+    """Edge shapes of the tcgen05 path: a single frame (no x restaging), the longest supported history, the widest / narrowest
+    even input (the two bias columns sit right after the features), against the FP32 kernel and the bf16 emulation."""
+    from taco_b200 import CriticLSTM
+    from oracle import critic as oc
+    lstm, w, b = _random_critic(in_dim, hid, [64], seed=in_dim * 100 + seq_len)
+    n = 777
+    states = torch.randn(n, seq_len, in_dim, generator=torch.Generator().manual_seed(in_dim + seq_len)) * 1.2
+    c = CriticLSTM(in_dim, seq_len, hid, [64])
+    assert c.tensor_cores_available
+    c.load(lstm, w, b)
+    v_tc = c.forward(states.cuda(), tensor_cores=True).cpu()
+    assert (v_tc - oc.critic_forward_bf16(states, lstm, w, b)).abs().max().item() <= 1.5e-2
+    torch.testing.assert_close(c.forward(states.cuda()).cpu(), oc.critic_forward(states, lstm, w, b), rtol=0, atol=5e-6)
+    c.close()
+
+
+def test_fp32_path_deep_lstm_vs_oracle():
+    """Three stacked LSTM layers, odd widths, a sequence of 7 frames of 11 features: only the FP32 kernel takes this shape."""
+    from taco_b200 import CriticLSTM
+    from oracle import critic as oc
+    lstm, w, b = _random_critic(11, 37, [19, 5], seed=77, nl=3)
+    states = torch.randn(203, 7, 11, generator=torch.Generator().manual_seed(5))
+    c = CriticLSTM(11, 7, 37, [19, 5], lstm_layers=3)
+    assert not c.tensor_cores_available
+    c.load(lstm, w, b)
+    torch.testing.assert_close(c.forward(states.cuda()).cpu(), oc.critic_forward(states, lstm, w, b), rtol=0, atol=5e-6)
+    c.close()
+
+
 def test_tensor_core_path_rejects_unsupported_shapes():
     from taco_b200 import CriticLSTM
     c = CriticLSTM(26, 5, 128, [256])                      # LSTM width 128: the cell state would not fit the register file

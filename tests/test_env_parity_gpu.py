@@ -186,6 +186,32 @@ def test_host_buffer_entry_point_matches_device_path(n, mode, monkeypatch):
     a_env.close(); b_env.close()
 
 
+def test_host_buffer_entry_point_without_result_buffers():
+    """Every result pointer of taco_env_step_host may be NULL (actions only): the step still runs and the device buffers hold the
+    results -- in mapped and in copy mode."""
+    import os
+    import taco_b200
+    from taco_b200 import make_cfg
+    n = 5000
+    a_env = taco_b200.FpvVecTask(make_cfg("mix", n, domain_randomization=True), "cuda:0", "cuda:0", -1, True, seed=9)
+    b_env = taco_b200.FpvVecTask(make_cfg("mix", n, domain_randomization=True), "cuda:0", "cuda:0", -1, True, seed=9)
+    h_rew = torch.empty(n).pin_memory()
+    try:
+        for t in range(6):
+            act = a_env.random_actions(t)
+            o, r, x, e = a_env.step(act)
+            os.environ["TACO_HOST_MODE"] = "copy" if t % 2 else "mapped"
+            if t < 3:
+                b_env.step_host(act.cpu().pin_memory())
+            else:
+                b_env.step_host(act.cpu().pin_memory(), h_rew)                     # one result buffer only
+                assert torch.equal(r.cpu(), h_rew)
+            assert torch.equal(r, b_env.rew_buf) and torch.equal(x, b_env.reset_buf) and torch.equal(o["states"], b_env.states_buf)
+    finally:
+        os.environ.pop("TACO_HOST_MODE", None)
+    a_env.close(); b_env.close()
+
+
 def test_api_errors():
     import taco_b200
     from taco_b200 import make_cfg
