@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """PPO training on the native rollout path -- the loop of the reference's ``train_fpv_asymmetry_ppo.py`` / ``PPO.run``
 (IsaacGymEnvs/train/train_fpv_asymmetry_ppo.py:363-538, IsaacGymEnvs/algorithms/ppo_asymmetry.py:260-342) with
-  rollout  = collect_rollout: actor kernel -> critic kernel -> fused env step, zero-copy into the RolloutBuffer, GAE on the device
+  rollout  = GraphedRollout: actor kernel -> critic kernel -> fused env step, zero-copy into the RolloutBuffer, GAE on the device,
+             the whole horizon replayed as ONE CUDA graph (--no-graph: the eager collect_rollout loop)
   update   = taco_b200.ppo.ppo_update (PyTorch autograd; spectral projection on the device; gradients averaged over ranks)
 
     python examples/train_fpv_ppo.py --task pos --num-envs 4096 --epochs 60
@@ -32,6 +33,7 @@ def main():
     ap.add_argument("--lstm-hidden", type=int, default=64)
     ap.add_argument("--lipschitz", type=float, default=4.0, help="README training command: --lipschitz_para=4; 0 disables")
     ap.add_argument("--tensor-cores", default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--no-graph", action="store_true", help="collect rollouts with the eager loop instead of one CUDA-graph replay per rollout")
     ap.add_argument("--seed", type=int, default=42)
     args = ap.parse_args()
 
@@ -64,10 +66,19 @@ def main():
     # the tensor-core kernels are also the fast path at small env counts (latency of one tile chain: ~12 us actor, ~36 us critic)
     tc = args.tensor_cores != "off" and actor.tensor_cores_available and critic.tensor_cores_available
     env.reset()
+    graphed = None
     for epoch in range(args.epochs):
-        t0 = time.perf_counter()
+        ts = time.perf_counter()
         sync_rollout_nets(agent, actor, critic)
-        stats = taco_b200.collect_rollout(env, actor, buf, critic, seed=args.seed + epoch, tensor_cores=tc)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if args.no_graph:
+            stats = taco_b200.collect_rollout(env, actor, buf, critic, seed=args.seed, tensor_cores=tc)
+        elif graphed is None:                       # the first rollout runs eagerly inside the constructor, then the loop is one graph
+            graphed = taco_b200.GraphedRollout(env, actor, buf, critic, seed=args.seed, tensor_cores=tc)
+            stats = graphed.first_stats
+        else:
+            stats = graphed.run()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         n_s = n * args.horizon
@@ -80,9 +91,11 @@ def main():
             print(json.dumps({"epoch": epoch, "mean_reward": s["mean_reward"], "episode_return": s["mean_episode_return"],
                               "episode_length": s["mean_episode_length"], "difficulty": out["difficulty"], "lipschitz": out["lipschitz_para"],
                               "pg_loss": out["policy_gradient_loss"], "value_loss": out["value_loss"], "kl": out["approx_kl"],
-                              "optim_steps": out["optim_steps"], "rollout_s": t1 - t0, "update_s": t2 - t1,
-                              "rollout_env_steps_per_s": world * n_s / (t1 - t0), "loop_env_steps_per_s": world * n_s / (t2 - t0),
+                              "optim_steps": out["optim_steps"], "sync_s": t0 - ts, "rollout_s": t1 - t0, "update_s": t2 - t1,
+                              "rollout_env_steps_per_s": world * n_s / (t1 - t0), "loop_env_steps_per_s": world * n_s / (t2 - ts),
                               "tensor_cores": bool(tc), "world": world}), flush=True)
+    if graphed is not None:
+        graphed.close()
     env.close(); actor.close(); critic.close()
     if world > 1:
         dist.destroy_process_group()

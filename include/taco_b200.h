@@ -118,6 +118,17 @@ int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host,
 /* -- VecTask.reset (vec_task_asymmetry.py:352-361) does not simulate; this additionally marks every env for
  * reset on the next step and zeroes the observation history, i.e. restores the freshly-constructed state. */
 int taco_env_reset_all(TacoEnv* env, void* stream);
+/* -- CUDA-graph support.  Every launch of the step kernel carries the RL step index (Philox counter word, time slot of the
+ * pending-action ring) as a kernel parameter, so a captured launch would replay with a stale index.  Between
+ * taco_env_graph_begin and taco_env_graph_end the index of a launch is *counter (one device word, initialised to the current
+ * step index) + the number of steps taken since graph_begin: a graph captured over a whole rollout -- rewind, H x (actor, critic,
+ * step), taco_env_graph_advance(H) as its last node -- replays correctly any number of times.  taco_env_graph_end reads the counter
+ * back (synchronises) and returns to host-side counting.  taco_env_step_counter reports the device word (NULL outside graph mode)
+ * for other kernels that need the same index (taco_actor_act_counter) and the host's view of the step index. */
+int taco_env_graph_begin(TacoEnv* env, void* stream);
+int taco_env_graph_advance(TacoEnv* env, uint32_t steps, void* stream);
+int taco_env_graph_end(TacoEnv* env, void* stream);
+int taco_env_step_counter(TacoEnv* env, uint32_t** counter_dev, uint32_t* step_index_host);
 /* -- zero-copy rollout storage: what PPOReplayBuffer.store copies every step (IsaacGymEnvs/algorithms/buffer_asymmetry.py:49-68:
  * obs_buf (H,N,Lo,26), states_buf (H,N,Ls,26), rew_buf, done_buf) the step kernel writes in place.  obs_ring / states_ring
  * are caller-owned contiguous float32 device buffers of `slots` = horizon + 1 slots of (num_envs, len, 26); with a ring
@@ -162,7 +173,8 @@ int taco_actor_destroy(TacoActor* actor);
 /* weights/biases: host float32, row-major (out,in) per layer like nn.Linear.  With lipschitz_const > 0 every weight
  * matrix whose largest singular value sigma exceeds it is scaled by lipschitz_const / sigma on the device (power
  * iteration in double precision) -- the reference does this after each optimiser step, so calling it once per update
- * gives rollouts pre-normalised weights.  Synchronises the stream (the host buffers are free on return). */
+ * gives rollouts pre-normalised weights; lipschitz_const = 0 only measures the norms (taco_actor_sigmas), a negative value skips
+ * the measurement too.  Synchronises the stream (the host buffers are free on return). */
 int taco_actor_load(TacoActor* actor, const float* const* weights_host, const float* const* biases_host,
                     float lipschitz_const, void* stream);
 /* largest singular value of every layer as measured by the last taco_actor_load (before scaling): n_layers doubles */
@@ -211,6 +223,12 @@ int taco_critic_tc_available(TacoCritic* critic);
  * Asynchronous on `stream`. */
 int taco_critic_forward(TacoCritic* critic, const float* states_dev, float* value_dev, int32_t n, int32_t use_tensor_cores,
                         void* stream);
+
+/* taco_actor_act whose Philox step index is step_index + *step_base_dev (step_base_dev: device word, e.g. the env's counter from
+ * taco_env_step_counter; NULL = plain taco_actor_act): capturable in a CUDA graph together with the env steps. */
+int taco_actor_act_counter(TacoActor* actor, const float* obs_dev, int32_t n, const float* log_std_host, int64_t env_offset,
+                           uint64_t seed, uint32_t step_index, const uint32_t* step_base_dev, float* mean_dev, float* action_dev,
+                           float* clipped_dev, float* logp_dev, int32_t use_tensor_cores, void* stream);
 
 /* -- rollout-buffer post-processing: PPOReplayBuffer.compute_returns_and_advantage
  * (IsaacGymEnvs/algorithms/buffer_asymmetry.py:93-132) and the time-out bootstrap PPO applies to the reward it stores

@@ -65,6 +65,11 @@ def lib():
         "taco_env_step": (C.c_int, [vp, vp, vp]),
         "taco_env_step_host": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "taco_env_reset_all": (C.c_int, [vp, vp]),
+        "taco_env_graph_begin": (C.c_int, [vp, vp]),
+        "taco_env_graph_advance": (C.c_int, [vp, u32, vp]),
+        "taco_env_graph_end": (C.c_int, [vp, vp]),
+        "taco_env_step_counter": (C.c_int, [vp, C.POINTER(vp), C.POINTER(u32)]),
+        "taco_actor_act_counter": (C.c_int, [vp, vp, i32, vp, C.c_int64, u64, u32, vp, vp, vp, vp, vp, i32, vp]),
         "taco_env_attach_rollout": (C.c_int, [vp, vp, vp, i32, vp, vp, vp, vp]),
         "taco_env_rewind_rollout": (C.c_int, [vp, vp]),
         "taco_env_detach_rollout": (C.c_int, [vp, vp]),

@@ -96,10 +96,11 @@ class ActorMLP:
                                                  1 if tensor_cores else 0, self._stream()), "taco_actor_forward")
         return out
 
-    def act(self, obs, step_index, seed=0, env_offset=0, tensor_cores=False, out=None):
+    def act(self, obs, step_index, seed=0, env_offset=0, tensor_cores=False, out=None, step_base=0):
         """Returns (action, clipped_action, log_p, mean): the sample of nets_asymmetry.py:336-346 with Philox noise and
         the clip of ppo_asymmetry.py:310.  ``out`` = (action, clipped, log_p, mean) writes into caller tensors (e.g. rows of
-        a RolloutBuffer): contiguous float32 (N,4) / (N,4) / (N[,1]) / (N,4) on the actor's device."""
+        a RolloutBuffer): contiguous float32 (N,4) / (N,4) / (N[,1]) / (N,4) on the actor's device.  ``step_base``: device address of
+        a uint32 added to ``step_index`` on the device (the env's graph-mode counter, ``FpvVecTask.step_counter()[0]``)."""
         obs = self._check_obs(obs)
         n, k = obs.size(0), self.sizes[-1]
         if out is None:
@@ -112,10 +113,11 @@ class ActorMLP:
             for t, cnt in ((action, n * k), (clipped, n * k), (logp, n), (mean, n * k)):
                 if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != cnt or t.device.type != "cuda":
                     raise ValueError("act(out=...): tensors must be contiguous float32 CUDA tensors of (N,4), (N,4), (N,), (N,4)")
-        _capi.check(self._lib.taco_actor_act(self._h, C.c_void_p(obs.data_ptr()), n, self.log_std.ctypes.data_as(C.c_void_p),
-                                             int(env_offset), int(seed) & 0xFFFFFFFFFFFFFFFF, int(step_index) & 0xFFFFFFFF,
-                                             C.c_void_p(mean.data_ptr()), C.c_void_p(action.data_ptr()), C.c_void_p(clipped.data_ptr()),
-                                             C.c_void_p(logp.data_ptr()), 1 if tensor_cores else 0, self._stream()), "taco_actor_act")
+        _capi.check(self._lib.taco_actor_act_counter(self._h, C.c_void_p(obs.data_ptr()), n, self.log_std.ctypes.data_as(C.c_void_p),
+                                                     int(env_offset), int(seed) & 0xFFFFFFFFFFFFFFFF, int(step_index) & 0xFFFFFFFF,
+                                                     C.c_void_p(int(step_base)), C.c_void_p(mean.data_ptr()), C.c_void_p(action.data_ptr()),
+                                                     C.c_void_p(clipped.data_ptr()), C.c_void_p(logp.data_ptr()), 1 if tensor_cores else 0,
+                                                     self._stream()), "taco_actor_act")
         return action, clipped, logp, mean
 
     def close(self):

@@ -60,6 +60,7 @@ struct SampleParams {    // PPO_ActorCritic.act sampling (nets_asymmetry.py:336-
     float logp_const;    // -sum(log std) - out/2 * log(2 pi)
     long long env_offset;
     uint32_t seed_lo, seed_hi, step_index;
+    const uint32_t* step_base;   // device word added to step_index (null: none), see taco_actor_act_counter
 };
 
 struct TcParams {
@@ -209,7 +210,8 @@ __device__ __forceinline__ void actor_tail(const float* pre, int out_dim, long l
         for (int o = 0; o < out_dim; ++o) mean[row * out_dim + o] = mu[o];
     }
     if (sp.action) {
-        const uint4 r = philox4x32_10((uint32_t)(sp.env_offset + row), sp.step_index, 0, STREAM_ACTOR, sp.seed_lo, sp.seed_hi);
+        const uint4 r = philox4x32_10((uint32_t)(sp.env_offset + row), sp.step_index + (sp.step_base ? __ldg(sp.step_base) : 0u), 0, STREAM_ACTOR,
+                                      sp.seed_lo, sp.seed_hi);
         float z[4];
         box_muller(r.x, r.y, z[0], z[1]);
         box_muller(r.z, r.w, z[2], z[3]);

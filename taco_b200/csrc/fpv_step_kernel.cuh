@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
         act.z = clampf(act.z, -ca, ca); act.w = clampf(act.w, -ca, ca);
 
         const uint32_t g = (uint32_t)(p.env_offset + i);        // global env id = Philox counter word 0
-        const uint32_t k0 = p.seed_lo, k1 = p.seed_hi, t_rl = p.step_index;
+        const uint32_t k0 = p.seed_lo, k1 = p.seed_hi, t_rl = p.step_index + (p.step_base ? __ldg(p.step_base) : 0u);
         int task = TASK;
         const bool is_mix = (TASK == TACO_TASK_MIX);
         if (is_mix) {

@@ -23,7 +23,8 @@ struct StepParams {
     long long env_offset;
     long long mix_n1, mix_n2;      // global task-group boundaries (fpv_asymmetry.py:924-926)
     int task_mode, len_obs, len_states, max_len, cfi, substeps, delay_time;
-    uint32_t flags, seed_lo, seed_hi, step_index;
+    uint32_t flags, seed_lo, seed_hi, step_index;   // step_index: absolute RL step, or the offset to *step_base (graph mode)
+    const uint32_t* step_base;     // device word added to step_index (null outside graph mode): a captured launch stays valid on replay
     float dt, inv_dt, h, half_h, half_h2, c_sin3, c_sin5, c_cos4, inv_mass, difficulty, clip_actions;
     // host-precomputed (double -> float) bounds of the difficulty-dependent uniform draws
     float flip_xy_rng, flip_xy_lo, flip_lin_rng, flip_lin_lo, dr_rng, dr_lo, tau_rng, tau_lo, noise_rng, noise_lo;

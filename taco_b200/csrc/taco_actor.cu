@@ -320,7 +320,7 @@ int taco_actor_load(TacoActor* a, const float* const* weights_host, const float*
         ACT_CUDA(cudaMemcpyAsync(a->b_f32 + a->b_off[l], biases_host[l], (size_t)out * sizeof(float), cudaMemcpyHostToDevice, s));
     }
     // spectral projection of every weight matrix (ppo_asymmetry.py:398-404); also records sigma when lipschitz_const <= 0
-    for (int l = 0; l < a->n_layers; ++l) {
+    for (int l = 0; l < a->n_layers && lipschitz_const >= 0.0f; ++l) {        // negative: weights are known to be projected, skip the measurement
         const int in = a->sizes[l], out = a->sizes[l + 1];
         spectral_norm_kernel<<<1, kSnThreads, (size_t)(in + out) * sizeof(double), s>>>(a->w_f32 + a->w_off[l], out, in, lipschitz_const,
                                                                                          a->sigma + l, 20000, 1e-12);
@@ -384,9 +384,9 @@ int taco_actor_forward(TacoActor* a, const float* obs_dev, float* mean_dev, int3
     return actor_run(a, obs_dev, mean_dev, n, use_tensor_cores, sp, stream);
 }
 
-int taco_actor_act(TacoActor* a, const float* obs_dev, int32_t n, const float* log_std_host, int64_t env_offset, uint64_t seed,
-                   uint32_t step_index, float* mean_dev, float* action_dev, float* clipped_dev, float* logp_dev, int32_t use_tensor_cores,
-                   void* stream) {
+int taco_actor_act_counter(TacoActor* a, const float* obs_dev, int32_t n, const float* log_std_host, int64_t env_offset, uint64_t seed,
+                           uint32_t step_index, const uint32_t* step_base_dev, float* mean_dev, float* action_dev, float* clipped_dev,
+                           float* logp_dev, int32_t use_tensor_cores, void* stream) {
     if (!a || !log_std_host || !action_dev) return afail(TACO_E_INVALID, "taco_actor_act: null argument");
     SampleParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -403,7 +403,15 @@ int taco_actor_act(TacoActor* a, const float* obs_dev, int32_t n, const float* l
     sp.env_offset = env_offset;
     sp.seed_lo = (uint32_t)(seed & 0xFFFFFFFFull); sp.seed_hi = (uint32_t)(seed >> 32);
     sp.step_index = step_index;
+    sp.step_base = step_base_dev;
     return actor_run(a, obs_dev, mean_dev, n, use_tensor_cores, sp, stream);
+}
+
+int taco_actor_act(TacoActor* a, const float* obs_dev, int32_t n, const float* log_std_host, int64_t env_offset, uint64_t seed,
+                   uint32_t step_index, float* mean_dev, float* action_dev, float* clipped_dev, float* logp_dev, int32_t use_tensor_cores,
+                   void* stream) {
+    return taco_actor_act_counter(a, obs_dev, n, log_std_host, env_offset, seed, step_index, nullptr, mean_dev, action_dev, clipped_dev, logp_dev,
+                                  use_tensor_cores, stream);
 }
 
 }  // extern "C"

@@ -58,6 +58,11 @@ struct TacoEnv {
     float* export_stage = nullptr;     // n * TACO_STATE_WORDS floats, device
     float4* dbg_delay = nullptr;
     uint32_t step_index = 0;
+    // graph mode (taco_env_graph_begin .. _end): the step index of a launch = *step_counter (device) + its offset since
+    // graph_begin, so a CUDA graph captured over a rollout replays with fresh Philox counters / queue time slots
+    uint32_t* step_counter = nullptr;   // device, one word
+    bool graph_mode = false;
+    uint32_t graph_origin = 0;
     // host-buffer pipeline (taco_env_step_host): copy-in / kernel / copy-out of successive env chunks overlap
     static constexpr int kMaxChunks = 16;
     static constexpr int kKernelStreams = 3;     // chunk kernels rotate over these so that a chunk's tail wave overlaps the next chunk
@@ -355,6 +360,7 @@ int taco_env_destroy(TacoEnv* env) {
     }
     if (env->export_stage) cudaFree(env->export_stage);
     if (env->arena) cudaFree(env->arena);
+    if (env->step_counter) cudaFree(env->step_counter);
     delete env;
     return TACO_OK;
 }
@@ -402,6 +408,15 @@ static void advance_history(TacoEnv* env) {
     env->step_index += 1;
 }
 
+// the step index of the next launch: absolute, or an offset to the device counter in graph mode
+static void bind_step_index(TacoEnv* env) {
+    StepParams& p = env->p;
+    if (env->graph_mode) { p.step_base = env->step_counter; p.step_index = env->step_index - env->graph_origin; }
+    else { p.step_base = nullptr; p.step_index = env->step_index; }
+}
+
+__global__ void step_counter_kernel(uint32_t* c, uint32_t value, int add) { *c = add ? *c + value : value; }
+
 int taco_env_step(TacoEnv* env, const float* actions_dev, void* stream) {
     if (!env || !actions_dev) return fail(TACO_E_INVALID, "taco_env_step: null argument");
     if (((uintptr_t)actions_dev & 15u) != 0) return fail(TACO_E_INVALID, "actions must be 16-byte aligned (contiguous (N,4) float32)");
@@ -410,7 +425,7 @@ int taco_env_step(TacoEnv* env, const float* actions_dev, void* stream) {
     const int rc = bind_history(env);
     if (rc != TACO_OK) return rc;
     p.actions = (const float4*)actions_dev;
-    p.step_index = env->step_index;
+    bind_step_index(env);
     if (env->cfg.flags & TACO_F_STRICT_FP) launch_fpv_step_strict(p, (cudaStream_t)stream);
     else launch_fpv_step_fast(p, (cudaStream_t)stream);
     TACO_CUDA(cudaGetLastError());
@@ -468,7 +483,7 @@ int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host,
             if (rc != TACO_OK) return rc;
             p.actions = (const float4*)d_act;
             p.host_rew = (float*)d_rew; p.host_reset = (long long*)d_reset; p.host_tout = (uint8_t*)d_tout;
-            p.step_index = env->step_index;
+            bind_step_index(env);
             if (env->cfg.flags & TACO_F_STRICT_FP) launch_fpv_step_strict(p, s); else launch_fpv_step_fast(p, s);
             const cudaError_t le = cudaGetLastError();
             p.host_rew = nullptr; p.host_reset = nullptr; p.host_tout = nullptr;
@@ -497,7 +512,7 @@ int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host,
     rc = bind_history(env);
     if (rc != TACO_OK) return rc;
     p.actions = (const float4*)env->actions_stage;
-    p.step_index = env->step_index;
+    bind_step_index(env);
     const bool strict = (env->cfg.flags & TACO_F_STRICT_FP) != 0;
     const bool want_out = rew_host || reset_host || time_outs_host;
     TACO_CUDA(cudaEventRecord(env->ev_begin, s));                    // work already queued on the caller's stream comes first
@@ -533,6 +548,44 @@ int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host,
         TACO_CUDA(cudaStreamWaitEvent(s, env->ev_end, 0));
     }
     TACO_CUDA(cudaStreamSynchronize(s));
+    return TACO_OK;
+}
+
+int taco_env_graph_begin(TacoEnv* env, void* stream) {
+    if (!env) return fail(TACO_E_INVALID, "taco_env_graph_begin: null argument");
+    DeviceGuard guard(env->device);
+    if (!env->step_counter) TACO_CUDA(cudaMalloc(&env->step_counter, sizeof(uint32_t)));
+    step_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->step_counter, env->step_index, 0);
+    TACO_CUDA(cudaGetLastError());
+    env->graph_mode = true;
+    env->graph_origin = env->step_index;
+    return TACO_OK;
+}
+
+int taco_env_graph_advance(TacoEnv* env, uint32_t steps, void* stream) {
+    if (!env || !env->graph_mode) return fail(TACO_E_INVALID, "taco_env_graph_advance: call taco_env_graph_begin first");
+    DeviceGuard guard(env->device);
+    step_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->step_counter, steps, 1);
+    TACO_CUDA(cudaGetLastError());
+    return TACO_OK;
+}
+
+int taco_env_graph_end(TacoEnv* env, void* stream) {
+    if (!env) return fail(TACO_E_INVALID, "taco_env_graph_end: null argument");
+    if (!env->graph_mode) return TACO_OK;
+    DeviceGuard guard(env->device);
+    uint32_t v = 0;
+    TACO_CUDA(cudaMemcpyAsync(&v, env->step_counter, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    TACO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    env->step_index = v;
+    env->graph_mode = false;
+    return TACO_OK;
+}
+
+int taco_env_step_counter(TacoEnv* env, uint32_t** counter_dev, uint32_t* step_index_host) {
+    if (!env) return fail(TACO_E_INVALID, "taco_env_step_counter: null argument");
+    if (counter_dev) *counter_dev = env->graph_mode ? env->step_counter : nullptr;
+    if (step_index_host) *step_index_host = env->step_index;
     return TACO_OK;
 }
 
@@ -602,6 +655,7 @@ int taco_env_reset_all(TacoEnv* env, void* stream) {
     init_state_kernel<<<(env->n_pad + 255) / 256, 256, 0, s>>>(env->p);
     TACO_CUDA(cudaGetLastError());
     env->step_index = 0;
+    env->graph_mode = false;                                         // host-side counting again; taco_env_graph_begin re-arms
     return TACO_OK;
 }
 

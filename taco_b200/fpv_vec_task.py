@@ -245,6 +245,35 @@ class FpvVecTask:
         _capi.check(self._lib.taco_env_rewind_rollout(self._h, C.c_void_p(stream)), "taco_env_rewind_rollout")
         self._ring_cur = 0
 
+    # ------------------------------------------------------------------ CUDA-graph support
+    def graph_begin(self):
+        """Switch the step index to a device-side counter (taco_env_graph_begin) so that launches captured in a CUDA graph stay valid
+        on replay; see ``taco_b200.rollout.GraphedRollout``."""
+        stream = torch.cuda.current_stream(self.device_id).cuda_stream
+        _capi.check(self._lib.taco_env_graph_begin(self._h, C.c_void_p(stream)), "taco_env_graph_begin")
+
+    def graph_advance(self, steps):
+        stream = torch.cuda.current_stream(self.device_id).cuda_stream
+        _capi.check(self._lib.taco_env_graph_advance(self._h, int(steps), C.c_void_p(stream)), "taco_env_graph_advance")
+
+    def graph_end(self):
+        """Back to host-side counting; the step index is read back from the device (synchronises)."""
+        stream = torch.cuda.current_stream(self.device_id).cuda_stream
+        _capi.check(self._lib.taco_env_graph_end(self._h, C.c_void_p(stream)), "taco_env_graph_end")
+        self.step_count = self.step_counter()[1]
+
+    def step_counter(self):
+        """(device address of the graph-mode step counter or 0, the library's host view of the step index)."""
+        ptr, host = C.c_void_p(), C.c_uint32()
+        _capi.check(self._lib.taco_env_step_counter(self._h, C.byref(ptr), C.byref(host)), "taco_env_step_counter")
+        return (ptr.value or 0), int(host.value)
+
+    def step_raw(self, actions):
+        """``step`` without the return-value bookkeeping: one C call (contiguous float32 (num_envs, 4) CUDA tensor)."""
+        stream = torch.cuda.current_stream(self.device_id).cuda_stream
+        _capi.check(self._lib.taco_env_step(self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(stream)), "taco_env_step")
+        self._advance()
+
     def detach_rollout(self):
         stream = torch.cuda.current_stream(self.device_id).cuda_stream
         _capi.check(self._lib.taco_env_detach_rollout(self._h, C.c_void_p(stream)), "taco_env_detach_rollout")

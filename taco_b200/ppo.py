@@ -238,6 +238,6 @@ def ppo_update(agent, optimizer, buffer, cfg, epoch, env=None, batch_idx=None, g
 def sync_rollout_nets(agent, actor=None, critic=None):
     """Copy the trained weights into the rollout kernels: once per update (the stored actor weights are already projected)."""
     if actor is not None:
-        actor.load_module(agent.actor_mlp, log_std=agent.log_std)
+        actor.load_module(agent.actor_mlp, log_std=agent.log_std, lipschitz_const=-1.0)      # already projected by ppo_update: no norm measurement
     if critic is not None:
         critic.load_modules(agent.critic_encoder, agent.critic_mlp)

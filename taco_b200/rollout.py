@@ -162,3 +162,77 @@ def collect_rollout(env, actor, buffer, value_fn, seed=0, tensor_cores=True, gro
         last_value = value_fn(buffer.obs_ring[H], buffer.states_ring[H])
     buffer.compute_returns_and_advantage(last_value, group=group)
     return tdist.allreduce_rollout_stats(env.stats(), group=group)
+
+
+class GraphedRollout:
+    """``collect_rollout`` captured ONCE as a CUDA graph and replayed: rewind -> horizon x (actor.act -> critic -> env.step) -> last
+    value -> GAE + normalisation -> statistics are ~3 H + 6 kernel launches that a replay submits with one call.  At the reference's
+    own scale (4096 envs) the eager loop is bound by Python / launch overhead (~300 us per step against ~65 us of GPU work); the
+    replay is not.  The env's step index lives in a device counter while the graph exists (``FpvVecTask.graph_begin``), so every
+    replay draws fresh Philox numbers: replays are bit-identical to the eager loop (tests/test_rollout_gpu.py).
+
+    The constructor collects the first rollout eagerly (``first_stats``); every ``run()`` is one more.
+    ``critic`` must be a ``CriticLSTM``; weights may be reloaded between replays (``ActorMLP.load`` / ``CriticLSTM.load`` write the
+    same device buffers), ``actor.log_std`` is frozen at capture.  Single-process statistics / advantage normalisation are inside the
+    graph; under torch.distributed the two small all-reduces run after the replay."""
+
+    def __init__(self, env, actor, buffer, critic, seed=0, tensor_cores=True, group=None):
+        from . import dist as tdist
+        from .critic import CriticLSTM
+        if not isinstance(critic, CriticLSTM):
+            raise TypeError("GraphedRollout needs the native critic (CriticLSTM)")
+        self.env, self.actor, self.buffer, self.critic, self.group = env, actor, buffer, critic, group
+        self.seed = int(seed)
+        self.tc_actor = bool(tensor_cores and actor.tensor_cores_available)
+        self.tc_critic = bool(tensor_cores and critic.tensor_cores_available)
+        self._tdist = tdist
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        # The FIRST rollout is collected eagerly, here: it leaves the ring cursor at H (so that the captured rewind contains the
+        # slot H -> slot 0 copy), runs every lazy initialisation outside the capture, and its experience is in ``buffer`` like
+        # that of any later ``run()``.
+        self.first_stats = collect_rollout(env, actor, buffer, critic, seed=self.seed, tensor_cores=tensor_cores, group=group)
+        H = buffer.horizon_len
+        self.stats = torch.zeros(8, dtype=torch.float64, device=buffer.device)
+        self.last_value = torch.empty(buffer.num_envs, 1, dtype=torch.float32, device=buffer.device)
+        buffer.rows(0)                                          # allocate the clipped-action scratch outside the capture
+        torch.cuda.synchronize(buffer.device)
+        env.graph_begin()
+        steps_before = env.step_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        env.step_count = steps_before                           # the capture advanced the host mirrors without running anything
+        self.replays = 0
+
+    def _body(self):
+        env, buf, H = self.env, self.buffer, self.buffer.horizon_len
+        counter = env.step_counter()[0]
+        base = env.step_count
+        env.rewind_rollout()
+        for s in range(H):
+            out = buf.rows(s)
+            self.actor.act(buf.obs_ring[s], env.step_count - base, seed=self.seed, env_offset=env.env_offset, tensor_cores=self.tc_actor,
+                           out=out, step_base=counter)
+            self.critic.forward(buf.states_ring[s], tensor_cores=self.tc_critic, out=buf.value_buf[s])
+            env.step_raw(out[1])
+        self.critic.forward(buf.states_ring[H], tensor_cores=self.tc_critic, out=self.last_value)
+        env.graph_advance(H)
+        buf.step, buf._have_timeouts = H, True
+        if self.world == 1:
+            buf.compute_returns_and_advantage(self.last_value)
+        env.stats(out=self.stats)
+
+    def run(self):
+        """One rollout.  Returns the (8,) float64 statistics tensor (all-reduced under torch.distributed)."""
+        self.graph.replay()
+        self.replays += 1
+        self.env.step_count += self.buffer.horizon_len
+        if self.world > 1:
+            self.buffer.compute_returns_and_advantage(self.last_value, group=self.group)
+        return self._tdist.allreduce_rollout_stats(self.stats, group=self.group)
+
+    def close(self):
+        """Leave graph mode (the library reads the step index back from the device)."""
+        if self.graph is not None:
+            self.graph = None
+            self.env.graph_end()

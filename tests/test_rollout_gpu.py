@@ -124,3 +124,53 @@ def test_collect_rollout_with_native_critic(tensor_cores):
     adv, ret = og.gae(aug.unsqueeze(-1), done.unsqueeze(-1), val.cpu(), last, gamma, lam)
     assert torch.equal(buf.ret_buf.cpu(), ret)
     env.close(); actor.close(); critic.close()
+
+
+@pytest.mark.parametrize("task,dr", [("flip", False), ("mix", True)])
+def test_graphed_rollout_replays_are_bit_identical_to_the_eager_loop(task, dr):
+    """GraphedRollout: the whole rollout as one CUDA-graph replay, the step index in a device counter.  Three rollouts (one eager
+    in the constructor + two replays, weights reloaded in between) equal three eager collect_rollout calls bit for bit."""
+    from taco_b200 import ActorMLP, CriticLSTM, FpvVecTask, GraphedRollout, RolloutBuffer, collect_rollout, make_cfg
+    n, H = 3000, 7
+    gen = torch.Generator().manual_seed(2)
+    sizes = [26, 64, 64, 4]
+    aw = [[torch.randn(sizes[i + 1], sizes[i], generator=gen) * 0.25 for i in range(3)] for _ in range(2)]
+    ab = [torch.zeros(sizes[i + 1]) for i in range(3)]
+    hid, mlp = 32, [64]
+    lstm = [(torch.randn(4 * hid, 26, generator=gen) * 0.3, torch.randn(4 * hid, hid, generator=gen) * 0.2,
+             torch.randn(4 * hid, generator=gen) * 0.1, torch.randn(4 * hid, generator=gen) * 0.1)]
+    cs = [hid] + mlp + [1]
+    cw = [torch.randn(cs[i + 1], cs[i], generator=gen) / cs[i] ** 0.5 for i in range(2)]
+    cb = [torch.randn(cs[i + 1], generator=gen) * 0.1 for i in range(2)]
+    runs = {}
+    for mode in ("eager", "graph"):
+        env = FpvVecTask(make_cfg(task, n, domain_randomization=dr, **{"env.maxEpisodeLength": 9}), seed=21)
+        actor, critic = ActorMLP(26, [64, 64], 4), CriticLSTM(26, 5, hid, mlp)
+        actor.load(aw[0], ab, log_std=torch.full((4,), -0.3)); critic.load(lstm, cw, cb)
+        buf = RolloutBuffer(n, 26, 1, 26, 5, 4, H, 1, 0.99, 0.95, "cuda:0")
+        snaps, gr = [], None
+        for k in range(3):
+            if k == 2:
+                actor.load(aw[1], ab, log_std=torch.full((4,), -0.3))           # new weights reach the replayed kernels
+            if mode == "eager":
+                stats = collect_rollout(env, actor, buf, critic, seed=4, tensor_cores=True)
+            elif k == 0:
+                gr = GraphedRollout(env, actor, buf, critic, seed=4, tensor_cores=True)
+                stats = gr.first_stats
+            else:
+                stats = gr.run()
+            torch.cuda.synchronize()
+            snaps.append([t.clone() for t in (buf.obs_ring, buf.states_ring, buf.act_buf, buf.logp_buf, buf.value_buf, buf.rew_buf, buf.done_buf,
+                                              buf.timeout_buf, buf.ret_buf, buf.adv_buf, stats)])
+        if gr is not None:
+            gr.close()
+            assert env.step_count == 3 * H and env.step_counter() == (0, 3 * H)
+        env.rewind_rollout()
+        o, r, x, e = env.step(env.random_actions(0))                               # eager stepping continues after the graph
+        snaps.append([o["states"].clone(), r.clone(), x.clone()])
+        runs[mode] = snaps
+        env.close(); actor.close(); critic.close()
+    for k, (a, b) in enumerate(zip(runs["eager"], runs["graph"])):
+        for j, (ta, tb) in enumerate(zip(a, b)):
+            assert torch.equal(ta, tb), (k, j)
+    assert runs["eager"][2][6].sum() > 0 and runs["eager"][2][7].sum() > 0                 # the window holds resets and time-outs
