@@ -302,6 +302,42 @@ def actor_rollout_point(torch, taco_b200, dev, n, hidden, strict_fp, peaks, iter
     return out
 
 
+def small_rollout_point(torch, taco_b200, dev, task, hidden, strict_fp, n=4096, horizon=32, reps=5):
+    """The rollout loop at the reference's own scale (README.md:41: 4096 envs): agent.act (actor sample + LSTM critic value) + env.step
+    + zero-copy store + GAE, eager (collect_rollout) against one CUDA-graph replay per rollout (GraphedRollout, critic chain as a
+    parallel branch).  Random-init networks of the bench's stated default sizes."""
+    gen = torch.Generator().manual_seed(SEED)
+    sizes = [26] + list(hidden) + [4]
+    ws = [torch.randn(sizes[i + 1], sizes[i], generator=gen) / sizes[i] ** 0.5 for i in range(len(sizes) - 1)]
+    bs = [torch.zeros(sizes[i + 1]) for i in range(len(sizes) - 1)]
+    c_hid, cs = 64, [64] + list(hidden) + [1]
+    lstm = [(torch.randn(4 * c_hid, 26, generator=gen) * 0.2, torch.randn(4 * c_hid, c_hid, generator=gen) * 0.15, torch.zeros(4 * c_hid), torch.zeros(4 * c_hid))]
+    cw = [torch.randn(cs[i + 1], cs[i], generator=gen) / cs[i] ** 0.5 for i in range(len(cs) - 1)]
+    cb = [torch.zeros(cs[i + 1]) for i in range(len(cs) - 1)]
+    out = {"workload": f"{task}, {n} envs, horizon {horizon}: actor {'x'.join(map(str, sizes))} + critic LSTM 64 / MLP {'x'.join(map(str, cs))} in the loop, GAE at the end"}
+    for mode in ("eager", "graph"):
+        env = taco_b200.FpvVecTask(taco_b200.make_cfg(task, n), dev, dev, -1, True, seed=SEED, strict_fp=strict_fp)
+        actor = taco_b200.ActorMLP(26, list(hidden), 4, device=dev); actor.load(ws, bs, lipschitz_const=-1.0)
+        critic = taco_b200.CriticLSTM(26, 5, c_hid, list(hidden), device=dev); critic.load(lstm, cw, cb)
+        buf = taco_b200.RolloutBuffer(n, 26, 1, 26, 5, 4, horizon, 1, 0.99, 0.95, dev)
+        tc = actor.tensor_cores_available and critic.tensor_cores_available
+        if mode == "eager":
+            run = lambda: taco_b200.collect_rollout(env, actor, buf, critic, seed=SEED, tensor_cores=tc)
+            run()
+        else:
+            gr = taco_b200.GraphedRollout(env, actor, buf, critic, seed=SEED, tensor_cores=tc)
+            run = gr.run
+        run()
+        ms = _timed(torch, run, reps, warm=1)
+        out[mode + "_ms_per_rollout"] = ms
+        out[mode + "_env_steps_per_s"] = n * horizon / (ms * 1e-3)
+        out[mode + "_us_per_step"] = ms / horizon * 1e3
+        if mode == "graph":
+            gr.close()
+        env.close(); actor.close(); critic.close()
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -389,6 +425,11 @@ def main():
         small = {"workload": f"{args.task}, 4096 envs (BASELINE config 2), L2-resident; 32 CTAs on 148 SMs = one warp per scheduler: bound by the latency of ~8.4k instructions per env-step, not by bandwidth", "value": 4096 * 200 / (ms_s * 1e-3),
                  "unit": "env-steps/s", "us_per_step": ms_s / 200 * 1e3}
         env_s.close()
+        if not args.no_actor:
+            try:
+                small["rollout_loop"] = small_rollout_point(torch, taco_b200, dev, args.task, [int(x) for x in args.actor_hidden.split(",")], not args.fast_fp)
+            except Exception as exc:
+                small["rollout_loop"] = {"error": repr(exc)}
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
     actor_pt = None

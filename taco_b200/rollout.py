@@ -166,7 +166,8 @@ def collect_rollout(env, actor, buffer, value_fn, seed=0, tensor_cores=True, gro
 
 class GraphedRollout:
     """``collect_rollout`` captured ONCE as a CUDA graph and replayed: rewind -> horizon x (actor.act -> critic -> env.step) -> last
-    value -> GAE + normalisation -> statistics are ~3 H + 6 kernel launches that a replay submits with one call.  At the reference's
+    value -> GAE + normalisation -> statistics are ~3 H + 6 kernel launches that a replay submits with one call, with the critic
+    chain as a parallel branch next to the actor -> step chain.  At the reference's
     own scale (4096 envs) the eager loop is bound by Python / launch overhead (~300 us per step against ~65 us of GPU work); the
     replay is not.  The env's step index lives in a device counter while the graph exists (``FpvVecTask.graph_begin``), so every
     replay draws fresh Philox numbers: replays are bit-identical to the eager loop (tests/test_rollout_gpu.py).
@@ -195,6 +196,7 @@ class GraphedRollout:
         self.stats = torch.zeros(8, dtype=torch.float64, device=buffer.device)
         self.last_value = torch.empty(buffer.num_envs, 1, dtype=torch.float32, device=buffer.device)
         buffer.rows(0)                                          # allocate the clipped-action scratch outside the capture
+        self._side = torch.cuda.Stream(device=buffer.device)    # the critic's branch of the graph
         torch.cuda.synchronize(buffer.device)
         env.graph_begin()
         steps_before = env.step_count
@@ -208,15 +210,28 @@ class GraphedRollout:
         env, buf, H = self.env, self.buffer, self.buffer.horizon_len
         counter = env.step_counter()[0]
         base = env.step_count
+        # two branches of the graph: actor -> step -> actor -> ... on the capturing stream, and the critic chain beside it (the value
+        # of slot s needs only the state history step s-1 wrote, nothing downstream needs it before GAE).  At small env counts both
+        # chains are latency-bound single-wave kernels on disjoint SMs, so they overlap fully.
+        main = torch.cuda.current_stream(buf.device)
+        side = self._side
         env.rewind_rollout()
-        for s in range(H):
+        for s in range(H + 1):
+            ev = torch.cuda.Event()
+            ev.record(main)                                       # slot s is complete (rewind, or step s-1)
+            side.wait_event(ev)
+            with torch.cuda.stream(side):
+                self.critic.forward(buf.states_ring[s], tensor_cores=self.tc_critic, out=buf.value_buf[s] if s < H else self.last_value)
+            if s == H:
+                break
             out = buf.rows(s)
             self.actor.act(buf.obs_ring[s], env.step_count - base, seed=self.seed, env_offset=env.env_offset, tensor_cores=self.tc_actor,
                            out=out, step_base=counter)
-            self.critic.forward(buf.states_ring[s], tensor_cores=self.tc_critic, out=buf.value_buf[s])
             env.step_raw(out[1])
-        self.critic.forward(buf.states_ring[H], tensor_cores=self.tc_critic, out=self.last_value)
         env.graph_advance(H)
+        done = torch.cuda.Event()
+        done.record(side)
+        main.wait_event(done)                                     # join: every value is written
         buf.step, buf._have_timeouts = H, True
         if self.world == 1:
             buf.compute_returns_and_advantage(self.last_value)
