@@ -41,6 +41,7 @@ struct DevGuard {
 constexpr int kMaxLayers = 8;        // linear layers of the FP32 path
 constexpr int kFpEnvs = 32;          // envs per CTA of the FP32 kernel (one warp lane per env)
 constexpr int kFpThreads = 128;
+constexpr int kFpTile = 8;           // output neurons per warp pass of the FP32 kernel
 
 struct FpParams {
     const float* obs; float* mean;
@@ -53,7 +54,7 @@ struct FpParams {
 };
 
 // FP32 reference path: CTA = 32 envs; activations ping-pong in shared memory; lane = env, each warp owns a strip of
-// output neurons, 4 per pass; the dot product runs over k in order with one FMA per term.
+// output neurons, kFpTile per pass; the dot product runs over k in order with one FMA per term.
 __global__ void __launch_bounds__(kFpThreads) actor_fp32_kernel(const FpParams p) {
     extern __shared__ float s_act[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -68,19 +69,33 @@ __global__ void __launch_bounds__(kFpThreads) actor_fp32_kernel(const FpParams p
         const float* __restrict__ W = p.w[l];
         const float* __restrict__ B = p.b[l];
         const bool last = (l + 1 == p.n_layers);
-        for (int j0 = warp * 4; j0 < out; j0 += (kFpThreads / 32) * 4) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            const float* wr[4];
+        // kFpTile output neurons per pass; when the rows of W are 16-byte aligned (in % 4 == 0) the weights come as float4 along k:
+        // 4 LDS + kFpTile LDG.128 per 4 * kFpTile FMAs.  Every dot product still runs over k in ascending order, one FMA per term.
+        const bool vec = (in & 3) == 0;
+        for (int j0 = warp * kFpTile; j0 < out; j0 += (kFpThreads / 32) * kFpTile) {
+            float acc[kFpTile];
+            const float* wr[kFpTile];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) wr[i] = W + (size_t)min(j0 + i, out - 1) * in;
+            for (int i = 0; i < kFpTile; ++i) { acc[i] = 0.f; wr[i] = W + (size_t)min(j0 + i, out - 1) * in; }
             const float* a = cur + lane * p.stride;
-            for (int k = 0; k < in; ++k) {
-                const float x = a[k];
+            if (vec) {
+                for (int k = 0; k < in; k += 4) {
+                    const float x0 = a[k], x1 = a[k + 1], x2 = a[k + 2], x3 = a[k + 3];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] = fmaf(x, __ldg(wr[i] + k), acc[i]);
+                    for (int i = 0; i < kFpTile; ++i) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(wr[i] + k));
+                        acc[i] = fmaf(x3, w.w, fmaf(x2, w.z, fmaf(x1, w.y, fmaf(x0, w.x, acc[i]))));
+                    }
+                }
+            } else {
+                for (int k = 0; k < in; ++k) {
+                    const float x = a[k];
+#pragma unroll
+                    for (int i = 0; i < kFpTile; ++i) acc[i] = fmaf(x, __ldg(wr[i] + k), acc[i]);
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kFpTile; ++i) {
                 if (j0 + i < out) {
                     const float v = acc[i] + __ldg(B + j0 + i);
                     nxt[lane * p.stride + j0 + i] = last ? v : fmaxf(v, 0.0f);

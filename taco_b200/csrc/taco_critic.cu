@@ -43,6 +43,7 @@ constexpr int kMaxLstmLayers = 4;
 constexpr int kMaxMlpLayers = 8;     // linear layers of the FP32 path
 constexpr int kFpEnvs = 32;          // envs per CTA of the FP32 kernel (one warp lane per env)
 constexpr int kFpThreads = 128;
+constexpr int kFpTile = 8;           // output neurons per warp pass of the FP32 kernel's MLP part
 
 struct FpParams {
     const float* states; float* value;
@@ -82,24 +83,62 @@ __global__ void __launch_bounds__(kFpThreads) critic_fp32_kernel(const FpParams 
             float* cst = hl + 2 * H;
             const float* __restrict__ Wi = p.w_ih[l];
             const float* __restrict__ Wh = p.w_hh[l];
-            for (int j = warp; j < H; j += kWarps) {
-                float a[4] = {0.f, 0.f, 0.f, 0.f}, g[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int k = 0; k < in_l; ++k) {
-                    const float x = inp[k];
+            // two hidden units per pass = 8 gate rows per product; float4 weights along k when the rows are 16-byte aligned.  Every
+            // dot product still runs over k in ascending order with one FMA per term.
+            const bool vec_i = (in_l & 3) == 0, vec_h = (H & 3) == 0;
+            for (int j0 = warp * 2; j0 < H; j0 += kWarps * 2) {
+                float a[8], g[8];
+                const float* wi[8];
+                const float* wh[8];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) a[q] = fmaf(x, __ldg(Wi + (size_t)(q * H + j) * in_l + k), a[q]);
+                for (int q = 0; q < 8; ++q) {
+                    const int j = min(j0 + (q >> 2), H - 1), row_ = (q & 3) * H + j;
+                    a[q] = 0.f; g[q] = 0.f; wi[q] = Wi + (size_t)row_ * in_l; wh[q] = Wh + (size_t)row_ * H;
                 }
-                for (int k = 0; k < H; ++k) {
-                    const float x = hprev[k];
+                if (vec_i) {
+                    for (int k = 0; k < in_l; k += 4) {
+                        const float x0 = inp[k], x1 = inp[k + 1], x2 = inp[k + 2], x3 = inp[k + 3];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) g[q] = fmaf(x, __ldg(Wh + (size_t)(q * H + j) * H + k), g[q]);
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 w = __ldg(reinterpret_cast<const float4*>(wi[q] + k));
+                            a[q] = fmaf(x3, w.w, fmaf(x2, w.z, fmaf(x1, w.y, fmaf(x0, w.x, a[q]))));
+                        }
+                    }
+                } else {
+                    for (int k = 0; k < in_l; ++k) {
+                        const float x = inp[k];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) a[q] = fmaf(x, __ldg(wi[q] + k), a[q]);
+                    }
                 }
-                float gate[4];
+                if (vec_h) {
+                    for (int k = 0; k < H; k += 4) {
+                        const float x0 = hprev[k], x1 = hprev[k + 1], x2 = hprev[k + 2], x3 = hprev[k + 3];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) gate[q] = (a[q] + __ldg(p.b_ih[l] + q * H + j)) + (g[q] + __ldg(p.b_hh[l] + q * H + j));
-                const float c = sigmoid_f(gate[1]) * cst[j] + sigmoid_f(gate[0]) * tanhf(gate[2]);
-                cst[j] = c;
-                hnew[j] = sigmoid_f(gate[3]) * tanhf(c);
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 w = __ldg(reinterpret_cast<const float4*>(wh[q] + k));
+                            g[q] = fmaf(x3, w.w, fmaf(x2, w.z, fmaf(x1, w.y, fmaf(x0, w.x, g[q]))));
+                        }
+                    }
+                } else {
+                    for (int k = 0; k < H; ++k) {
+                        const float x = hprev[k];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) g[q] = fmaf(x, __ldg(wh[q] + k), g[q]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int j = j0 + u;
+                    if (j < H) {
+                        float gate[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) gate[q] = (a[u * 4 + q] + __ldg(p.b_ih[l] + q * H + j)) + (g[u * 4 + q] + __ldg(p.b_hh[l] + q * H + j));
+                        const float c = sigmoid_f(gate[1]) * cst[j] + sigmoid_f(gate[0]) * tanhf(gate[2]);
+                        cst[j] = c;
+                        hnew[j] = sigmoid_f(gate[3]) * tanhf(c);
+                    }
+                }
             }
             __syncthreads();
         }
@@ -117,18 +156,30 @@ __global__ void __launch_bounds__(kFpThreads) critic_fp32_kernel(const FpParams 
         const float* __restrict__ W = p.w[l];
         const float* __restrict__ B = p.b[l];
         const bool last = (l + 1 == p.n_mlp);
-        for (int j0 = warp * 4; j0 < out; j0 += kWarps * 4) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            const float* wr[4];
+        const bool vec = (in & 3) == 0;
+        for (int j0 = warp * kFpTile; j0 < out; j0 += kWarps * kFpTile) {
+            float acc[kFpTile];
+            const float* wr[kFpTile];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) wr[i] = W + (size_t)min(j0 + i, out - 1) * in;
-            for (int k = 0; k < in; ++k) {
-                const float x = cur[k];
+            for (int i = 0; i < kFpTile; ++i) { acc[i] = 0.f; wr[i] = W + (size_t)min(j0 + i, out - 1) * in; }
+            if (vec) {
+                for (int k = 0; k < in; k += 4) {
+                    const float x0 = cur[k], x1 = cur[k + 1], x2 = cur[k + 2], x3 = cur[k + 3];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] = fmaf(x, __ldg(wr[i] + k), acc[i]);
+                    for (int i = 0; i < kFpTile; ++i) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(wr[i] + k));
+                        acc[i] = fmaf(x3, w.w, fmaf(x2, w.z, fmaf(x1, w.y, fmaf(x0, w.x, acc[i]))));
+                    }
+                }
+            } else {
+                for (int k = 0; k < in; ++k) {
+                    const float x = cur[k];
+#pragma unroll
+                    for (int i = 0; i < kFpTile; ++i) acc[i] = fmaf(x, __ldg(wr[i] + k), acc[i]);
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < kFpTile; ++i) {
                 if (j0 + i < out) {
                     const float v = acc[i] + __ldg(B + j0 + i);
                     nxt[j0 + i] = last ? v : fmaxf(v, 0.0f);
