@@ -111,8 +111,11 @@ int taco_env_buffers(TacoEnv* env, TacoBuffers* out);
 /* -- VecTask.step (vec_task_asymmetry.py:290-334): actions_dev = (num_envs,4) contiguous f32 on the env's
  * device.  Asynchronous on `stream`, no host sync. */
 int taco_env_step(TacoEnv* env, const float* actions_dev, void* stream);
-/* Same step through HOST buffers: copies actions H2D, steps, copies rew/reset/time_outs D2H and
- * synchronises the stream.  Any output pointer may be NULL.  Pinned host memory recommended. */
+/* Same step through HOST buffers; synchronises the stream before returning.  Any output pointer may be NULL.
+ * Pinned buffers (cudaHostAlloc / cudaHostRegister; torch pin_memory): ONE launch -- every thread loads its env's action from host
+ * memory and posts rew / reset / time_outs into host memory across PCIe itself ("mapped mode").  Pageable buffers, or
+ * TACO_HOST_MODE=copy in the environment: a chunked cudaMemcpyAsync pipeline (copy-in / kernel / copy-out of successive env
+ * chunks overlap).  Both modes produce the results of taco_env_step and leave them in the device buffers as well. */
 int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host, int64_t* reset_host,
                        uint8_t* time_outs_host, void* stream);
 /* -- VecTask.reset (vec_task_asymmetry.py:352-361) does not simulate; this additionally marks every env for
