@@ -67,6 +67,7 @@ struct TcParams {
     const float* obs;    // (n_rows, in_dim) f32
     float* mean;         // (n_rows, out_dim) f32
     int in_dim, out_dim, n_rows, num_tiles, n_hidden;
+    int obs_vec2;        // rows of obs are 8-byte aligned (even in_dim, aligned base): observation loads use 8-byte accesses
     const uint8_t* wimg; // pre-swizzled bf16 chunk images of the hidden layers and of the (16-row padded) output layer
     const float* bias;   // [kMaxHidden][kMaxN] f32
     const float* b_out;  // [kOutPad]
@@ -237,14 +238,25 @@ __device__ __forceinline__ void relu_pack32(const uint32_t (&v)[32], const float
     }
 }
 
-// the observation features [32 g, 32 g + 32) of one row as 16 packed bf16 pairs (zero beyond in_dim / for invalid rows)
-__device__ __forceinline__ void load_obs_group(const float* x, int g, int in_dim, bool valid, uint32_t* pk) {
+// the observation features [32 g, 32 g + 32) of one row as 16 packed bf16 pairs (zero beyond in_dim / for invalid rows).  Rows of an
+// even width are 8-byte aligned ((N, in_dim) float32 contiguous): one 8-byte load per pair halves the L1 wavefronts of this
+// row-per-thread access pattern (every lane touches its own row, i.e. its own cache line).
+__device__ __forceinline__ void load_obs_group(const float* x, int g, int in_dim, bool valid, uint32_t* pk, bool vec2) {
+    if (vec2) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int k = g * 32 + 2 * j;
-        const float f0 = (valid && k < in_dim) ? __ldg(x + k) : 0.0f;
-        const float f1 = (valid && k + 1 < in_dim) ? __ldg(x + k + 1) : 0.0f;
-        pk[j] = pack_bf16x2(f0, f1);
+        for (int j = 0; j < 16; ++j) {
+            const int k = g * 32 + 2 * j;
+            const float2 f = (valid && k < in_dim) ? __ldg(reinterpret_cast<const float2*>(x + k)) : make_float2(0.0f, 0.0f);
+            pk[j] = pack_bf16x2(f.x, f.y);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int k = g * 32 + 2 * j;
+            const float f0 = (valid && k < in_dim) ? __ldg(x + k) : 0.0f;
+            const float f1 = (valid && k + 1 < in_dim) ? __ldg(x + k + 1) : 0.0f;
+            pk[j] = pack_bf16x2(f0, f1);
+        }
     }
 }
 
@@ -360,7 +372,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
             const long long row0 = (long long)tile * kTileM + r;
             for (int g = ch; g < kc0 * 2; g += 2) {
                 uint32_t pk[16];
-                load_obs_group(p.obs + row0 * p.in_dim, g, p.in_dim, row0 < p.n_rows, pk);
+                load_obs_group(p.obs + row0 * p.in_dim, g, p.in_dim, row0 < p.n_rows, pk, p.obs_vec2 != 0);
                 tmem_st16(t_a + (uint32_t)(g * 16), pk);
             }
             tmem_st_wait();
@@ -420,7 +432,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
             // output MMAs run; once D is in registers the next A(t) is written and the issuer released, and only then the tanh /
             // sampling tail of this tile runs (overlapping the next tile's first MMAs).
             uint32_t pkn[16];
-            if (has_next) load_obs_group(x_next, ch, p.in_dim, row_next < p.n_rows, pkn);
+            if (has_next) load_obs_group(x_next, ch, p.in_dim, row_next < p.n_rows, pkn, p.obs_vec2 != 0);
             mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
             tc_fence_after();
             TACO_DBG(1 + t, dbg_n, 0x06);
@@ -429,7 +441,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
             if (has_next) {
                 tmem_st16(t_a + (uint32_t)(ch * 16), pkn);
                 for (int g = ch + 2; g < kc0 * 2; g += 2) {
-                    load_obs_group(x_next, g, p.in_dim, row_next < p.n_rows, pkn);
+                    load_obs_group(x_next, g, p.in_dim, row_next < p.n_rows, pkn, p.obs_vec2 != 0);
                     tmem_st16(t_a + (uint32_t)(g * 16), pkn);
                 }
                 tmem_st_wait();

@@ -211,6 +211,7 @@ static int actor_run(TacoActor* a, const float* obs_dev, float* mean_dev, int32_
         p.obs = obs_dev; p.mean = mean_dev;
         p.in_dim = a->sizes[0]; p.out_dim = a->sizes.back(); p.n_rows = n; p.num_tiles = (n + kTileM - 1) / kTileM;
         p.n_hidden = a->n_layers - 1;
+        p.obs_vec2 = ((p.in_dim & 1) == 0 && ((uintptr_t)obs_dev & 7u) == 0) ? 1 : 0;
         p.wimg = a->wimg; p.bias = a->bias_pad; p.b_out = a->b_out;
         for (int l = 0; l <= p.n_hidden; ++l) p.layer[l] = a->tc_layer[l];
         p.sp = sp;
