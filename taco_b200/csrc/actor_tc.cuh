@@ -67,6 +67,7 @@ struct TcParams {
     const float* obs;    // (n_rows, in_dim) f32
     float* mean;         // (n_rows, out_dim) f32
     int in_dim, out_dim, n_rows, num_tiles, n_hidden;
+    int obs_bulk;        // in_dim <= 26, even, 16-byte aligned base: whole tiles of observations are staged by the bulk-copy engine
     int obs_vec2;        // rows of obs are 8-byte aligned (even in_dim, aligned base): observation loads use 8-byte accesses
     const uint8_t* wimg; // pre-swizzled bf16 chunk images of the hidden layers and of the (16-row padded) output layer
     const float* bias;   // [kMaxHidden][kMaxN] f32
@@ -84,6 +85,9 @@ constexpr int kDbgCap = 4096;
 
 constexpr int kSmemBias = kMaxHidden * kMaxN * 4;          // 4 KB
 constexpr int kTcSmemBytes = 1024 /*alignment slack*/ + kSlots * kSlotBytes + kSmemBias + 256;
+constexpr int kObsBulkMaxIn = 26;              // widest observation row the bulk-staged path takes (26 x len_obs = 1)
+constexpr int kObsStageBytes = kTileM * kObsBulkMaxIn * 4;        // one tile's observation block, fp32, as it lies in global memory
+constexpr int kActorSmemBytes = kTcSmemBytes + 2 * kObsStageBytes;
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -260,6 +264,17 @@ __device__ __forceinline__ void load_obs_group(const float* x, int g, int in_dim
     }
 }
 
+// features [0, 32) of row r of a bulk-staged observation block (rows of in_dim floats, as in global memory) as 16 packed bf16
+// pairs; 8-byte reads at a row stride of in_dim * 4 bytes (26 words: conflict-free per half-warp)
+__device__ __forceinline__ void read_staged_obs(const float* stage, int r, int in_dim, uint32_t* pk) {
+    const float2* row = reinterpret_cast<const float2*>(stage + r * in_dim);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float2 f = (2 * j < in_dim) ? row[j] : make_float2(0.0f, 0.0f);
+        pk[j] = pack_bf16x2(f.x, f.y);
+    }
+}
+
 #ifndef TACO_TC_NO_ACTOR_KERNEL      // critic_tc.cuh reuses the wrappers above and the weight packer below, not this kernel
 __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -274,6 +289,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
     const uint32_t bar_a = bar_empty + 8 * kSlots;                   // [2] epilogue(t) -> MMA: D(t) drained (and, for a new layer, A(t) written)
     const uint32_t bar_d = bar_a + 16;                               // [2] MMA -> epilogue(t): the part of D(t) is complete
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 4);
+    const uint32_t bar_obs = bar_d + 16 + 8;                         // [2] a tile's observation block has landed in the staging buffer
+    float* s_obs = reinterpret_cast<float*>(sm + kTcSmemBytes - 1024);   // [2 tiles][128 rows x in_dim] (only with p.obs_bulk)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_pairs = (p.num_tiles + 1) >> 1;
@@ -282,7 +299,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
     for (int i = threadIdx.x; i < kMaxHidden * kMaxN; i += kTcThreads) s_bias[i] = p.bias[i];
     if (threadIdx.x == 0) {
         for (int s = 0; s < kSlots; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int t = 0; t < 2; ++t) { mbar_init(bar_a + 8 * t, (kEpiWarps / 2) * 32); mbar_init(bar_d + 8 * t, 1); }
+        for (int t = 0; t < 2; ++t) { mbar_init(bar_a + 8 * t, (kEpiWarps / 2) * 32); mbar_init(bar_d + 8 * t, 1); mbar_init(bar_obs + 8 * t, 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(s_tmem), kTmemCols);
@@ -366,14 +383,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
         int dbg_n = (ch == 0 && quad == 0 && lane == 0) ? 0 : kDbgCap;
         int tile = 2 * (int)blockIdx.x + t;
         const int tile_step = 2 * (int)gridDim.x;
+        // Bulk-staged observations (p.obs_bulk): a FULL tile's rows are one contiguous block of global memory (128 x in_dim floats), so
+        // one elected thread of the tile has the bulk-copy engine fetch the block of the tile AFTER the one being staged; the
+        // 128 x 26 row-per-thread scalar loads (one cache line per lane and instruction) leave the LSU.  Partial last tiles use loads.
+        float* s_obs_t = s_obs + t * (kTileM * kObsBulkMaxIn);
+        const uint32_t obs_bytes = (uint32_t)(kTileM * p.in_dim * 4);
+        uint32_t o_phase = 0;
+        const bool staged_first = p.obs_bulk && (long long)(tile + 1) * kTileM <= p.n_rows;
+        auto fetch_obs = [&](int tl) {                               // all 256 threads of the tile call this; one issues the copy
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "r"((kEpiWarps / 2) * 32) : "memory");     // every reader of the buffer is done
+            if (e % 8 == 0 && elect_one_sync()) {
+                fence_proxy_async_smem();
+                mbar_arrive_expect_tx(bar_obs + 8 * t, obs_bytes);
+                bulk_g2s(smem_u32(s_obs_t), p.obs + (size_t)tl * kTileM * p.in_dim, obs_bytes, bar_obs + 8 * t);
+            }
+        };
+        auto bulk_tile = [&](int tl) { return p.obs_bulk && tl < p.num_tiles && (long long)(tl + 1) * kTileM <= p.n_rows; };
         if (tile < p.num_tiles) {
             // ---- the first tile's observation row as packed bf16 into A(t), K padded with zeros to kc0 * 64; groups of 32
             // features (16 TMEM columns) alternate between ch 0 / 1
             const long long row0 = (long long)tile * kTileM + r;
-            for (int g = ch; g < kc0 * 2; g += 2) {
+            if (staged_first) {
+                fetch_obs(tile);
+                mbar_wait(bar_obs + 8 * t, o_phase); o_phase ^= 1u;
                 uint32_t pk[16];
-                load_obs_group(p.obs + row0 * p.in_dim, g, p.in_dim, row0 < p.n_rows, pk, p.obs_vec2 != 0);
-                tmem_st16(t_a + (uint32_t)(g * 16), pk);
+                if (ch == 0) read_staged_obs(s_obs_t, r, p.in_dim, pk);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = 0u;
+                }
+                tmem_st16(t_a + (uint32_t)(ch * 16), pk);
+                if (bulk_tile(tile + tile_step)) fetch_obs(tile + tile_step);
+            } else {
+                for (int g = ch; g < kc0 * 2; g += 2) {
+                    uint32_t pk[16];
+                    load_obs_group(p.obs + row0 * p.in_dim, g, p.in_dim, row0 < p.n_rows, pk, p.obs_vec2 != 0);
+                    tmem_st16(t_a + (uint32_t)(g * 16), pk);
+                }
+                if (bulk_tile(tile + tile_step)) fetch_obs(tile + tile_step);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -432,7 +479,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
             // output MMAs run; once D is in registers the next A(t) is written and the issuer released, and only then the tanh /
             // sampling tail of this tile runs (overlapping the next tile's first MMAs).
             uint32_t pkn[16];
-            if (has_next) load_obs_group(x_next, ch, p.in_dim, row_next < p.n_rows, pkn, p.obs_vec2 != 0);
+            const bool next_staged = has_next && bulk_tile(tile + tile_step);
+            if (next_staged) {                                       // the block was fetched a whole tile ago: no load latency to hide
+                mbar_wait(bar_obs + 8 * t, o_phase); o_phase ^= 1u;
+                if (ch == 0) read_staged_obs(s_obs_t, r, p.in_dim, pkn);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pkn[j] = 0u;
+                }
+                if (bulk_tile(tile + 2 * tile_step)) fetch_obs(tile + 2 * tile_step);
+            } else if (has_next) load_obs_group(x_next, ch, p.in_dim, row_next < p.n_rows, pkn, p.obs_vec2 != 0);
             mbar_wait(bar_d + 8 * t, d_phase); d_phase ^= 1u;
             tc_fence_after();
             TACO_DBG(1 + t, dbg_n, 0x06);
@@ -440,7 +496,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
             if (ch == 0) { tmem_ld4(t_d, v); tmem_ld_wait(); }
             if (has_next) {
                 tmem_st16(t_a + (uint32_t)(ch * 16), pkn);
-                for (int g = ch + 2; g < kc0 * 2; g += 2) {
+                for (int g = ch + 2; g < kc0 * 2 && !next_staged; g += 2) {
                     load_obs_group(x_next, g, p.in_dim, row_next < p.n_rows, pkn, p.obs_vec2 != 0);
                     tmem_st16(t_a + (uint32_t)(g * 16), pkn);
                 }

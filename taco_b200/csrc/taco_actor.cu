@@ -212,6 +212,7 @@ static int actor_run(TacoActor* a, const float* obs_dev, float* mean_dev, int32_
         p.in_dim = a->sizes[0]; p.out_dim = a->sizes.back(); p.n_rows = n; p.num_tiles = (n + kTileM - 1) / kTileM;
         p.n_hidden = a->n_layers - 1;
         p.obs_vec2 = ((p.in_dim & 1) == 0 && ((uintptr_t)obs_dev & 7u) == 0) ? 1 : 0;
+        p.obs_bulk = ((p.in_dim & 1) == 0 && p.in_dim <= kObsBulkMaxIn && ((uintptr_t)obs_dev & 15u) == 0 && !getenv("TACO_ACTOR_NO_BULK_OBS")) ? 1 : 0;
         p.wimg = a->wimg; p.bias = a->bias_pad; p.b_out = a->b_out;
         for (int l = 0; l <= p.n_hidden; ++l) p.layer[l] = a->tc_layer[l];
         p.sp = sp;
@@ -223,7 +224,7 @@ static int actor_run(TacoActor* a, const float* obs_dev, float* mean_dev, int32_
             ACT_CUDA(cudaMalloc(&p.dbg, 3 * kDbgCap * sizeof(unsigned long long)));
             ACT_CUDA(cudaMemsetAsync(p.dbg, 0, 3 * kDbgCap * sizeof(unsigned long long), s));
         }
-        actor_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, s>>>(p);
+        actor_tc_kernel<<<grid, kTcThreads, kActorSmemBytes, s>>>(p);
         if (p.dbg) {
             std::vector<unsigned long long> h(3 * kDbgCap);
             ACT_CUDA(cudaStreamSynchronize(s));
@@ -302,7 +303,7 @@ int taco_actor_create(int device, const int32_t* sizes, int32_t n_sizes, TacoAct
         ce = cudaMalloc(&a->wimg, img);
         if (ce == cudaSuccess) ce = cudaMalloc(&a->bias_pad, kMaxHidden * kMaxN * sizeof(float));
         if (ce == cudaSuccess) ce = cudaMalloc(&a->b_out, kOutPad * sizeof(float));
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(actor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(actor_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kActorSmemBytes);
     }
     if (ce == cudaSuccess && a->fp_smem > 48 * 1024)
         ce = cudaFuncSetAttribute(actor_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a->fp_smem);
