@@ -221,11 +221,21 @@ __device__ __forceinline__ void actor_tail(const float* pre, int out_dim, long l
         box_muller(r.x, r.y, z[0], z[1]);
         box_muller(r.z, r.w, z[2], z[3]);
         float lp = sp.logp_const;
+        float a[kOutPad] = {0.f, 0.f, 0.f, 0.f};
         for (int o = 0; o < out_dim; ++o) {
-            const float a = mu[o] + sp.std_[o] * z[o];
-            sp.action[row * out_dim + o] = a;
-            if (sp.clipped) sp.clipped[row * out_dim + o] = fminf(fmaxf(a, -1.0f), 1.0f);
+            a[o] = mu[o] + sp.std_[o] * z[o];
             lp += -0.5f * (z[o] * z[o]);
+        }
+        if (out_dim == 4 && ((reinterpret_cast<uintptr_t>(sp.action) | reinterpret_cast<uintptr_t>(sp.clipped)) & 15u) == 0) {
+            *reinterpret_cast<float4*>(sp.action + row * 4) = make_float4(a[0], a[1], a[2], a[3]);
+            if (sp.clipped)
+                *reinterpret_cast<float4*>(sp.clipped + row * 4) = make_float4(fminf(fmaxf(a[0], -1.0f), 1.0f), fminf(fmaxf(a[1], -1.0f), 1.0f),
+                                                                               fminf(fmaxf(a[2], -1.0f), 1.0f), fminf(fmaxf(a[3], -1.0f), 1.0f));
+        } else {
+            for (int o = 0; o < out_dim; ++o) {
+                sp.action[row * out_dim + o] = a[o];
+                if (sp.clipped) sp.clipped[row * out_dim + o] = fminf(fmaxf(a[o], -1.0f), 1.0f);
+            }
         }
         if (sp.logp) sp.logp[row] = lp;
     }

@@ -295,8 +295,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
                                     const uint32_t a_c = a_addr + (uint32_t)(c * (kKC / 2));
                                     umma_bf16_ts(d_addr, a_c, b_c, idesc, (uint32_t)(c != 0));
                                     umma_bf16_ts(d_addr, a_c + 8u, b_c + 2u, idesc, 1u);
-                                    umma_bf16_ts(d_addr, a_c + 16u, b_c + 4u, idesc, 1u);
-                                    umma_bf16_ts(d_addr, a_c + 24u, b_c + 6u, idesc, 1u);
+                                    if (ring || c == 0) {                  // the x_t chunk of an LSTM step holds only 32 K values (26 + 2 bias + pad)
+                                        umma_bf16_ts(d_addr, a_c + 16u, b_c + 4u, idesc, 1u);
+                                        umma_bf16_ts(d_addr, a_c + 24u, b_c + 6u, idesc, 1u);
+                                    }
                                 }
                                 if (t == nt - 1 && ring) umma_commit(bar_empty + 8 * slot);
                                 umma_commit(bar_d + 8 * t);
