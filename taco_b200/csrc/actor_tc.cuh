@@ -67,6 +67,7 @@ struct TcParams {
     const float* obs;    // (n_rows, in_dim) f32
     float* mean;         // (n_rows, out_dim) f32
     int in_dim, out_dim, n_rows, num_tiles, n_hidden;
+    int tiles_per_cta;   // 2 (a CTA keeps a pair of tiles in flight) or 1
     int obs_bulk;        // in_dim <= 26, even, 16-byte aligned base: whole tiles of observations are staged by the bulk-copy engine
     int obs_vec2;        // rows of obs are 8-byte aligned (even in_dim, aligned base): observation loads use 8-byte accesses
     const uint8_t* wimg; // pre-swizzled bf16 chunk images of the hidden layers and of the (16-row padded) output layer
@@ -303,7 +304,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
     float* s_obs = reinterpret_cast<float*>(sm + kTcSmemBytes - 1024);   // [2 tiles][128 rows x in_dim] (only with p.obs_bulk)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_pairs = (p.num_tiles + 1) >> 1;
+    const int tps = p.tiles_per_cta;                                 // 2, or 1 when there are fewer tiles than SMs (small batches: one tile per CTA halves the latency)
+    const int num_pairs = (p.num_tiles + tps - 1) / tps;
     const int n_layers = p.n_hidden + 1;                             // hidden layers + the output layer as a 16-wide part
 
     for (int i = threadIdx.x; i < kMaxHidden * kMaxN; i += kTcThreads) s_bias[i] = p.bias[i];
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
         int dbg_n = lane == 0 ? 0 : kDbgCap;
         const uint64_t bdesc0 = umma_desc_sw128(s_ring);
         for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-            const int nt = (2 * pair + 1 < p.num_tiles) ? 2 : 1;
+            const int nt = min(tps, p.num_tiles - tps * pair);
             for (int l = 0; l < n_layers; ++l) {
                 const int n = p.layer[l].n, kch = p.layer[l].kchunks;
                 for (int h0 = 0; h0 < n; h0 += kPartN) {
@@ -391,8 +393,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) actor_tc_kernel(const TcParams 
         uint32_t d_phase = 0;
         const int kc0 = p.layer[0].kchunks;
         int dbg_n = (ch == 0 && quad == 0 && lane == 0) ? 0 : kDbgCap;
-        int tile = 2 * (int)blockIdx.x + t;
-        const int tile_step = 2 * (int)gridDim.x;
+        int tile = t < tps ? tps * (int)blockIdx.x + t : p.num_tiles;      // tile slot 1 idles with one tile per CTA
+        const int tile_step = tps * (int)gridDim.x;
         // Bulk-staged observations (p.obs_bulk): a FULL tile's rows are one contiguous block of global memory (128 x in_dim floats), so
         // one elected thread of the tile has the bulk-copy engine fetch the block of the tile AFTER the one being staged; the
         // 128 x 26 row-per-thread scalar loads (one cache line per lane and instruction) leave the LSU.  Partial last tiles use loads.

@@ -40,6 +40,7 @@ struct CriticTcParams {
     const float* states;   // (n_rows, seq_len, in_dim) f32
     float* value;          // (n_rows) f32
     int in_dim, seq_len, n_rows, num_tiles;
+    int tiles_per_cta;     // 2 (a CTA keeps a pair of tiles in flight) or 1
     int lstm_hidden;       // H: multiple of 16, <= 64
     int n_hidden;          // MLP hidden layers, 1..3
     const uint8_t* wimg;   // pre-swizzled bf16 chunk images: LSTM [W_hh | W_ih] (gate-permuted rows), MLP layers, output (16 rows)
@@ -210,7 +211,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
     uint32_t* s_x = reinterpret_cast<uint32_t*>(sm + kTcSmemBytes - 1024);       // [2 tiles][128 rows][kXStride] staged state frames (bf16 pairs)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_pairs = (p.num_tiles + 1) >> 1;
+    const int tps = p.tiles_per_cta;                                 // 2, or 1 when there are fewer tiles than SMs (small batches: one tile per CTA halves the latency)
+    const int num_pairs = (p.num_tiles + tps - 1) / tps;
     const int T = p.seq_len;
     const int n_sched = T + p.n_hidden + 1;            // T LSTM steps, the MLP hidden layers, the output part
 
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
         const uint64_t bdesc0 = umma_desc_sw128(s_ring);
         mbar_wait(bar_lstm, 0u);                                       // the resident LSTM image
         for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-            const int nt = (2 * pair + 1 < p.num_tiles) ? 2 : 1;
+            const int nt = min(tps, p.num_tiles - tps * pair);
             for (int s = 0; s < n_sched; ++s) {
                 const int l = s < T ? 0 : s - T + 1;
                 const int n = p.layer[l].n, kch = p.layer[l].kchunks;
@@ -321,8 +323,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
         uint32_t d_phase = 0;
         int dbg_n = (ch == 0 && quad == 0 && lane == 0) ? 0 : kDbgCap;
         const size_t row_floats = (size_t)T * p.in_dim;
-        int tile = 2 * (int)blockIdx.x + t;
-        const int tile_step = 2 * (int)gridDim.x;
+        int tile = t < tps ? tps * (int)blockIdx.x + t : p.num_tiles;      // tile slot 1 idles with one tile per CTA
+        const int tile_step = tps * (int)gridDim.x;
         const int tt = ((e & 7) << 5) | lane;                       // index among the 256 epilogue threads of this tile
         const float inv_in = 1.0f / (float)(p.in_dim >> 1);           // 1 / feature pairs per frame
         uint32_t* s_xt = s_x + t * (kTileM * kXStride);

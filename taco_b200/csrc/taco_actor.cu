@@ -216,7 +216,8 @@ static int actor_run(TacoActor* a, const float* obs_dev, float* mean_dev, int32_
         p.wimg = a->wimg; p.bias = a->bias_pad; p.b_out = a->b_out;
         for (int l = 0; l <= p.n_hidden; ++l) p.layer[l] = a->tc_layer[l];
         p.sp = sp;
-        const int num_pairs = (p.num_tiles + 1) / 2;                   // a CTA keeps two tiles in flight
+        p.tiles_per_cta = p.num_tiles <= a->num_sms ? 1 : 2;           // a CTA keeps two tiles in flight unless every tile can have its own SM
+        const int num_pairs = (p.num_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
         const int grid = num_pairs < a->num_sms ? num_pairs : a->num_sms;
         // developer aid: TACO_ACTOR_TIMELINE=<file> records clock64 stamps of CTA 0's MMA issuer / epilogue (synchronous)
         const char* tl = getenv("TACO_ACTOR_TIMELINE");

@@ -381,7 +381,8 @@ int taco_critic_forward(TacoCritic* c, const float* states_dev, float* value_dev
         p.lstm_hidden = c->hidden; p.n_hidden = c->n_mlp - 1;
         p.wimg = c->wimg; p.bias = c->bias_pad; p.b_out = c->b_out;
         for (int l = 0; l <= p.n_hidden + 1; ++l) p.layer[l] = c->tc_layer[l];
-        const int num_pairs = (p.num_tiles + 1) / 2;
+        p.tiles_per_cta = p.num_tiles <= c->num_sms ? 1 : 2;
+        const int num_pairs = (p.num_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
         const int grid = num_pairs < c->num_sms ? num_pairs : c->num_sms;
         // developer aid: TACO_CRITIC_TIMELINE=<file> records clock64 stamps of CTA 0's MMA issuer / epilogue (synchronous)
         const char* tl = getenv("TACO_CRITIC_TIMELINE");
