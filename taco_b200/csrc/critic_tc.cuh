@@ -64,11 +64,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "memory");
 }
 __device__ __forceinline__ float tanh_mufu(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sigmoid_mufu(float x) { return fmaf(0.5f, tanh_mufu(0.5f * x), 0.5f); }
 
-// TACO_CRITIC_GATES: 0 (default) = tanh.approx.f32; 1 = MUFU.TANH on packed half pairs (tanh.approx.f16x2; measured 6 % SLOWER --
-// the conversions cost more issue slots than the MUFU slots they save -- and twice the error); 2 = no transcendentals at all
-// (timing experiment only, wrong values: 3 % faster, i.e. the LSTM phase is bound by instruction issue / latency, not by MUFU)
+// TACO_CRITIC_GATES (tuning builds): 0 (default) = tanh.approx.f32; 1 = MUFU.TANH on packed half pairs (tanh.approx.f16x2: the same
+// 16.4 results per clock and SM as the f32 form, tools/probes/mufu_probe.cu, plus conversions -- no faster, twice the error);
+// 2 = no transcendentals at all (timing experiment only, wrong values)
 #ifndef TACO_CRITIC_GATES
 #define TACO_CRITIC_GATES 0
 #endif
