@@ -14,10 +14,13 @@ Parity status
   torch modules, executed in the build container through import stubs
   (``oracle/ref_loader.py``); the vectors live in ``tests/golden/*.npz`` and the
   generating script is ``oracle/make_golden.py``.
-* ``FpvBase`` glue (delay buffer, observation history, resets, commands): restated from
-  the reference source; the reference class cannot be instantiated anywhere (IsaacGym /
-  PhysX binaries are absent), and the reference ships no tests => **parity unpinned**
-  for the glue beyond the leaf modules it calls.
+* ``FpvBase`` glue (delay buffer, observation history, resets, commands, mix groups): PINNED against the
+  reference's own classes.  ``oracle/fake_gym.py`` is a fake ``isaacgym`` (gymapi / gymtorch) + ``gym.spaces`` over
+  which FpvPos / FpvRotate / FpvFlip / FpvMix and VecTask run unmodified on the CPU (``simulate`` = our integrator,
+  below); ``oracle/ref_draws.py`` feeds their torch.rand / torch.normal call sites from the shared Philox slot table;
+  ``oracle/make_golden_glue.py`` records 72-step trajectories into ``tests/golden/glue_<task>_<mode>.npz``.
+  ``tests/test_oracle_glue.py`` holds ``RefFpvEnv(reference_exact=True)`` to them: every integer / mask / index
+  exact, floats <= 2e-6 on the first steps and <= 7e-5 over the run.
 * Rigid-body step: PhysX is closed source and absent => our own documented integrator
   (``oracle/rigid_body.py``), **parity unpinned** against PhysX by construction.
 * Random numbers: the reference draws from torch's global generator (irreproducible

@@ -10,11 +10,16 @@ Follows, in order:
 using oracle.dynamics / oracle.rewards / oracle.leaf_math (pinned to the reference's torch
 modules by tests/golden) and oracle.rigid_body (our PhysX stand-in).
 
-Differences from the reference that are deliberate and documented in DESIGN.md:
+Pinned against the reference's own FpvPos / FpvRotate / FpvFlip / FpvMix run over oracle/fake_gym.py
+(tests/golden/glue_*.npz, tests/test_oracle_glue.py).  Differences from the reference that are deliberate and
+documented in DESIGN.md:
   * resets are expressed with boolean masks instead of index lists (same result);
-  * random numbers come from the Philox slot table below instead of torch's global RNG;
+  * random numbers come from the Philox slot table below instead of torch's global RNG (oracle/ref_draws.py maps
+    every reference call site onto the table);
   * "reset is visible immediately": the root state written by a reset is what the next
-    refresh_state sees (PhysX-internal in the reference, FPV:508 / quirk 17 in SURVEY.md).
+    refresh_state sees (PhysX-internal in the reference, FPV:508 / quirk 17 in SURVEY.md);
+  * unless ``reference_exact=True``: the angular velocity is carried in body coordinates across the control
+    sub-steps of one RL step, and the random attitude draws use ``sincos_draw`` (both: see ``__init__``).
 The dense (N,4,100) delay buffer is kept exactly as in the reference (FPV:189,326-331,
 366,378-380) so that the kernel's compressed action queue is checked against it.
 """
@@ -47,8 +52,17 @@ def f32(x):
 
 
 class RefFpvEnv:
-    def __init__(self, cfg, env_offset=0, num_envs_global=None, seed=0):
+    def __init__(self, cfg, env_offset=0, num_envs_global=None, seed=0, reference_exact=False):
+        """``reference_exact=True`` switches off the two places where the specification the CUDA kernel implements
+        deliberately departs from what the reference classes compute over a simulator (both documented in DESIGN.md):
+        the angular velocity goes through the world-frame root state between control sub-steps (R(q) w_b, then
+        R(q)^T of that, fpv_asymmetry.py:350) instead of being carried in body coordinates, and the random attitude
+        draws use torch.sin / torch.cos (torch_utils.py:199-213) instead of the polynomial ``sincos_draw``.  In that
+        mode this class is held to trajectories recorded from the reference's own FpvPos / FpvRotate / FpvFlip /
+        FpvMix (tests/golden/glue_*.npz, tests/test_oracle_glue.py)."""
         e = cfg["env"]
+        self.reference_exact = bool(reference_exact)
+        self._sincos = None if reference_exact else sincos_draw
         self.cfg = cfg
         self.N = int(e["numEnvs"])
         self.env_offset = int(env_offset)
@@ -169,9 +183,9 @@ class RefFpvEnv:
             if self.random_copter_quat:
                 # rand_quat(n, pitch_lim, roll_lim, yaw_lim): the "pitch" draw lands in the ROLL slot (FPV:698-704)
                 full = quat_from_euler(rand_range(-math.pi, math.pi, U(1, 0)), rand_range(-math.pi, math.pi, U(1, 1)),
-                                       rand_range(-math.pi, math.pi, U(1, 2)), sincos_draw)
+                                       rand_range(-math.pi, math.pi, U(1, 2)), self._sincos)
                 zero = torch.zeros(N)
-                roll_only = quat_from_euler(rand_range(-math.pi, math.pi, U(1, 0)), zero, zero, sincos_draw)      # FPV:864,1038
+                roll_only = quat_from_euler(rand_range(-math.pi, math.pi, U(1, 0)), zero, zero, self._sincos)      # FPV:864,1038
                 new_q = torch.where(is_flip.unsqueeze(1), roll_only, full)
             else:
                 new_q = torch.tensor([0.0, 0.0, 0.0, 1.0]).repeat(N, 1)
@@ -250,7 +264,7 @@ class RefFpvEnv:
             self.tpos = torch.where(Rc, torch.cat((txy, tz.unsqueeze(1)), dim=1), self.tpos)
             yaw = rand_range(-math.pi, math.pi, U(3, 3)) if self.random_target_yaw else torch.zeros(N)
             zero = torch.zeros(N)
-            self.tquat = torch.where(Rc, quat_from_euler(zero, zero, yaw, sincos_draw), self.tquat)
+            self.tquat = torch.where(Rc, quat_from_euler(zero, zero, yaw, self._sincos), self.tquat)
         # ---- command (FPV:758-759, :814-821, :886-917, :1058-1112)
         if bool(cmd_mask.any()):
             cblk = self._block(0, px.STREAM_COMMAND)
@@ -356,7 +370,10 @@ class RefFpvEnv:
             torque_b = torch.where(R.unsqueeze(1), torch.zeros(N, 3), torque_b)
             self.pos, self.quat, self.linvel, w_b = rb.integrate(                                  # VT:313
                 self.pos, self.quat, self.linvel, self.angvel_body, force_b, torque_b, self.dt, self.substeps)
-        if w_b is not None:
+            if self.reference_exact:                                   # the simulator hands back a world-frame root state
+                self.angvel = qrot(self.quat, w_b)
+                w_b = None
+        if w_b is not None and not self.reference_exact:
             self.angvel = qrot(self.quat, w_b)                         # world-frame root state at the end of the RL step
         self.last_delay_index = torch.stack(delay_idx_log, dim=1)
         self.last_delayed_actions = torch.stack(delay_act_log, dim=1)          # (N, cfi, 4)
@@ -414,7 +431,7 @@ class RefFpvEnv:
                 noisy[:, i] = noisy[:, i] + d * (nrm[i] * sig_p)
             lim = d * 0.05
             nq = quat_from_euler(rand_range(-lim, lim, f32(px.u01(ub[:, 0]))), rand_range(-lim, lim, f32(px.u01(ub[:, 1]))),
-                                 rand_range(-lim, lim, f32(px.u01(ub[:, 2]))), sincos_draw)
+                                 rand_range(-lim, lim, f32(px.u01(ub[:, 2]))), self._sincos)
             noisy[:, 3:12] = rotmat9(qmul(self.rel_quat_body, nq))
             for i in range(3):
                 noisy[:, 12 + i] = noisy[:, 12 + i] + d * (nrm[3 + i] * sig_v)

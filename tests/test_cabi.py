@@ -78,7 +78,12 @@ def test_product_does_not_import_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "taco_b200")):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
-                assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("oracle/", "").replace("oracle.philox", "").replace("oracle/philox.py", "").lower() or True
+                src = open(os.path.join(dirpath, f)).read()
+                # comments may CITE oracle files (oracle/..., oracle.philox ...); nothing may import, load or execute them
+                for pat in (r"^\s*(from|import)\s+oracle\b", r"^\s*from\s+\.+\s*oracle\b", r"import_module\(\s*['\"]oracle",
+                            r"__import__\(\s*['\"]oracle", r"librigid_body", r"dlopen\([^)]*oracle", r"CDLL\([^)]*oracle",
+                            r"#include\s*[<\"][^>\"]*oracle"):
+                    assert not re.search(pat, src, flags=re.M), (f, pat)
 
 
 # ---------------------------------------------------------------------------------------------- a plain-C consumer
