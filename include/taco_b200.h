@@ -198,7 +198,11 @@ int taco_actor_forward(TacoActor* actor, const float* obs_dev, float* mean_dev, 
 /* PPO_ActorCritic.act, actor branch: mean as above; action = mean + exp(log_std)^2 * eps (scale_tril = diag(exp(log_std)^2),
  * nets_asymmetry.py:338), eps ~ N(0,1) from Philox(seed; env_offset + row, step_index, stream 6); clipped =
  * clamp(action, -1, 1) (ppo_asymmetry.py:310); logp = MultivariateNormal.log_prob(action).  log_std_host: `out` floats on
- * the host.  clipped_dev / logp_dev may be NULL. */
+ * the host, or NULL = the values of the last taco_actor_set_log_std / taco_actor_act.  The kernels read std and the log-prob
+ * constant from device memory owned by the actor (uploaded when log_std_host differs from the last values; that is refused while
+ * `stream` is capturing), so launches captured in a CUDA graph follow taco_actor_set_log_std between replays.
+ * clipped_dev / logp_dev may be NULL. */
+int taco_actor_set_log_std(TacoActor* actor, const float* log_std_host, void* stream);
 int taco_actor_act(TacoActor* actor, const float* obs_dev, int32_t n, const float* log_std_host, int64_t env_offset,
                    uint64_t seed, uint32_t step_index, float* mean_dev, float* action_dev, float* clipped_dev,
                    float* logp_dev, int32_t use_tensor_cores, void* stream);

@@ -89,6 +89,7 @@ def lib():
         "taco_actor_sigmas": (C.c_int, [vp, vp]),
         "taco_actor_weights": (C.c_int, [vp, i32, vp, vp]),
         "taco_actor_tc_available": (C.c_int, [vp]),
+        "taco_actor_set_log_std": (C.c_int, [vp, vp, vp]),
         "taco_spectral_project": (C.c_int, [C.c_int, vp, i32, i32, f32, vp, vp]),
         "taco_actor_act": (C.c_int, [vp, vp, i32, vp, C.c_int64, u64, u32, vp, vp, vp, vp, i32, vp]),
         "taco_critic_create": (C.c_int, [C.c_int, i32, i32, i32, i32, C.POINTER(i32), i32, C.POINTER(vp)]),

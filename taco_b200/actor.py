@@ -60,7 +60,16 @@ class ActorMLP:
         bp = (C.c_void_p * self.n_layers)(*[b.ctypes.data for b in bs])
         _capi.check(self._lib.taco_actor_load(self._h, wp, bp, float(lipschitz_const), self._stream()), "taco_actor_load")
         if log_std is not None:
-            self.log_std = np.ascontiguousarray(log_std.detach().cpu().numpy() if isinstance(log_std, torch.Tensor) else log_std, dtype=np.float32)
+            self.set_log_std(log_std)
+
+    def set_log_std(self, log_std):
+        """The policy's ``log_std`` parameter (nets_asymmetry.py:315,338).  The kernels read exp(log_std)^2 and the log-prob constant
+        from device memory owned by the actor, so this also takes effect in launches already captured in a CUDA graph."""
+        v = np.ascontiguousarray(log_std.detach().cpu().numpy() if isinstance(log_std, torch.Tensor) else log_std, dtype=np.float32).reshape(-1)
+        if v.shape != (self.sizes[-1],):
+            raise ValueError(f"log_std must have {self.sizes[-1]} entries")
+        self.log_std = v
+        _capi.check(self._lib.taco_actor_set_log_std(self._h, v.ctypes.data_as(C.c_void_p), self._stream()), "taco_actor_set_log_std")
 
     def load_module(self, actor_mlp, log_std=None, lipschitz_const=0.0):
         """Load from a reference-style ``MLP`` (its ``.layers`` Sequential of Linear / activation modules)."""

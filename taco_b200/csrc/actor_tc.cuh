@@ -56,8 +56,9 @@ struct SampleParams {    // PPO_ActorCritic.act sampling (nets_asymmetry.py:336-
     float* action;       // (n, out) mean + std * eps
     float* clipped;      // (n, out) clamp(action, -1, 1)   (ppo_asymmetry.py:310)
     float* logp;         // (n)
-    float std_[kOutPad]; // exp(log_std)^2: scale_tril = diag(exp(log_std)^2)  (nets_asymmetry.py:338)
-    float logp_const;    // -sum(log std) - out/2 * log(2 pi)
+    const float* samp;   // device, owned by the TacoActor: [0..3] std = exp(log_std)^2 (scale_tril = diag(exp(log_std)^2),
+                         // nets_asymmetry.py:338), [4] logp_const = -sum(log std) - out/2 * log(2 pi).  In device memory, not by
+                         // value, so that a launch captured in a CUDA graph follows taco_actor_set_log_std between replays
     long long env_offset;
     uint32_t seed_lo, seed_hi, step_index;
     const uint32_t* step_base;   // device word added to step_index (null: none), see taco_actor_act_counter
@@ -221,10 +222,10 @@ __device__ __forceinline__ void actor_tail(const float* pre, int out_dim, long l
         float z[4];
         box_muller(r.x, r.y, z[0], z[1]);
         box_muller(r.z, r.w, z[2], z[3]);
-        float lp = sp.logp_const;
+        float lp = __ldg(sp.samp + 4);
         float a[kOutPad] = {0.f, 0.f, 0.f, 0.f};
         for (int o = 0; o < out_dim; ++o) {
-            a[o] = mu[o] + sp.std_[o] * z[o];
+            a[o] = mu[o] + __ldg(sp.samp + o) * z[o];
             lp += -0.5f * (z[o] * z[o]);
         }
         if (out_dim == 4 && ((reinterpret_cast<uintptr_t>(sp.action) | reinterpret_cast<uintptr_t>(sp.clipped)) & 15u) == 0) {

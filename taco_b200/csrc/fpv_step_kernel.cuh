@@ -28,6 +28,9 @@
 #error "define TACO_VARIANT (fast / strict) before including fpv_step_kernel.cuh"
 #endif
 
+// difficulty-dependent scalars: by-value kernel parameters, or -- in graph mode -- their device copy (step_params.h)
+#define TACO_DIFF(field, idx) (p.diff_dev ? __ldg(p.diff_dev + (idx)) : p.field)
+
 namespace taco {
 namespace TACO_VARIANT {   // distinct symbols per translation unit: the two builds must not be merged by the linker
 
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
             const long long gg = p.env_offset + i;
             task = gg < p.mix_n1 ? TACO_TASK_POS : (gg < p.mix_n2 ? TACO_TASK_ROTATE : TACO_TASK_FLIP);
         }
-        const float d = p.difficulty;
+        const float d = TACO_DIFF(difficulty, 0);
         const bool at500 = (progress == 500);                   // fpv_asymmetry.py:152,597 (before counters clear)
 
         // pending-action runs live in a ring indexed by the RL step of the LAUNCH (slot = step_index & 15, the same for
@@ -171,8 +174,8 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
             // copter position (:730-737, :788-793, :855-861, :993-1036)
             if (flags & TACO_F_RANDOM_COPTER_POS) {
                 if (flip_env && !is_mix) {
-                    pos.x = rr(p.flip_xy_rng, p.flip_xy_lo, u01(b0.x));
-                    pos.y = rr(p.flip_xy_rng, p.flip_xy_lo, u01(b0.y));
+                    pos.x = rr(TACO_DIFF(flip_xy_rng, 1), TACO_DIFF(flip_xy_lo, 2), u01(b0.x));
+                    pos.y = rr(TACO_DIFF(flip_xy_rng, 1), TACO_DIFF(flip_xy_lo, 2), u01(b0.y));
                     pos.z = 3.0f + d * rr(4.0f, -2.0f, u01(b0.z));
                 } else {
                     pos.x = rr(4.0f, -2.0f, u01(b0.x));
@@ -196,8 +199,8 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
             // velocities (:745-750, :869-878, :1042-1050): flip keeps stale w_y, w_z
             if (flags & TACO_F_RANDOM_COPTER_VEL) {
                 if (flip_env) {
-                    vel = v3(rr(p.flip_lin_rng, p.flip_lin_lo, u01(b2.x)), rr(p.flip_lin_rng, p.flip_lin_lo, u01(b2.y)),
-                             rr(p.flip_lin_rng, p.flip_lin_lo, u01(b2.z)));
+                    vel = v3(rr(TACO_DIFF(flip_lin_rng, 3), TACO_DIFF(flip_lin_lo, 4), u01(b2.x)), rr(TACO_DIFF(flip_lin_rng, 3), TACO_DIFF(flip_lin_lo, 4), u01(b2.y)),
+                             rr(TACO_DIFF(flip_lin_rng, 3), TACO_DIFF(flip_lin_lo, 4), u01(b2.z)));
                     wld.x = 10.0f * ((b0.w >> 31) ? 1.0f : -1.0f);
                 } else {
                     vel = v3(3.0f * rr(2.0f, -1.0f, u01(b2.x)), 3.0f * rr(2.0f, -1.0f, u01(b2.y)), 3.0f * rr(2.0f, -1.0f, u01(b2.z)));
@@ -218,11 +221,11 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
                 const uint4 b7 = philox4x32_10(g, t_rl, 7, STREAM_RESET, k0, k1);
                 const uint4 b8 = philox4x32_10(g, t_rl, 8, STREAM_RESET, k0, k1);
                 if (flags & TACO_F_RANDOM_ROTORDYNAMIC_COE) {     // thrust_dynamics.py:117-122
-                    poly[0] = kPolyNom[0] * rr(p.dr_rng, p.dr_lo, u01(b5.x));
-                    poly[1] = kPolyNom[1] * rr(p.dr_rng, p.dr_lo, u01(b5.y));
-                    poly[2] = kPolyNom[2] * rr(p.dr_rng, p.dr_lo, u01(b5.z));
-                    poly[3] = kPolyNom[3] * rr(p.dr_rng, p.dr_lo, u01(b5.w));
-                    poly[4] = kPolyNom[4] * rr(p.dr_rng, p.dr_lo, u01(b6.x));
+                    poly[0] = kPolyNom[0] * rr(TACO_DIFF(dr_rng, 5), TACO_DIFF(dr_lo, 6), u01(b5.x));
+                    poly[1] = kPolyNom[1] * rr(TACO_DIFF(dr_rng, 5), TACO_DIFF(dr_lo, 6), u01(b5.y));
+                    poly[2] = kPolyNom[2] * rr(TACO_DIFF(dr_rng, 5), TACO_DIFF(dr_lo, 6), u01(b5.z));
+                    poly[3] = kPolyNom[3] * rr(TACO_DIFF(dr_rng, 5), TACO_DIFF(dr_lo, 6), u01(b5.w));
+                    poly[4] = kPolyNom[4] * rr(TACO_DIFF(dr_rng, 5), TACO_DIFF(dr_lo, 6), u01(b6.x));
                 } else {
 #pragma unroll
                     for (int j = 0; j < 5; ++j) poly[j] = kPolyNom[j];
@@ -237,11 +240,11 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
                     for (int j = 0; j < 4; ++j) lag[j] = p.lag_gain_fixed;
                 }
                 if (flags & TACO_F_RANDOM_AERODYNAMIC_COE) {      // thrust_dynamics.py:201-210
-                    aero[0] = kAeroNom[0] * rr(p.dr_rng, p.dr_lo, u01(b6.y));
-                    aero[1] = kAeroNom[1] * rr(p.dr_rng, p.dr_lo, u01(b6.z));
-                    aero[2] = kAeroNom[2] * rr(p.dr_rng, p.dr_lo, u01(b6.w));
-                    aero[3] = kAeroNom[3] * rr(p.dr_rng, p.dr_lo, u01(b7.x));
-                    aero[4] = kAeroNom[4] * rr(p.dr_rng, p.dr_lo, u01(b7.y));
+                    aero[0] = kAeroNom[0] * rr(TACO_DIFF(dr_rng, 5), TACO_DIFF(dr_lo, 6), u01(b6.y));
+                    aero[1] = kAeroNom[1] * rr(TACO_DIFF(dr_rng, 5), TACO_DIFF(dr_lo, 6), u01(b6.z));
+                    aero[2] = kAeroNom[2] * rr(TACO_DIFF(dr_rng, 5), TACO_DIFF(dr_lo, 6), u01(b6.w));
+                    aero[3] = kAeroNom[3] * rr(TACO_DIFF(dr_rng, 5), TACO_DIFF(dr_lo, 6), u01(b7.x));
+                    aero[4] = kAeroNom[4] * rr(TACO_DIFF(dr_rng, 5), TACO_DIFF(dr_lo, 6), u01(b7.y));
                 } else {
 #pragma unroll
                     for (int j = 0; j < 5; ++j) aero[j] = kAeroNom[j];
@@ -535,8 +538,8 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
             }
             fn[18] = fc[18] + d * (z[9] * su_);
             fn[23] = fc[23] + d * (z[10] * sh_);
-            const Q4 nq = quat_from_euler(rr(p.noise_rng, p.noise_lo, u01(ub.x)), rr(p.noise_rng, p.noise_lo, u01(ub.y)),
-                                          rr(p.noise_rng, p.noise_lo, u01(ub.z)));
+            const Q4 nq = quat_from_euler(rr(TACO_DIFF(noise_rng, 7), TACO_DIFF(noise_lo, 8), u01(ub.x)), rr(TACO_DIFF(noise_rng, 7), TACO_DIFF(noise_lo, 8), u01(ub.y)),
+                                          rr(TACO_DIFF(noise_rng, 7), TACO_DIFF(noise_lo, 8), u01(ub.z)));
             float mn[9];
             rotmat9(qmul(rq, nq), mn);
 #pragma unroll

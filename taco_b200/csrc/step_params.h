@@ -28,6 +28,10 @@ struct StepParams {
     float dt, inv_dt, h, half_h, half_h2, c_sin3, c_sin5, c_cos4, inv_mass, difficulty, clip_actions;
     // host-precomputed (double -> float) bounds of the difficulty-dependent uniform draws
     float flip_xy_rng, flip_xy_lo, flip_lin_rng, flip_lin_lo, dr_rng, dr_lo, tau_rng, tau_lo, noise_rng, noise_lo;
+    // graph mode only (else null): device copy of [difficulty, flip_xy_rng, flip_xy_lo, flip_lin_rng, flip_lin_lo, dr_rng, dr_lo,
+    // noise_rng, noise_lo], rewritten by taco_env_set_difficulty -- a launch captured in a CUDA graph freezes the by-value
+    // fields above, and the trainer changes the difficulty every epoch (ppo_asymmetry.py:173-175)
+    const float* diff_dev;
     float lag_gain_fixed;          // 0.001 / rotor_response_time (or 1.0 when rotor_response is off)
     int has_dr;                    // per-env DR planes are live
     // inputs / state / outputs (device)

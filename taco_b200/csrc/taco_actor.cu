@@ -195,7 +195,33 @@ struct TacoActor {
     TcLayer tc_layer[kMaxHidden + 1];    // hidden layers + the output layer (16-row padded image)
     int num_sms = 148;
     int fp_smem = 0;
+    // sampling constants [std0..3, logp_const, pad]: device copy read by the kernels, host copy to detect changes
+    float* samp_dev = nullptr;
+    float samp_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool samp_set = false;
 };
+
+// std = exp(log_std)^2 in float32 (nets_asymmetry.py:338) and the constant of the log-probability; uploads when they changed
+static int actor_set_log_std(TacoActor* a, const float* log_std_host, cudaStream_t s) {
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int out = a->sizes.back();
+    double lsum = 0.0;
+    for (int o = 0; o < out; ++o) {
+        const float e = expf(log_std_host[o]);
+        v[o] = e * e;
+        lsum += std::log((double)v[o]);
+    }
+    v[4] = (float)(-lsum - 0.5 * out * std::log(2.0 * M_PI));
+    if (a->samp_set && memcmp(v, a->samp_host, sizeof(v)) == 0) return TACO_OK;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    ACT_CUDA(cudaStreamIsCapturing(s, &cs));
+    if (cs != cudaStreamCaptureStatusNone)
+        return afail(TACO_E_INVALID, "taco_actor: log_std changed while the stream is capturing; call taco_actor_set_log_std before the capture");
+    memcpy(a->samp_host, v, sizeof(v));
+    ACT_CUDA(cudaMemcpyAsync(a->samp_dev, a->samp_host, sizeof(v), cudaMemcpyHostToDevice, s));   // pageable source: staged before the call returns
+    a->samp_set = true;
+    return TACO_OK;
+}
 
 static int actor_run(TacoActor* a, const float* obs_dev, float* mean_dev, int32_t n, int32_t use_tc, const SampleParams& sp, void* stream) {
     if (!a || !obs_dev || !mean_dev) return afail(TACO_E_INVALID, "taco_actor: null argument");
@@ -293,6 +319,7 @@ int taco_actor_create(int device, const int32_t* sizes, int32_t n_sizes, TacoAct
     if (ce == cudaSuccess) ce = cudaMalloc(&a->b_f32, bo * sizeof(float));
     if (ce == cudaSuccess) ce = cudaMalloc(&a->sigma, kMaxLayers * sizeof(double));
     if (ce == cudaSuccess) ce = cudaMemset(a->sigma, 0, kMaxLayers * sizeof(double));
+    if (ce == cudaSuccess) ce = cudaMalloc(&a->samp_dev, 8 * sizeof(float));
     if (ce == cudaSuccess && a->tc_ok) {
         size_t img = 0;
         for (int l = 0; l <= n_hidden; ++l) {
@@ -320,7 +347,7 @@ int taco_actor_create(int device, const int32_t* sizes, int32_t n_sizes, TacoAct
 int taco_actor_destroy(TacoActor* a) {
     if (!a) return TACO_OK;
     DevGuard guard(a->device);
-    cudaFree(a->w_f32); cudaFree(a->b_f32); cudaFree(a->sigma);
+    cudaFree(a->w_f32); cudaFree(a->b_f32); cudaFree(a->sigma); cudaFree(a->samp_dev);
     cudaFree(a->wimg); cudaFree(a->bias_pad); cudaFree(a->b_out);
     delete a;
     return TACO_OK;
@@ -405,24 +432,28 @@ int taco_actor_forward(TacoActor* a, const float* obs_dev, float* mean_dev, int3
 int taco_actor_act_counter(TacoActor* a, const float* obs_dev, int32_t n, const float* log_std_host, int64_t env_offset, uint64_t seed,
                            uint32_t step_index, const uint32_t* step_base_dev, float* mean_dev, float* action_dev, float* clipped_dev,
                            float* logp_dev, int32_t use_tensor_cores, void* stream) {
-    if (!a || !log_std_host || !action_dev) return afail(TACO_E_INVALID, "taco_actor_act: null argument");
+    if (!a || !action_dev) return afail(TACO_E_INVALID, "taco_actor_act: null argument");
+    if (!log_std_host && !a->samp_set) return afail(TACO_E_INVALID, "taco_actor_act: no log_std given and taco_actor_set_log_std was never called");
+    DevGuard guard(a->device);
+    if (log_std_host) {
+        const int rc = actor_set_log_std(a, log_std_host, (cudaStream_t)stream);
+        if (rc != TACO_OK) return rc;
+    }
     SampleParams sp;
     memset(&sp, 0, sizeof(sp));
     sp.action = action_dev; sp.clipped = clipped_dev; sp.logp = logp_dev;
-    const int out = a->sizes.back();
-    double lsum = 0.0;
-    for (int o = 0; o < out; ++o) {
-        // scale_tril = diag(exp(log_std) * exp(log_std)) in float32 (nets_asymmetry.py:338)
-        const float e = expf(log_std_host[o]);
-        sp.std_[o] = e * e;
-        lsum += std::log((double)sp.std_[o]);
-    }
-    sp.logp_const = (float)(-lsum - 0.5 * out * std::log(2.0 * M_PI));
+    sp.samp = a->samp_dev;
     sp.env_offset = env_offset;
     sp.seed_lo = (uint32_t)(seed & 0xFFFFFFFFull); sp.seed_hi = (uint32_t)(seed >> 32);
     sp.step_index = step_index;
     sp.step_base = step_base_dev;
     return actor_run(a, obs_dev, mean_dev, n, use_tensor_cores, sp, stream);
+}
+
+int taco_actor_set_log_std(TacoActor* a, const float* log_std_host, void* stream) {
+    if (!a || !log_std_host) return afail(TACO_E_INVALID, "taco_actor_set_log_std: null argument");
+    DevGuard guard(a->device);
+    return actor_set_log_std(a, log_std_host, (cudaStream_t)stream);
 }
 
 int taco_actor_act(TacoActor* a, const float* obs_dev, int32_t n, const float* log_std_host, int64_t env_offset, uint64_t seed,

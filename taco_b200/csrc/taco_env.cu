@@ -61,6 +61,7 @@ struct TacoEnv {
     // graph mode (taco_env_graph_begin .. _end): the step index of a launch = *step_counter (device) + its offset since
     // graph_begin, so a CUDA graph captured over a rollout replays with fresh Philox counters / queue time slots
     uint32_t* step_counter = nullptr;   // device, one word
+    float* diff_dev = nullptr;          // device, 9 floats (upload_derived)
     bool graph_mode = false;
     uint32_t graph_origin = 0;
     // host-buffer pipeline (taco_env_step_host): copy-in / kernel / copy-out of successive env chunks overlap
@@ -88,6 +89,14 @@ static void refresh_derived(TacoEnv* e) {
     const double nl = d * 0.05;
     p.noise_rng = (float)(nl - (-nl)); p.noise_lo = (float)(-nl);
     p.difficulty = e->cfg.difficulty;
+}
+
+// the device copy of the difficulty-dependent scalars that launches captured in a CUDA graph read (StepParams::diff_dev)
+static cudaError_t upload_derived(TacoEnv* e) {
+    if (!e->diff_dev) return cudaSuccess;
+    const StepParams& p = e->p;
+    const float v[9] = {p.difficulty, p.flip_xy_rng, p.flip_xy_lo, p.flip_lin_rng, p.flip_lin_lo, p.dr_rng, p.dr_lo, p.noise_rng, p.noise_lo};
+    return cudaMemcpy(e->diff_dev, v, sizeof(v), cudaMemcpyHostToDevice);
 }
 
 // ---- small utility kernels -----------------------------------------------------------------
@@ -361,6 +370,7 @@ int taco_env_destroy(TacoEnv* env) {
     if (env->export_stage) cudaFree(env->export_stage);
     if (env->arena) cudaFree(env->arena);
     if (env->step_counter) cudaFree(env->step_counter);
+    if (env->diff_dev) cudaFree(env->diff_dev);
     delete env;
     return TACO_OK;
 }
@@ -555,10 +565,13 @@ int taco_env_graph_begin(TacoEnv* env, void* stream) {
     if (!env) return fail(TACO_E_INVALID, "taco_env_graph_begin: null argument");
     DeviceGuard guard(env->device);
     if (!env->step_counter) TACO_CUDA(cudaMalloc(&env->step_counter, sizeof(uint32_t)));
+    if (!env->diff_dev) TACO_CUDA(cudaMalloc(&env->diff_dev, 9 * sizeof(float)));
+    TACO_CUDA(upload_derived(env));
     step_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->step_counter, env->step_index, 0);
     TACO_CUDA(cudaGetLastError());
     env->graph_mode = true;
     env->graph_origin = env->step_index;
+    env->p.diff_dev = env->diff_dev;
     return TACO_OK;
 }
 
@@ -579,6 +592,7 @@ int taco_env_graph_end(TacoEnv* env, void* stream) {
     TACO_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     env->step_index = v;
     env->graph_mode = false;
+    env->p.diff_dev = nullptr;
     return TACO_OK;
 }
 
@@ -656,6 +670,7 @@ int taco_env_reset_all(TacoEnv* env, void* stream) {
     TACO_CUDA(cudaGetLastError());
     env->step_index = 0;
     env->graph_mode = false;                                         // host-side counting again; taco_env_graph_begin re-arms
+    env->p.diff_dev = nullptr;
     return TACO_OK;
 }
 
@@ -663,6 +678,8 @@ int taco_env_set_difficulty(TacoEnv* env, float difficulty) {
     if (!env) return fail(TACO_E_INVALID, "taco_env_set_difficulty: null argument");
     env->cfg.difficulty = difficulty;
     refresh_derived(env);
+    DeviceGuard guard(env->device);
+    TACO_CUDA(upload_derived(env));       // captured launches (graph mode) read the device copy
     return TACO_OK;
 }
 

@@ -229,6 +229,10 @@ class FpvVecTask:
             raise ValueError("RolloutBuffer shape does not match the env")
         if buffer.device_id != self.device_id:
             raise ValueError("RolloutBuffer is on another device")
+        if not (math.isinf(self.clip_obs) and math.isinf(self.clip_states)):
+            # step() returns clamp(obs_buf) / clamp(states_buf) (vec_task_asymmetry.py:331-332); the ring holds the raw history that
+            # actor, critic and the update read in place, so a finite clip would silently diverge from the drop-in path
+            raise ValueError("attach_rollout: clipObservations / clipStates must be inf for the zero-copy rollout path")
         if self.rollout_buffer is not None:
             self.detach_rollout()
         stream = torch.cuda.current_stream(self.device_id).cuda_stream

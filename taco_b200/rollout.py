@@ -124,6 +124,19 @@ class RolloutBuffer:
         return torch.randperm(n).reshape(self.mini_batch_num, -1).tolist()
 
 
+_warned_fp32 = set()
+
+
+def _warn_fp32_fallback(actor_tc, critic_tc):
+    """The FP32 CUDA-core kernels are the parity path: 70-100x slower than the tcgen05 kernels at large env counts.  Say so once."""
+    import warnings
+    which = tuple(n for n, ok in (("actor", actor_tc), ("critic", critic_tc)) if not ok)
+    if which and which not in _warned_fp32:
+        _warned_fp32.add(which)
+        warnings.warn(f"taco_b200: the {' and '.join(which)} shape is outside the tcgen05 kernels' envelope (see include/taco_b200.h); "
+                      "falling back to the FP32 CUDA-core kernel, which is 70-100x slower at large env counts", RuntimeWarning, stacklevel=3)
+
+
 def collect_rollout(env, actor, buffer, value_fn, seed=0, tensor_cores=True, group=None):
     """One rollout of ``buffer.horizon_len`` steps: the data-collection loop of ``PPO.run``
     (IsaacGymEnvs/algorithms/ppo_asymmetry.py:305-342) with no host round trip inside it.
@@ -146,10 +159,13 @@ def collect_rollout(env, actor, buffer, value_fn, seed=0, tensor_cores=True, gro
     sigma = torch.from_numpy(actor.log_std).to(buffer.device).expand(buffer.num_envs, -1)     # act() returns log_std as `sigma`
     native_critic = isinstance(value_fn, CriticLSTM)
     critic_tc = native_critic and tensor_cores and value_fn.tensor_cores_available
+    actor_tc = bool(tensor_cores and actor.tensor_cores_available)        # shapes the tcgen05 kernel rejects use the FP32 kernel
+    if tensor_cores and not (actor_tc and (critic_tc or not native_critic)):
+        _warn_fp32_fallback(actor_tc, critic_tc or not native_critic)
     for s in range(H):
         obs, states = buffer.obs_ring[s], buffer.states_ring[s]
         out = buffer.rows(s)
-        actor.act(obs, env.step_count, seed=seed, env_offset=env.env_offset, tensor_cores=tensor_cores, out=out)
+        actor.act(obs, env.step_count, seed=seed, env_offset=env.env_offset, tensor_cores=actor_tc, out=out)
         if native_critic:
             value = value_fn.forward(states, tensor_cores=critic_tc, out=buffer.value_buf[s])
         else:
@@ -174,7 +190,8 @@ class GraphedRollout:
 
     The constructor collects the first rollout eagerly (``first_stats``); every ``run()`` is one more.
     ``critic`` must be a ``CriticLSTM``; weights may be reloaded between replays (``ActorMLP.load`` / ``CriticLSTM.load`` write the
-    same device buffers), ``actor.log_std`` is frozen at capture.  Single-process statistics / advantage normalisation are inside the
+    same device buffers, ``ActorMLP.set_log_std`` the sampler constants the captured kernels read from device memory) and
+    ``env.difficulty`` may be set between replays (graph-mode launches read its device copy).  Single-process statistics / advantage normalisation are inside the
     graph; under torch.distributed the two small all-reduces run after the replay."""
 
     def __init__(self, env, actor, buffer, critic, seed=0, tensor_cores=True, group=None):

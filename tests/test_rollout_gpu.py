@@ -129,7 +129,8 @@ def test_collect_rollout_with_native_critic(tensor_cores):
 @pytest.mark.parametrize("task,dr", [("flip", False), ("mix", True)])
 def test_graphed_rollout_replays_are_bit_identical_to_the_eager_loop(task, dr):
     """GraphedRollout: the whole rollout as one CUDA-graph replay, the step index in a device counter.  Three rollouts (one eager
-    in the constructor + two replays, weights reloaded in between) equal three eager collect_rollout calls bit for bit."""
+    in the constructor + two replays; weights, log_std and the env difficulty changed in between) equal three eager collect_rollout
+    calls bit for bit."""
     from taco_b200 import ActorMLP, CriticLSTM, FpvVecTask, GraphedRollout, RolloutBuffer, collect_rollout, make_cfg
     n, H = 3000, 7
     gen = torch.Generator().manual_seed(2)
@@ -151,7 +152,10 @@ def test_graphed_rollout_replays_are_bit_identical_to_the_eager_loop(task, dr):
         snaps, gr = [], None
         for k in range(3):
             if k == 2:
-                actor.load(aw[1], ab, log_std=torch.full((4,), -0.3))           # new weights reach the replayed kernels
+                # new weights, a new log_std (a trained nn.Parameter in the reference, nets_asymmetry.py:315) and a new difficulty
+                # (written by the trainer every epoch, ppo_asymmetry.py:173-175) all reach the replayed kernels
+                actor.load(aw[1], ab, log_std=torch.full((4,), -0.55))
+                env.difficulty = 0.35
             if mode == "eager":
                 stats = collect_rollout(env, actor, buf, critic, seed=4, tensor_cores=True)
             elif k == 0:

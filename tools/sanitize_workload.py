@@ -1,0 +1,75 @@
+"""Small workload for compute-sanitizer (memcheck / racecheck / synccheck / initcheck): every hand-written kernel
+on shapes that exercise its edge paths.  usage: compute-sanitizer --tool <tool> python tools/sanitize_workload.py [part]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import taco_b200  # noqa: E402
+from taco_b200 import ActorMLP, CriticLSTM, RolloutBuffer, make_cfg  # noqa: E402
+
+part = sys.argv[1] if len(sys.argv) > 1 else "all"
+gen = torch.Generator().manual_seed(0)
+
+
+def step_part():
+    # ragged env counts (not a multiple of the 128-env CTA), every DR / noise switch, all four tasks
+    for task, n, kw in (("mix", 1000, dict(domain_randomization=True, observation_noise=True, rotor_noise=True)),
+                        ("flip", 129, {}), ("rotate", 1, {}), ("pos", 4096 + 77, {})):
+        env = taco_b200.FpvVecTask(make_cfg(task, n, **kw), "cuda:0", "cuda:0", -1, True, seed=3)
+        env.reset()
+        for t in range(3):
+            env.step(env.random_actions(t))
+        env.stats()
+        torch.cuda.synchronize()
+        env.close()
+    print("step ok")
+
+
+def nets_part():
+    sizes = [26, 256, 256, 256, 4]
+    ws = [torch.randn(sizes[i + 1], sizes[i], generator=gen) / sizes[i] ** 0.5 for i in range(4)]
+    bs = [torch.randn(sizes[i + 1], generator=gen) * 0.1 for i in range(4)]
+    actor = ActorMLP(26, sizes[1:-1], 4)
+    actor.load(ws, bs, lipschitz_const=4.0)
+    hid, mlp = 64, [256, 256, 256]
+    lstm = [(torch.randn(4 * hid, 26, generator=gen) * 0.3, torch.randn(4 * hid, hid, generator=gen) * 0.2,
+             torch.randn(4 * hid, generator=gen) * 0.1, torch.randn(4 * hid, generator=gen) * 0.1)]
+    cs = [hid] + mlp + [1]
+    cw = [torch.randn(cs[i + 1], cs[i], generator=gen) / cs[i] ** 0.5 for i in range(4)]
+    cb = [torch.randn(cs[i + 1], generator=gen) * 0.1 for i in range(4)]
+    critic = CriticLSTM(26, 5, hid, mlp)
+    critic.load(lstm, cw, cb)
+    # 1000 envs: one tile per CTA, partial last tile; 148*2*128 + 77: a pair of tiles per CTA, partial last tile
+    for n in (1000, 148 * 2 * 128 + 77):
+        obs = torch.randn(n, 1, 26, generator=gen).cuda()
+        states = torch.randn(n, 5, 26, generator=gen).cuda()
+        for tc in (True, False):
+            if not tc and n > 2000:
+                continue
+            actor.forward(obs, tensor_cores=tc)
+            actor.act(obs, step_index=1, tensor_cores=tc)
+            critic.forward(states, tensor_cores=tc)
+        torch.cuda.synchronize()
+    actor.close(); critic.close()
+    print("nets ok")
+
+
+def gae_part():
+    H, N = 6, 500
+    buf = RolloutBuffer(N, 26, 1, 26, 5, 4, H, 1, 0.99, 0.95, "cuda:0")
+    buf.rew_buf.copy_(torch.rand(H, N, 1, generator=gen) * 0.02)
+    buf.value_buf.copy_(torch.randn(H, N, 1, generator=gen) * 0.3)
+    buf.done_buf.copy_((torch.rand(H, N, 1, generator=gen) < 0.1).float())
+    buf.compute_returns_and_advantage((torch.randn(N, 1, generator=gen) * 0.3).cuda())
+    torch.cuda.synchronize()
+    print("gae ok")
+
+
+if part in ("all", "step"):
+    step_part()
+if part in ("all", "nets"):
+    nets_part()
+if part in ("all", "gae"):
+    gae_part()
