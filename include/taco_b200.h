@@ -147,6 +147,7 @@ int taco_env_detach_rollout(TacoEnv* env, void* stream);
 int taco_env_rollout_cursor(TacoEnv* env);   /* newest slot index, or -1 when no ring is attached */
 /* -- env.difficulty is written by the trainer every epoch (algorithms/ppo_asymmetry.py:173-175) */
 int taco_env_set_difficulty(TacoEnv* env, float difficulty);
+int taco_env_get_difficulty(TacoEnv* env, float* out);
 int taco_env_set_seed(TacoEnv* env, uint64_t seed);
 
 /* -- rollout statistics accumulated on the device since the last call (ppo_asymmetry.py:313-339):
@@ -161,6 +162,15 @@ int taco_env_fill_random_actions(TacoEnv* env, float* actions_dev, uint32_t step
 /* -- test / checkpoint access: TACO_STATE_WORDS floats per env, layout in DESIGN.md (host pointers) */
 int taco_env_export_state(TacoEnv* env, float* out_host);
 int taco_env_import_state(TacoEnv* env, const float* in_host);
+/* -- env-state checkpoint (the reference never checkpoints the env): everything the next step depends on --
+ * state and DR planes, pending-action ring, observation / state history, reward / reset / time-out buffers, step index,
+ * difficulty, seed -- as one opaque host blob of taco_env_checkpoint_size bytes.  A loaded env continues bit-identically.  The
+ * target env must have been created with the same TacoCfg (difficulty and seed are taken from the checkpoint).  Synchronous; not
+ * allowed while a rollout ring is attached or in graph mode.  taco_env_import_state keeps the pending-action ring consistent when
+ * it changes an env's progress counter (the run end slots are rebased to the new 10 * progress clock). */
+int taco_env_checkpoint_size(TacoEnv* env, uint64_t* bytes);
+int taco_env_checkpoint_save(TacoEnv* env, void* out_host, uint64_t bytes);
+int taco_env_checkpoint_load(TacoEnv* env, const void* in_host, uint64_t bytes);
 /* delayed action read at each control sub-step of the last step: (num_envs, control_freq_inv, 4) f32, host */
 int taco_env_debug_delay(TacoEnv* env, float* out_host);
 

@@ -90,6 +90,10 @@ def lib():
         "taco_actor_weights": (C.c_int, [vp, i32, vp, vp]),
         "taco_actor_tc_available": (C.c_int, [vp]),
         "taco_actor_set_log_std": (C.c_int, [vp, vp, vp]),
+        "taco_env_get_difficulty": (C.c_int, [vp, C.POINTER(f32)]),
+        "taco_env_checkpoint_size": (C.c_int, [vp, C.POINTER(u64)]),
+        "taco_env_checkpoint_save": (C.c_int, [vp, vp, u64]),
+        "taco_env_checkpoint_load": (C.c_int, [vp, vp, u64]),
         "taco_spectral_project": (C.c_int, [C.c_int, vp, i32, i32, f32, vp, vp]),
         "taco_actor_act": (C.c_int, [vp, vp, i32, vp, C.c_int64, u64, u32, vp, vp, vp, vp, i32, vp]),
         "taco_critic_create": (C.c_int, [C.c_int, i32, i32, i32, i32, C.POINTER(i32), i32, C.POINTER(vp)]),

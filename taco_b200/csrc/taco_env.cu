@@ -191,9 +191,17 @@ __global__ void import_state_kernel(StepParams p, const float* in) {
     p.S[5][i] = make_float4(o[22], o[23], o[24], o[25]);
     p.S[6][i] = make_float4(o[26], o[27], o[28], o[29]);
     p.S[7][i] = make_float4(o[30], o[31], o[32], o[33]);
+    // the pending-action runs themselves are not imported (only their scalar meta: length / counts), but their end slots are kept
+    // on the absolute clock 10 * progress (fpv_step_kernel.cuh): a changed progress counter rebases them
+    const int shift = 10 * ((int)o[34] - p.progress[i]);
+    if (shift != 0)
+        for (int k = 0; k < kQueueCap; ++k) {
+            const size_t j = (size_t)k * p.n_pad + i;
+            const int e = (int)p.qend[j] + shift;
+            p.qend[j] = (uint16_t)(e < 0 ? 0 : (e > 65535 ? 65535 : e));
+        }
     p.progress[i] = (int)o[34];
     p.reset_buf[i] = (long long)o[38];
-    // the pending-action queue itself is not imported: only its scalar meta (length / counts) is restored
     p.qmeta[i] = (((uint32_t)o[36] & 31u) << QM_N_SHIFT) |
                  (((uint32_t)o[35] & 2047u) << QM_LEN_SHIFT) | (((uint32_t)o[37] & 1u) << QM_OVF_SHIFT);
     if (p.has_dr) {
@@ -683,6 +691,12 @@ int taco_env_set_difficulty(TacoEnv* env, float difficulty) {
     return TACO_OK;
 }
 
+int taco_env_get_difficulty(TacoEnv* env, float* out) {
+    if (!env || !out) return fail(TACO_E_INVALID, "taco_env_get_difficulty: null argument");
+    *out = env->cfg.difficulty;
+    return TACO_OK;
+}
+
 int taco_env_set_seed(TacoEnv* env, uint64_t seed) {
     if (!env) return fail(TACO_E_INVALID, "taco_env_set_seed: null argument");
     env->cfg.seed = seed;
@@ -735,6 +749,61 @@ int taco_env_import_state(TacoEnv* env, const float* in_host) {
     import_state_kernel<<<(env->n + 255) / 256, 256>>>(env->p, env->export_stage);
     TACO_CUDA(cudaGetLastError());
     TACO_CUDA(cudaDeviceSynchronize());
+    return TACO_OK;
+}
+
+// ---- env-state checkpoint: the whole device arena (SoA state planes, DR planes, pending-action ring, reward / reset / time-out
+// buffers, both observation / state history buffers, statistics partials) + a header.  The reference never checkpoints the env
+// (SURVEY.md section 5); here a resumed run continues bit-identically.
+struct CkptHeader {
+    char magic[8];              // "TACOENV1"
+    uint64_t arena_bytes;
+    TacoCfg cfg;                // must match the env's (difficulty and seed are restored from the checkpoint)
+    uint32_t step_index;
+    int32_t cur;
+};
+
+int taco_env_checkpoint_size(TacoEnv* env, uint64_t* bytes) {
+    if (!env || !bytes) return fail(TACO_E_INVALID, "taco_env_checkpoint_size: null argument");
+    *bytes = sizeof(CkptHeader) + env->arena_bytes;
+    return TACO_OK;
+}
+
+int taco_env_checkpoint_save(TacoEnv* env, void* out_host, uint64_t bytes) {
+    if (!env || !out_host) return fail(TACO_E_INVALID, "taco_env_checkpoint_save: null argument");
+    if (bytes != sizeof(CkptHeader) + env->arena_bytes) return fail(TACO_E_INVALID, "taco_env_checkpoint_save: wrong buffer size (taco_env_checkpoint_size)");
+    if (env->ring_slots || env->graph_mode) return fail(TACO_E_INVALID, "taco_env_checkpoint_save: detach the rollout ring / leave graph mode first");
+    DeviceGuard guard(env->device);
+    CkptHeader h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.magic, "TACOENV1", 8);
+    h.arena_bytes = env->arena_bytes; h.cfg = env->cfg; h.step_index = env->step_index; h.cur = env->cur;
+    memcpy(out_host, &h, sizeof(h));
+    TACO_CUDA(cudaDeviceSynchronize());
+    TACO_CUDA(cudaMemcpy((char*)out_host + sizeof(h), env->arena, env->arena_bytes, cudaMemcpyDeviceToHost));
+    return TACO_OK;
+}
+
+int taco_env_checkpoint_load(TacoEnv* env, const void* in_host, uint64_t bytes) {
+    if (!env || !in_host) return fail(TACO_E_INVALID, "taco_env_checkpoint_load: null argument");
+    if (bytes < sizeof(CkptHeader)) return fail(TACO_E_INVALID, "taco_env_checkpoint_load: truncated checkpoint");
+    if (env->ring_slots || env->graph_mode) return fail(TACO_E_INVALID, "taco_env_checkpoint_load: detach the rollout ring / leave graph mode first");
+    CkptHeader h;
+    memcpy(&h, in_host, sizeof(h));
+    if (memcmp(h.magic, "TACOENV1", 8) != 0) return fail(TACO_E_INVALID, "taco_env_checkpoint_load: not a taco env checkpoint");
+    if (h.arena_bytes != env->arena_bytes || bytes != sizeof(CkptHeader) + h.arena_bytes)
+        return fail(TACO_E_INVALID, "taco_env_checkpoint_load: checkpoint size does not match this env");
+    TacoCfg a = h.cfg, b = env->cfg;
+    a.difficulty = b.difficulty = 0.f; a.seed = b.seed = 0;
+    if (memcmp(&a, &b, sizeof(TacoCfg)) != 0) return fail(TACO_E_INVALID, "taco_env_checkpoint_load: the checkpoint was written by an env with another configuration");
+    DeviceGuard guard(env->device);
+    TACO_CUDA(cudaDeviceSynchronize());
+    TACO_CUDA(cudaMemcpy(env->arena, (const char*)in_host + sizeof(h), env->arena_bytes, cudaMemcpyHostToDevice));
+    env->step_index = h.step_index; env->cur = h.cur;
+    env->cfg.difficulty = h.cfg.difficulty;
+    refresh_derived(env);
+    TACO_CUDA(upload_derived(env));
+    taco_env_set_seed(env, h.cfg.seed);
     return TACO_OK;
 }
 

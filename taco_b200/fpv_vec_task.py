@@ -179,8 +179,11 @@ class FpvVecTask:
     def reset(self):
         """vec_task_asymmetry.py:352-361: returns the current (initially zero) buffers; the actual
         re-initialisation happens lazily at the start of the next step (reset_buf starts all ones)."""
-        self.obs_dict["obs"] = self._clamped(self.obs_buf, self.clip_obs).to(self.rl_device)
-        self.obs_dict["states"] = self._clamped(self.states_buf, self.clip_states).to(self.rl_device)
+        # Fresh tensors, like the reference's out-of-place clamp: PPO.run keeps these two as ITS persistent observation storage
+        # (``obs.copy_(next_obs)``, ppo_asymmetry.py:297-299,328-329) and stores them AFTER env.step (:326); a view of the
+        # library's ping-pong buffer would be overwritten by every second step.
+        self.obs_dict["obs"] = torch.clamp(self.obs_buf, -self.clip_obs, self.clip_obs).to(self.rl_device)
+        self.obs_dict["states"] = torch.clamp(self.states_buf, -self.clip_states, self.clip_states).to(self.rl_device)
         return self.obs_dict
 
     def step(self, actions):
@@ -322,6 +325,34 @@ class FpvVecTask:
         arr = np.ascontiguousarray(arr, dtype=np.float32)
         assert arr.shape == (self.num_envs, _capi.STATE_WORDS)
         _capi.check(self._lib.taco_env_import_state(self._h, arr.ctypes.data_as(C.c_void_p)), "taco_env_import_state")
+
+    def state_checkpoint(self):
+        """The complete env state (everything the next ``step`` depends on) as one uint8 numpy array; see ``load_state_checkpoint``."""
+        nbytes = C.c_uint64()
+        _capi.check(self._lib.taco_env_checkpoint_size(self._h, C.byref(nbytes)), "taco_env_checkpoint_size")
+        blob = np.empty(nbytes.value, dtype=np.uint8)
+        _capi.check(self._lib.taco_env_checkpoint_save(self._h, blob.ctypes.data_as(C.c_void_p), nbytes.value), "taco_env_checkpoint_save")
+        return blob
+
+    def load_state_checkpoint(self, blob):
+        """Restore a ``state_checkpoint()`` of an env with the same cfg: stepping continues bit-identically (same Philox step index,
+        pending-action ring, history buffers, difficulty and seed)."""
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        _capi.check(self._lib.taco_env_checkpoint_load(self._h, blob.ctypes.data_as(C.c_void_p), blob.size), "taco_env_checkpoint_load")
+        self._wrap_buffers()
+        self.step_count = self.step_counter()[1]
+        self._difficulty = self._read_difficulty()
+
+    def _read_difficulty(self):
+        d = C.c_float()
+        _capi.check(self._lib.taco_env_get_difficulty(self._h, C.byref(d)), "taco_env_get_difficulty")
+        return d.value
+
+    def save_state(self, path):
+        np.save(path, self.state_checkpoint(), allow_pickle=False)
+
+    def load_state(self, path):
+        self.load_state_checkpoint(np.load(path, allow_pickle=False))
 
     def debug_delay(self):
         out = np.empty((self.num_envs, self.control_freq_inv, 4), dtype=np.float32)

@@ -76,6 +76,10 @@ class TorchActorCritic(nn.Module):
         self.critic_mlp = _MLP(lstm_hidden, critic_hidden, 1, nn.Identity)
         self.critic_mlp.para_init()
 
+    def forward(self, actor_input):
+        """nets_asymmetry.py:379-387: the deterministic action mean; what ``export_actor`` traces."""
+        return self.actor_mlp(actor_input)
+
     def evaluate(self, actor_input, critic_input, actor_output):
         """nets_asymmetry.py:356-377.  MultivariateNormal(mean, scale_tril=diag(exp(log_std)^2)) written out: the standard
         deviation is exp(2 log_std)."""
@@ -241,3 +245,46 @@ def sync_rollout_nets(agent, actor=None, critic=None):
         actor.load_module(agent.actor_mlp, log_std=agent.log_std, lipschitz_const=-1.0)      # already projected by ppo_update: no norm measurement
     if critic is not None:
         critic.load_modules(agent.critic_encoder, agent.critic_mlp)
+
+
+# ------------------------------------------------------------------------------------------------ checkpoints / export
+def save_checkpoint(path, agent, optimizer=None, epoch=None, env=None, para_only=True, extra=None):
+    """``PPO.save`` (ppo_asymmetry.py:452-456): ``para_only=True`` writes ``agent.state_dict()`` exactly like the reference
+    (parameter names equal the reference's, so the file loads into a reference ``PPO_ActorCritic`` and vice versa);
+    ``para_only=False`` writes a resumable training checkpoint: state dict, optimiser state, epoch and -- which the reference
+    never saves -- the complete env state (``FpvVecTask.state_checkpoint``)."""
+    if para_only:
+        torch.save(agent.state_dict(), path)
+        return
+    blob = {"agent": agent.state_dict(), "optimizer": optimizer.state_dict() if optimizer is not None else None,
+            "epoch": epoch, "extra": extra}
+    if env is not None:
+        blob["env_state"] = torch.from_numpy(env.state_checkpoint())
+        blob["env_difficulty"] = env.difficulty
+    torch.save(blob, path)
+
+
+def load_checkpoint(path, agent, optimizer=None, env=None, map_location=None):
+    """Inverse of ``save_checkpoint`` (either form).  Returns the stored epoch (None for a bare state dict)."""
+    blob = torch.load(path, map_location=map_location, weights_only=True)
+    if "agent" not in blob:                                  # a bare state dict (para_only=True, or a reference model's)
+        agent.load_state_dict(blob)
+        return None
+    agent.load_state_dict(blob["agent"])
+    if optimizer is not None and blob.get("optimizer") is not None:
+        optimizer.load_state_dict(blob["optimizer"])
+    if env is not None and blob.get("env_state") is not None:
+        env.load_state_checkpoint(blob["env_state"].numpy())
+    return blob.get("epoch")
+
+
+def export_actor(agent, path, len_obs, num_obs, device="cuda:0"):
+    """``PPO.save_actor_as_pt`` (ppo_asymmetry.py:458-468): the deterministic policy (``forward`` = action mean) traced with
+    ``torch.jit.trace`` on a zero ``(1, len_obs, num_obs)`` observation and saved as TorchScript -- the file the reference deploys
+    (``actor_0.pt`` / ``actor_1.pt``).  Returns (eager output, traced output) on the probe input, which the reference prints."""
+    agent.eval()
+    obs = torch.zeros((1, len_obs, num_obs), device=device)
+    traced = torch.jit.trace(agent, obs)
+    traced.save(path)
+    with torch.no_grad():
+        return agent(obs), traced(torch.zeros((1, len_obs, num_obs), device=device))
