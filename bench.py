@@ -13,8 +13,10 @@ statistics vector at the end of the timed rollout.
 Prints ONE JSON line on rank 0.  `value` = device-resident throughput through FpvVecTask.step;
 `e2e` = the same step through the C ABI's host-buffer entry point (pinned-host actions H2D,
 rew/reset/time_outs D2H, every step); `roofline` = HBM roofline of the step kernel using the
-algorithmic bytes of SURVEY.md section 8(d); `cpu_baseline` = the oracle port (the reference's torch
-modules' arithmetic + restated glue) timed on this host's cores on a bounded sample.
+algorithmic bytes of SURVEY.md section 8(d); `sustained` = an internal 300-step window of the same workload with its own clock
+samples (independent of --steps); `cpu_baseline` = the oracle port (the reference's torch modules' arithmetic + restated glue,
+pinned to the reference's own classes by tests/golden/glue_*.npz) timed on this host's cores on a bounded sample of the SAME
+workload; `policy_loop`, `config3_mix_actor`, `config4_rotate`, `config5_mix_dr` = the other BASELINE.json workloads.
 """
 import argparse
 import json
@@ -48,14 +50,16 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=20)        # 20 warm-up steps
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=2 * 1024 * 1024)
     ap.add_argument("--task", default=TASK, choices=["pos", "rotate", "flip", "mix"])
     ap.add_argument("--dr", action="store_true", help="per-env domain randomisation (BASELINE config 5)")
     ap.add_argument("--fast-fp", action="store_true", help="time the FMA-contracted kernel build instead of the default strict (-fmad=false) one")
-    ap.add_argument("--cpu-envs", type=int, default=4096)
-    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--cpu-envs", type=int, default=262144, help="envs per step of the bounded CPU sample (a 4096-env step is dispatch-bound on the CPU)")
+    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip policy_loop / config4 / config5")
+    ap.add_argument("--horizon", type=int, default=32, help="rollout horizon of the policy_loop point (SURVEY.md section 8d suggests 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-small", action="store_true")
@@ -129,45 +133,80 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_baseline(task, n_envs, steps, warm=3, dr=False):
-    """The reference's CPU path for this hot path = its torch control/reward modules driven by the
-    restated FpvBase glue + our rigid-body stand-in (oracle/).  Timed with all host threads."""
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def workload_config(task, dr, n, world):
+    """The `config` object: identical in the GPU arm and in the --impl reference arm (what is measured, not how)."""
+    return {"workload": f"{task} task fused env step (BASELINE configs[1] scaled to {n} envs/GPU so the working set exceeds L2), "
+                        f"len_obs=1, len_states=5, delay_time=20, rotor_response_time=0.017, substeps=2, "
+                        f"{'per-env DR on' if dr else 'no per-env DR'}, U(-1,1) Philox actions",
+            "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-sharded x{world}",
+            "l2": "inputs larger than L2 (working set ~%.1f GB/GPU)" % (n * 1900 / 1e9)}
+
+
+def cpu_baseline(task, n_envs, steps, warm=1, dr=False, threads=None):
+    """The reference's CPU path for this hot path = its torch control/reward modules driven by the restated FpvBase glue (pinned to
+    the reference's own env classes, tests/golden/glue_*.npz) + our rigid-body stand-in (oracle/)."""
     import torch
     from oracle.fpv_env import RefFpvEnv
     from oracle import philox as px
     from taco_b200.config import make_cfg
     import numpy as np
-    threads = os.cpu_count() or 1
+    threads = threads or (os.cpu_count() or 1)
     torch.set_num_threads(threads)
     cfg = make_cfg(task, n_envs, domain_randomization=dr)
     env = RefFpvEnv(cfg, seed=SEED)
-    acts = [torch.from_numpy(px.u01(px.draw(SEED, env.gid, t, 0, px.STREAM_ACTIONS)) * np.float32(2) - np.float32(1)) for t in range(warm + steps)]
+    n_act = min(warm + steps, 4)
+    acts = [torch.from_numpy(px.u01(px.draw(SEED, env.gid, t, 0, px.STREAM_ACTIONS)) * np.float32(2) - np.float32(1)) for t in range(n_act)]
     for t in range(warm):
-        env.step(acts[t])
+        env.step(acts[t % n_act])
     t0 = time.perf_counter()
     for t in range(warm, warm + steps):
-        env.step(acts[t])
+        env.step(acts[t % n_act])
     dt = time.perf_counter() - t0
-    return {"value": n_envs * steps / dt, "unit": "env-steps/s", "cores": threads, "kind": "port",
-            "sample": f"{task} task, {n_envs} envs x {steps} steps after {warm} warm-up, oracle port (torch CPU float32, {threads} threads), {dt:.1f} s",
+    return {"value": n_envs * steps / dt, "unit": "env-steps/s", "cores": threads, "kind": "port", "cpu_model": cpu_model(),
+            "sample": f"{task} task, {n_envs} envs x {steps} steps after {warm} warm-up, oracle port (torch CPU float32, {threads} threads, "
+                      f"{cpu_model()}), {dt:.1f} s",
             "ms_per_step": dt / steps * 1e3}
 
 
-def run_reference(args, rank):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference
-    env class itself cannot run anywhere: IsaacGym/PhysX binaries are absent).  Rank 0 only."""
+def cpu_baseline_extras():
+    """config 1 (pos task, 4096 envs -- the reference's own scale, README.md:41) with 1 thread and with all
+    threads; also the flip task at 4096 envs.  A 4096-env step is dispatch-bound on the CPU (~150 tiny torch ops per sub-step)."""
+    out = {}
+    for key, task, thr, steps in (("config1_pos_4096_all_threads", "pos", None, 20), ("config1_pos_4096_1_thread", "pos", 1, 10),
+                                  ("flip_4096_all_threads", "flip", None, 20)):
+        try:
+            r = cpu_baseline(task, 4096, steps, 2, False, threads=thr)
+            out[key] = {k: r[k] for k in ("value", "unit", "cores", "sample", "ms_per_step")}
+        except Exception as exc:
+            out[key] = {"error": repr(exc)}
+    return out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the reference env class itself cannot run
+    on a GPU box: IsaacGym/PhysX binaries are absent) on the SAME workload config as the GPU arm, each step a bounded sample of
+    --cpu-envs envs of it.  Rank 0 only."""
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 200))
-    warm = max(1, min(args.warmup, 5))
+    steps = max(1, min(args.steps, 20))
+    warm = max(1, min(args.warmup, 2))
     cb = cpu_baseline(args.task, args.cpu_envs, steps, warm, args.dr)
     line = {
         "impl": "reference", "metric": "env-steps/s", "value": cb["value"], "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.task} task, reference CPU path (oracle port), bounded sample {args.cpu_envs} envs/step",
-                   "len_obs": 1, "len_states": 5, "substeps": 2},
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": workload_config(args.task, args.dr, args.envs_per_gpu, world),
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_model")},
         "e2e": {"value": cb["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -338,17 +377,113 @@ def small_rollout_point(torch, taco_b200, dev, task, hidden, strict_fp, n=4096, 
     return out
 
 
+def kernel_source_sha():
+    """sha256 (16 hex) of the step kernel's sources: ties profiles/traffic_bytes_per_env.json to the build under test."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("fpv_step_kernel.cuh", "fpv_math.cuh", "philox.cuh", "step_params.h"):
+        with open(os.path.join(ROOT, "taco_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(task, dr):
+    """(bytes per env-step from the committed ncu capture, note) -- only when the capture was taken from THIS kernel source."""
+    tp = os.path.join(ROOT, "profiles", "traffic_bytes_per_env.json")
+    if not os.path.exists(tp):
+        return None, "no capture committed"
+    try:
+        t = json.load(open(tp))
+    except Exception as exc:
+        return None, repr(exc)
+    key = task + ("_dr" if dr else "")
+    if key not in t:
+        return None, f"no capture for {key}"
+    if t.get("kernel_source_sha16") != kernel_source_sha():
+        return None, f"capture {t.get('capture', '?')} was taken from another kernel source ({t.get('kernel_source_sha16')}); re-run tools/gpu_traffic.sh"
+    return float(t[key]), f"dram__bytes_read.sum + dram__bytes_write.sum per launch / envs, {t.get('capture', '?')}"
+
+
+def shard_point(torch, dist, taco_b200, dev, rank, world, task, n, dr, strict_fp, peak, steps=100, warm=20):
+    """One more BASELINE workload on this job's GPUs: fused step of `task` at n envs per GPU, weak-scaled, own HBM roofline."""
+    cfg = taco_b200.make_cfg(task, n, domain_randomization=dr)
+    env = taco_b200.FpvVecTask(cfg, dev, dev, -1, True, env_offset=rank * n, num_envs_global=world * n, seed=SEED, strict_fp=strict_fp)
+    acts = [env.random_actions(t) for t in range(4)]
+    for t in range(warm):
+        env.step(acts[t % 4])
+    env.stats()
+    ms, _ = time_steps(env, acts, steps, torch, dist, world)
+    env.close()
+    algo = ALGO_BYTES_DR if dr else ALGO_BYTES_NO_DR
+    ach = algo * n / (ms / steps * 1e-3) / 1e9
+    return {"workload": f"{task} task, {n} envs/GPU x {world} GPUs = {world * n} envs{', per-env DR on' if dr else ''}, random actions, "
+                        f"{steps} steps after {warm} warm-up, one stats all-reduce",
+            "value": float(world) * n * steps / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms / steps, "n_gpus": world,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_env_step": algo}}
+
+
+def policy_loop_point(torch, dist, taco_b200, dev, rank, world, n, hidden, horizon, strict_fp, reps=3):
+    """north_star "random-init-policy rollouts at 1, 2, 4, 8 GPUs": the whole collection loop of PPO.run on every rank's env shard
+    -- horizon x (actor sample + LSTM critic value + env.step, zero-copy store), GAE, then the two small all-reduces (advantage
+    moments, episode statistics) -- timed per rollout, max over ranks."""
+    gen = torch.Generator().manual_seed(SEED)
+    sizes = [26] + list(hidden) + [4]
+    ws, bs = [], []
+    for l in range(len(sizes) - 1):
+        w = torch.empty(sizes[l + 1], sizes[l])
+        torch.nn.init.orthogonal_(w, gain=(2 ** 0.5 if l + 2 < len(sizes) else 0.01), generator=gen)
+        ws.append(w); bs.append(torch.zeros(sizes[l + 1]))
+    c_hid, cs = 64, [64] + list(hidden) + [1]
+    w_ih = torch.empty(4 * c_hid, 26); w_hh = torch.empty(4 * c_hid, c_hid)
+    torch.nn.init.xavier_uniform_(w_ih, generator=gen); torch.nn.init.xavier_uniform_(w_hh, generator=gen)
+    lstm = [(w_ih, w_hh, torch.zeros(4 * c_hid), torch.zeros(4 * c_hid))]
+    cw, cb = [], []
+    for l in range(len(cs) - 1):
+        w = torch.empty(cs[l + 1], cs[l])
+        torch.nn.init.orthogonal_(w, gain=(2 ** 0.5 if l + 2 < len(cs) else 0.01), generator=gen)
+        cw.append(w); cb.append(torch.zeros(cs[l + 1]))
+    env = taco_b200.FpvVecTask(taco_b200.make_cfg("mix", n), dev, dev, -1, True, env_offset=rank * n, num_envs_global=world * n,
+                               seed=SEED, strict_fp=strict_fp)
+    actor = taco_b200.ActorMLP(26, list(hidden), 4, device=dev); actor.load(ws, bs, lipschitz_const=4.0)
+    critic = taco_b200.CriticLSTM(26, 5, c_hid, list(hidden), device=dev); critic.load(lstm, cw, cb)
+    buf = taco_b200.RolloutBuffer(n, 26, 1, 26, 5, 4, horizon, 1, 0.99, 0.95, dev)
+    run = lambda: taco_b200.collect_rollout(env, actor, buf, critic, seed=SEED, tensor_cores=True)
+    run()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        stats = run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    if world > 1:
+        tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+    env.close(); actor.close(); critic.close()
+    return {"workload": f"mix task, {n} envs/GPU x {world} GPUs, horizon {horizon}: actor {'x'.join(map(str, sizes))} + critic LSTM 64 / MLP "
+                        f"{'x'.join(map(str, cs))} (tcgen05 kernels; sizes are OUR stated default) + env.step every step, zero-copy store, GAE, "
+                        "2 small all-reduces per rollout; random-init spectral-normalised policy",
+            "value": float(world) * n * horizon / (ms * 1e-3), "unit": "env-steps/s", "ms_per_rollout": ms, "ms_per_step": ms / horizon,
+            "n_gpus": world, "gpu_launches_per_rollout": 3 * horizon + 5,
+            "episodes_finished_last_rollout": float(stats[1].item())}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, world)
         return
     import torch
     import torch.distributed as dist
     import taco_b200
+    from taco_b200 import _capi
     from taco_b200 import dist as tdist
     numa_cpus = tdist.bind_to_gpu_numa(local_rank) if (world > 1 and not args.no_numa) else None    # pinned host buffers next to the rank's GPU
     if not torch.cuda.is_available():
@@ -358,24 +493,37 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = args.envs_per_gpu
+    warmup = max(args.warmup, 3)
+    strict = not args.fast_fp
+    hidden = [int(x) for x in args.actor_hidden.split(",")]
     cfg = taco_b200.make_cfg(args.task, n, domain_randomization=args.dr)
     dev = f"cuda:{local_rank}"
-    env = taco_b200.FpvVecTask(cfg, dev, dev, -1, True, env_offset=rank * n, num_envs_global=world * n, seed=SEED, strict_fp=not args.fast_fp)
+    env = taco_b200.FpvVecTask(cfg, dev, dev, -1, True, env_offset=rank * n, num_envs_global=world * n, seed=SEED, strict_fp=strict)
     n_act = 4
     actions = [env.random_actions(t) for t in range(n_act)]     # synthetic U(-1,1), resident in HBM before timing
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for t in range(max(args.warmup, 3)):
+    for t in range(warmup):
         env.step(actions[t % n_act])
     warm_stats = env.stats()
     if world > 1:
         dist.all_reduce(warm_stats)                  # NCCL communicator set-up happens here, outside the timed region
+    launches0 = _capi.launch_count()
     t0 = sampler.mark()
     ms, stats = time_steps(env, actions, args.steps, torch, dist, world)
     t1 = sampler.mark()
+    launches = _capi.launch_count() - launches0      # counted by the library: one per kernel it launched in the timed region
+    if world > 1:
+        lt = torch.tensor([launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(lt)
+        launches = int(lt.item())
     total_env_steps = float(world) * n * args.steps
     value = total_env_steps / (ms * 1e-3)
+    # ---- sustained window: 300 more steps of the same workload (episodes desynchronised by now), own clock samples
+    s0 = sampler.mark()
+    ms_sus, _ = time_steps(env, actions, 300, torch, dist, world)
+    s1 = sampler.mark()
     # ---- end-to-end through the host-buffer C-ABI call
     e2e = None
     if not args.no_e2e:
@@ -384,16 +532,18 @@ def main():
         h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
         h_reset = torch.empty(n, dtype=torch.int64).pin_memory()
         h_tout = torch.empty(n, dtype=torch.uint8).pin_memory()
-        def time_host_steps(k):
+        h_flags = torch.empty(n, dtype=torch.uint8).pin_memory()
+
+        def time_host_steps(k, fn):
             for t in range(2):
-                env.step_host(h_act[t % n_act], h_rew, h_reset, h_tout)
+                fn(t)
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for t in range(k):
-                env.step_host(h_act[t % n_act], h_rew, h_reset, h_tout)
+                fn(t)
             e1.record()
             torch.cuda.synchronize()
             ms_ = e0.elapsed_time(e1)
@@ -402,69 +552,105 @@ def main():
                 dist.all_reduce(tm, op=dist.ReduceOp.MAX)
                 ms_ = float(tm.item())
             return float(world) * n * k / (ms_ * 1e-3)
+
+        ref_fmt = lambda t: env.step_host(h_act[t % n_act], h_rew, h_reset, h_tout)
         os.environ["TACO_HOST_MODE"] = "copy"          # the chunked copy pipeline (what pageable buffers get), for comparison
-        v_copy = time_host_steps(min(k_e2e, 10))
+        v_copy = time_host_steps(min(k_e2e, 10), ref_fmt)
         os.environ["TACO_HOST_MODE"] = "mapped"        # default: the kernel reads / writes the pinned host buffers itself
-        v_map = time_host_steps(k_e2e)
+        v_map = time_host_steps(k_e2e, ref_fmt)
+        v_compact = time_host_steps(k_e2e, lambda t: env.step_host_compact(h_act[t % n_act], h_rew, h_flags))
+        # e2e_full: obs and states cross PCIe too (they stay device-resident by design: the policy lives on the device)
+        h_obs = torch.empty(n, 1, 26, dtype=torch.float32).pin_memory()
+        h_states = torch.empty(n, 5, 26, dtype=torch.float32).pin_memory()
+
+        def full(t):
+            env.step_host(h_act[t % n_act], h_rew, h_reset, h_tout)
+            h_obs.copy_(env.obs_buf, non_blocking=True); h_states.copy_(env.states_buf, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        v_full = time_host_steps(min(k_e2e, 5), full)
+        pcie_gbs = v_map / world * 29 / 1e9
         e2e = {"value": v_map, "unit": "env-steps/s", "steps": k_e2e,
                "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * 13, "copy_pipeline_value": v_copy,
+               "compact": {"value": v_compact, "unit": "env-steps/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * 5,
+                           "note": "taco_env_step_host_compact: rew f32 + one flag byte (reset | time_out << 1) instead of f32 + int64 + bool"},
+               "e2e_full": {"value": v_full, "unit": "env-steps/s", "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": n * (13 + 104 + 520),
+                            "note": "additionally copies obs (104 B/env) and states (520 B/env) to pinned host memory every step"},
+               "host_link": {"bytes_per_env": 29, "achieved_gb_per_s_per_gpu": pcie_gbs,
+                             "note": "16 B in + 13 B out per env through one PCIe link per GPU; tools/probes/pcie_sm_probe.cu moves the same "
+                                     "bytes with no arithmetic at the same rate (profiles/pcie_sm_probe_r01e.txt): the call is bound by "
+                                     "the host link, and on this VM all GPUs share one host fabric (NUMA 0)"},
                "note": "per GPU bytes; taco_env_step_host with pinned host buffers, every step: one launch whose threads load their "
                        "action from host memory and post rew/reset/time_outs into host memory across PCIe, then a stream sync; "
-                       "copy_pipeline_value = the same call with TACO_HOST_MODE=copy (chunked cudaMemcpyAsync pipeline)"}
+                       "copy_pipeline_value = the same call with TACO_HOST_MODE=copy (chunked cudaMemcpyAsync pipeline). "
+                       "obs (104 B/env) and states (520 B/env) stay device-resident BY DESIGN -- the policy and the rollout buffer live on "
+                       "the device (taco_actor_act / taco_env_attach_rollout read them in place); e2e_full is the same call with both "
+                       "also copied to the host"}
     sampler.stop()
     clocks = sampler.summary(t0, t1) if rank == 0 else None
+    clocks_sus = sampler.summary(s0, s1) if rank == 0 else None
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    if "hbm_gbs" in peaks:
+        peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     # ---- small-N point of BASELINE config 2 (4096 envs, launch-latency bound)
     small = None
     if not args.no_small and world == 1:
         cfg_s = taco_b200.make_cfg(args.task, 4096)
-        env_s = taco_b200.FpvVecTask(cfg_s, dev, dev, -1, True, seed=SEED, strict_fp=not args.fast_fp)
+        env_s = taco_b200.FpvVecTask(cfg_s, dev, dev, -1, True, seed=SEED, strict_fp=strict)
         acts_s = [env_s.random_actions(t) for t in range(n_act)]
         for t in range(10):
             env_s.step(acts_s[t % n_act])
         ms_s, _ = time_steps(env_s, acts_s, 200, torch, dist, 1)
-        small = {"workload": f"{args.task}, 4096 envs (BASELINE config 2), L2-resident; 32 CTAs on 148 SMs = one warp per scheduler: bound by the latency of ~8.4k instructions per env-step, not by bandwidth", "value": 4096 * 200 / (ms_s * 1e-3),
-                 "unit": "env-steps/s", "us_per_step": ms_s / 200 * 1e3}
+        small = {"workload": f"{args.task}, 4096 envs (BASELINE config 2, the reference's own scale), L2-resident; bound by instruction latency, not by bandwidth",
+                 "value": 4096 * 200 / (ms_s * 1e-3), "unit": "env-steps/s", "us_per_step": ms_s / 200 * 1e3}
         env_s.close()
         if not args.no_actor:
             try:
-                small["rollout_loop"] = small_rollout_point(torch, taco_b200, dev, args.task, [int(x) for x in args.actor_hidden.split(",")], not args.fast_fp)
+                small["rollout_loop"] = small_rollout_point(torch, taco_b200, dev, args.task, hidden, strict)
             except Exception as exc:
                 small["rollout_loop"] = {"error": repr(exc)}
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    env.close()
+    extra = {}
+    if not args.no_extra_configs and not args.no_actor:
+        for key, fn in (("policy_loop", lambda: policy_loop_point(torch, dist, taco_b200, dev, rank, world, args.actor_envs, hidden, args.horizon, strict)),
+                        ("config4_rotate", lambda: shard_point(torch, dist, taco_b200, dev, rank, world, "rotate", 524288, False, strict, peak)),
+                        ("config5_mix_dr", lambda: shard_point(torch, dist, taco_b200, dev, rank, world, "mix", 2097152, True, strict, peak))):
+            try:
+                extra[key] = fn()
+            except Exception as exc:      # all ranks take the same path: a failure here is deterministic, not rank-local
+                extra[key] = {"error": repr(exc)}
+        if "value" in extra.get("config4_rotate", {}):
+            extra["config4_rotate"]["baseline_config"] = "BASELINE configs[3]: circle task, 4 Mi envs over 8 GPUs (exact at n_gpus = 8)"
+        if "value" in extra.get("config5_mix_dr", {}):
+            extra["config5_mix_dr"]["baseline_config"] = "BASELINE configs[4]: mix task, 16 Mi envs over 8 GPUs, per-env DR (exact at n_gpus = 8)"
     actor_pt = None
     if not args.no_actor and world == 1:
-        env.close()
-        actor_pt = actor_rollout_point(torch, taco_b200, dev, args.actor_envs, [int(x) for x in args.actor_hidden.split(",")], not args.fast_fp, peaks)
+        actor_pt = actor_rollout_point(torch, taco_b200, dev, args.actor_envs, hidden, strict, peaks)
     if rank == 0:
-        if "hbm_gbs" in peaks:
-            peak, peak_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         algo = ALGO_BYTES_DR if args.dr else ALGO_BYTES_NO_DR
         kernel_ms = ms / args.steps
         achieved = algo * n / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic_bytes_per_env.json")
-        if os.path.exists(tp):
-            try:
-                traffic = float(json.load(open(tp)).get(args.task)) * n
-            except Exception:
-                traffic = None
+        tr_per_env, tr_note = measured_traffic(args.task, args.dr)
+        ach_sus = algo * n / (ms_sus / 300 * 1e-3) / 1e9
         line = {
-            "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": "env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.task} task fused env step (BASELINE configs[1] scaled to {n} envs/GPU so the working set exceeds L2), "
-                                   f"len_obs=1, len_states=5, delay_time=20, rotor_response_time=0.017, substeps=2, "
-                                   f"{'per-env DR on' if args.dr else 'no per-env DR'}, U(-1,1) Philox actions",
-                       "envs_per_gpu": n, "global_envs": world * n, "parallelism": f"env-sharded x{world}", "rank0_numa_bound_cpus": (len(numa_cpus) if numa_cpus else None),
-                       "l2": "inputs larger than L2 (working set ~%.1f GB/GPU)" % (n * 1900 / 1e9),
-                       "fp_mode": "fast (FMA contraction)" if args.fast_fp else "strict (-fmad=false, the parity-tested build)"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "config": workload_config(args.task, args.dr, n, world),
+            "fp_mode": "fast (FMA contraction)" if args.fast_fp else "strict (-fmad=false, the parity-tested build)",
+            "rank0_numa_bound_cpus": (len(numa_cpus) if numa_cpus else None),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (tr_per_env * n if tr_per_env is not None else None), "traffic_note": tr_note,
                          "kernel": "fpv_step_kernel", "algorithmic_bytes_per_env_step": algo, "peak_source": peak_src,
-                         "kernel_ms": kernel_ms},
-            "gpu_launches": args.steps * world + 1 * world,
+                         "kernel_ms": kernel_ms, "kernel_source_sha16": kernel_source_sha()},
+            "sustained": {"steps": 300, "ms_per_step": ms_sus / 300, "value": float(world) * n * 300 / (ms_sus * 1e-3), "unit": "env-steps/s",
+                          "roofline": {"bound": "hbm", "achieved": ach_sus, "peak": peak, "unit": "GB/s", "frac": ach_sus / peak},
+                          "clocks": clocks_sus,
+                          "note": "300 consecutive steps right after the timed region (episodes desynchronised, GPU at its sustained clocks)"},
+            "gpu_launches": launches,
+            "gpu_launches_note": "counted by the library (taco_launch_count) over the timed region, summed over ranks: one fused step kernel per step + the stats reduction",
             "clocks": clocks,
             "rollout_stats": [float(x) for x in stats.cpu().tolist()],
         }
@@ -474,10 +660,13 @@ def main():
             line["config2_4096_envs"] = small
         if actor_pt is not None:
             line["config3_mix_actor"] = actor_pt
+        line.update(extra)
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.task, args.cpu_envs, args.cpu_steps, 3, args.dr).items() if k != "ms_per_step"}
+            cb = cpu_baseline(args.task, args.cpu_envs, args.cpu_steps, 1, args.dr)
+            line["cpu_baseline"] = {k: v for k, v in cb.items() if k != "ms_per_step"}
+            line["cpu_baseline"]["same_workload_gpu_value"] = value
+            line["cpu_baseline_extra"] = cpu_baseline_extras()
         emit(line)
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 

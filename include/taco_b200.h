@@ -118,6 +118,10 @@ int taco_env_step(TacoEnv* env, const float* actions_dev, void* stream);
  * chunks overlap).  Both modes produce the results of taco_env_step and leave them in the device buffers as well. */
 int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host, int64_t* reset_host,
                        uint8_t* time_outs_host, void* stream);
+/* Opt-in compact result format of the host-buffer step: rew_host (f32, may be NULL) + flags_host, one byte per env with bit 0 =
+ * reset_buf != 0 and bit 1 = time_outs: 5 bytes of device->host traffic per env instead of 13.  The reference dtypes (int64
+ * reset_buf, vec_task_asymmetry.py:246-247) stay what taco_env_step_host returns.  Pinned (device-mapped) host buffers only. */
+int taco_env_step_host_compact(TacoEnv* env, const float* actions_host, float* rew_host, uint8_t* flags_host, void* stream);
 /* -- VecTask.reset (vec_task_asymmetry.py:352-361) does not simulate; this additionally marks every env for
  * reset on the next step and zeroes the observation history, i.e. restores the freshly-constructed state. */
 int taco_env_reset_all(TacoEnv* env, void* stream);
@@ -265,6 +269,9 @@ int taco_gae_normalize(int device, float* adv_dev, int64_t count, const double* 
  * division-by-constant against IEEE division, for every divisor the step kernel uses; writes the mismatch count. */
 int taco_selftest_divc(int device, float dt, uint64_t* n_mismatch);
 
+/* number of CUDA kernels this library has launched in this process so far (every <<<>>> of libtaco_b200.so; captured launches
+ * count once, at capture) */
+int taco_launch_count(uint64_t* out);
 const char* taco_last_error(void);
 int taco_abi_version(void);
 

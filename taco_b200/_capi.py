@@ -58,12 +58,14 @@ def lib():
     vp, i32, u32, u64, f32 = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_float
     sig = {
         "taco_abi_version": (C.c_int, []),
+        "taco_launch_count": (C.c_int, [C.POINTER(u64)]),
         "taco_last_error": (C.c_char_p, []),
         "taco_env_create": (C.c_int, [C.POINTER(TacoCfg), C.c_int, C.POINTER(vp)]),
         "taco_env_destroy": (C.c_int, [vp]),
         "taco_env_buffers": (C.c_int, [vp, C.POINTER(TacoBuffers)]),
         "taco_env_step": (C.c_int, [vp, vp, vp]),
         "taco_env_step_host": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "taco_env_step_host_compact": (C.c_int, [vp, vp, vp, vp, vp]),
         "taco_env_reset_all": (C.c_int, [vp, vp]),
         "taco_env_graph_begin": (C.c_int, [vp, vp]),
         "taco_env_graph_advance": (C.c_int, [vp, u32, vp]),
@@ -131,3 +133,10 @@ class _CudaView:
 def wrap(ptr, shape, typestr, device, owner):
     import torch
     return torch.as_tensor(_CudaView(ptr, shape, typestr, owner), device=device)
+
+
+def launch_count():
+    """Kernel launches issued by libtaco_b200.so in this process so far."""
+    n = C.c_uint64()
+    check(lib().taco_launch_count(C.byref(n)), "taco_launch_count")
+    return int(n.value)

@@ -19,6 +19,7 @@
 #include "fpv_math.cuh"
 #include "philox.cuh"
 #include "step_params.h"
+#include "launch_count.h"
 #include "../../include/taco_b200.h"
 
 #ifndef TACO_MIN_BLOCKS
@@ -612,6 +613,7 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
         if (p.host_reset) p.host_reset[i] = done ? 1ll : 0ll;
         if (p.host_rew) p.host_rew[i] = rew;
         if (p.host_tout) p.host_tout[i] = tout ? 1 : 0;
+        if (p.host_flags) p.host_flags[i] = (uint8_t)((done ? 1 : 0) | (tout ? 2 : 0));
     } else {
 #pragma unroll
         for (int j = 0; j < 26; ++j) { fc[j] = 0.f; fn[j] = 0.f; }
@@ -660,6 +662,7 @@ static void launch_task(const StepParams& p, cudaStream_t stream) {
         else if (p.substeps == 1) fpv_step_kernel<TASK, false, 1><<<grid, kBlock, 0, stream>>>(p);
         else fpv_step_kernel<TASK, false, 0><<<grid, kBlock, 0, stream>>>(p);
     }
+    TACO_LAUNCHED();
 }
 
 static inline void launch_any(const StepParams& p, cudaStream_t stream) {

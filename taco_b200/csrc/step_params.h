@@ -55,6 +55,7 @@ struct StepParams {
     float* host_rew;               // taco_env_step_host, mapped mode: the caller's pinned host buffers (device-visible addresses,
     long long* host_reset;         // or null); the kernel posts rew / reset / time-outs across PCIe itself
     uint8_t* host_tout;
+    uint8_t* host_flags;           // taco_env_step_host_compact: one byte per env, bit 0 = reset, bit 1 = time-out
     double* stats;                 // [kStatSlots][kStatStride]
     float4* dbg_delay;             // [cfi][n_pad] or null
 };

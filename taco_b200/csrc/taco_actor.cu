@@ -8,6 +8,7 @@
 // path) and the tcgen05 bf16 path in actor_tc.cuh (the throughput path for env counts where the MLP is a real
 // dense contraction).  taco_actor_load uploads the weights, applies the spectral projection on the device
 // (power iteration in double precision, once per update) and pre-swizzles the bf16 weight images.
+#include "launch_count.h"
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -251,7 +252,7 @@ static int actor_run(TacoActor* a, const float* obs_dev, float* mean_dev, int32_
             ACT_CUDA(cudaMalloc(&p.dbg, 3 * kDbgCap * sizeof(unsigned long long)));
             ACT_CUDA(cudaMemsetAsync(p.dbg, 0, 3 * kDbgCap * sizeof(unsigned long long), s));
         }
-        actor_tc_kernel<<<grid, kTcThreads, kActorSmemBytes, s>>>(p);
+        actor_tc_kernel<<<grid, kTcThreads, kActorSmemBytes, s>>>(p); TACO_LAUNCHED();
         if (p.dbg) {
             std::vector<unsigned long long> h(3 * kDbgCap);
             ACT_CUDA(cudaStreamSynchronize(s));
@@ -268,7 +269,7 @@ static int actor_run(TacoActor* a, const float* obs_dev, float* mean_dev, int32_
         for (int l = 0; l < a->n_layers; ++l) { p.w[l] = a->w_f32 + a->w_off[l]; p.b[l] = a->b_f32 + a->b_off[l]; }
         p.stride = mx + 1;
         p.sp = sp;
-        actor_fp32_kernel<<<(n + kFpEnvs - 1) / kFpEnvs, kFpThreads, a->fp_smem, s>>>(p);
+        actor_fp32_kernel<<<(n + kFpEnvs - 1) / kFpEnvs, kFpThreads, a->fp_smem, s>>>(p); TACO_LAUNCHED();
     }
     ACT_CUDA(cudaGetLastError());
     return TACO_OK;
@@ -368,7 +369,7 @@ int taco_actor_load(TacoActor* a, const float* const* weights_host, const float*
     for (int l = 0; l < a->n_layers && lipschitz_const >= 0.0f; ++l) {        // negative: weights are known to be projected, skip the measurement
         const int in = a->sizes[l], out = a->sizes[l + 1];
         spectral_norm_kernel<<<1, kSnThreads, (size_t)(in + out) * sizeof(double), s>>>(a->w_f32 + a->w_off[l], out, in, lipschitz_const,
-                                                                                         a->sigma + l, 20000, 1e-12);
+                                                                                         a->sigma + l, 20000, 1e-12); TACO_LAUNCHED();
     }
     ACT_CUDA(cudaGetLastError());
     if (a->tc_ok) {
@@ -376,7 +377,7 @@ int taco_actor_load(TacoActor* a, const float* const* weights_host, const float*
         ACT_CUDA(cudaMemsetAsync(a->bias_pad, 0, kMaxHidden * kMaxN * sizeof(float), s));
         for (int l = 0; l <= n_hidden; ++l) {
             const int in = a->sizes[l], out = a->sizes[l + 1];
-            pack_weights_kernel<<<64, 256, 0, s>>>(a->w_f32 + a->w_off[l], out, a->tc_layer[l].n, in, a->wimg + a->tc_layer[l].img_off);
+            pack_weights_kernel<<<64, 256, 0, s>>>(a->w_f32 + a->w_off[l], out, a->tc_layer[l].n, in, a->wimg + a->tc_layer[l].img_off); TACO_LAUNCHED();
             if (l < n_hidden)
                 ACT_CUDA(cudaMemcpyAsync(a->bias_pad + l * kMaxN, a->b_f32 + a->b_off[l], (size_t)out * sizeof(float), cudaMemcpyDeviceToDevice, s));
         }
@@ -418,7 +419,7 @@ int taco_spectral_project(int device, float* w_dev, int32_t rows, int32_t cols, 
     DevGuard guard(device);
     const size_t smem = (size_t)(rows + cols) * sizeof(double);
     if (smem > 48 * 1024) ACT_CUDA(cudaFuncSetAttribute(spectral_norm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    spectral_norm_kernel<<<1, kSnThreads, smem, (cudaStream_t)stream>>>(w_dev, rows, cols, lipschitz_const, sigma_dev, 20000, 1e-12);
+    spectral_norm_kernel<<<1, kSnThreads, smem, (cudaStream_t)stream>>>(w_dev, rows, cols, lipschitz_const, sigma_dev, 20000, 1e-12); TACO_LAUNCHED();
     ACT_CUDA(cudaGetLastError());
     return TACO_OK;
 }

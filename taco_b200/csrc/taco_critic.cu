@@ -9,6 +9,7 @@
 //
 // Two kernels compute the same function: an FP32 CUDA-core path (any shape; the parity path) and the tcgen05 bf16 path in
 // critic_tc.cuh (one LSTM layer of width <= 64, MLP widths multiples of 64 up to 256).
+#include "launch_count.h"
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -347,10 +348,10 @@ int taco_critic_load(TacoCritic* c, const float* const* lstm_host, const float* 
         const int n_hidden = c->n_mlp - 1;
         CRT_CUDA(cudaMemsetAsync(c->bias_pad, 0, taco::actor::kMaxHidden * taco::actor::kMaxN * sizeof(float), s));
         pack_lstm_kernel<<<64, 256, 0, s>>>(c->lstm_f32 + c->lstm_off[0], c->lstm_f32 + c->lstm_off[1], c->lstm_f32 + c->lstm_off[2],
-                                            c->lstm_f32 + c->lstm_off[3], H, c->in_dim, 4 * H, c->wimg);
+                                            c->lstm_f32 + c->lstm_off[3], H, c->in_dim, 4 * H, c->wimg); TACO_LAUNCHED();
         for (int l = 0; l <= n_hidden; ++l) {
             const int in = c->mlp_sizes[l], out = c->mlp_sizes[l + 1];
-            taco::actor::pack_weights_kernel<<<64, 256, 0, s>>>(c->w_f32 + c->w_off[l], out, c->tc_layer[1 + l].n, in, c->wimg + c->tc_layer[1 + l].img_off);
+            taco::actor::pack_weights_kernel<<<64, 256, 0, s>>>(c->w_f32 + c->w_off[l], out, c->tc_layer[1 + l].n, in, c->wimg + c->tc_layer[1 + l].img_off); TACO_LAUNCHED();
             if (l < n_hidden)
                 CRT_CUDA(cudaMemcpyAsync(c->bias_pad + (size_t)(1 + l) * taco::actor::kMaxN, c->b_f32 + c->b_off[l], (size_t)out * sizeof(float),
                                          cudaMemcpyDeviceToDevice, s));
@@ -390,7 +391,7 @@ int taco_critic_forward(TacoCritic* c, const float* states_dev, float* value_dev
             CRT_CUDA(cudaMalloc(&p.dbg, 3 * taco::actor::kDbgCap * sizeof(unsigned long long)));
             CRT_CUDA(cudaMemsetAsync(p.dbg, 0, 3 * taco::actor::kDbgCap * sizeof(unsigned long long), s));
         }
-        critic_tc_kernel<<<grid, taco::actor::kTcThreads, kCriticSmemBytes, s>>>(p);
+        critic_tc_kernel<<<grid, taco::actor::kTcThreads, kCriticSmemBytes, s>>>(p); TACO_LAUNCHED();
         if (p.dbg) {
             std::vector<unsigned long long> h(3 * taco::actor::kDbgCap);
             CRT_CUDA(cudaStreamSynchronize(s));
@@ -410,7 +411,7 @@ int taco_critic_forward(TacoCritic* c, const float* states_dev, float* value_dev
         for (int l = 0; l <= c->n_mlp; ++l) p.mlp_sizes[l] = c->mlp_sizes[l];
         for (int l = 0; l < c->n_mlp; ++l) { p.w[l] = c->w_f32 + c->w_off[l]; p.b[l] = c->b_f32 + c->b_off[l]; }
         p.stride = c->fp_stride; p.off_lstm = c->off_lstm; p.off_mlp = c->off_mlp; p.mlp_w = c->mlp_w;
-        critic_fp32_kernel<<<(n + kFpEnvs - 1) / kFpEnvs, kFpThreads, c->fp_smem, s>>>(p);
+        critic_fp32_kernel<<<(n + kFpEnvs - 1) / kFpEnvs, kFpThreads, c->fp_smem, s>>>(p); TACO_LAUNCHED();
     }
     CRT_CUDA(cudaGetLastError());
     return TACO_OK;

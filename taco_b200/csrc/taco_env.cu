@@ -4,6 +4,7 @@
 // Mirrors, for buffer ownership and layout, VecTask.allocate_buffers
 // (IsaacGymEnvs/isaacgymenvs/tasks/base/vec_task_asymmetry.py:231-254) and the state tensors of
 // FpvBase.__init__ (IsaacGymEnvs/isaacgymenvs/tasks/fpv_asymmetry.py:124-200).
+#include "launch_count.h"
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -19,6 +20,7 @@
 
 namespace taco {
 
+std::atomic<unsigned long long> g_launches{0};
 static thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 #define TACO_CUDA(expr)                                                                          \
@@ -253,7 +255,7 @@ int taco_selftest_divc(int device, float dt, uint64_t* n_mismatch) {
     unsigned long long* d = nullptr;
     TACO_CUDA(cudaMalloc(&d, 2 * sizeof(unsigned long long) + 64 * sizeof(uint32_t)));
     TACO_CUDA(cudaMemset(d, 0, 2 * sizeof(unsigned long long) + 64 * sizeof(uint32_t)));
-    selftest_divc_kernel<<<148 * 8, 256>>>(d, dt, (uint32_t*)(d + 2));
+    selftest_divc_kernel<<<148 * 8, 256>>>(d, dt, (uint32_t*)(d + 2)); TACO_LAUNCHED();
     TACO_CUDA(cudaGetLastError());
     unsigned long long h[2 + 32] = {0};
     TACO_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
@@ -268,6 +270,11 @@ int taco_selftest_divc(int device, float dt, uint64_t* n_mismatch) {
     return TACO_OK;
 }
 int taco_abi_version(void) { return TACO_ABI_VERSION; }
+int taco_launch_count(uint64_t* out) {
+    if (!out) return fail(TACO_E_INVALID, "taco_launch_count: null argument");
+    *out = (uint64_t)taco::g_launches.load(std::memory_order_relaxed);
+    return TACO_OK;
+}
 
 int taco_env_create(const TacoCfg* cfg, int device, TacoEnv** out) {
     if (!cfg || !out) return fail(TACO_E_INVALID, "taco_env_create: null argument");
@@ -359,7 +366,7 @@ int taco_env_create(const TacoCfg* cfg, int device, TacoEnv** out) {
     p.dbg_delay = e->dbg_delay;
     e->cur = 0;
     e->step_index = 0;
-    init_state_kernel<<<(e->n_pad + 255) / 256, 256>>>(p);
+    init_state_kernel<<<(e->n_pad + 255) / 256, 256>>>(p); TACO_LAUNCHED();
     ce = cudaDeviceSynchronize();
     if (ce != cudaSuccess) { cudaFree(e->arena); delete e; return fail(TACO_E_CUDA, std::string("init kernel: ") + cudaGetErrorString(ce)); }
     *out = e;
@@ -479,6 +486,34 @@ static int pipe_init(TacoEnv* env) {
 // (H2D and D2H use opposite directions of the link).  Chunk kernels rotate over a few internal streams, so the partial
 // last wave of one chunk overlaps the first wave of the next; everything is ordered after the work already queued on
 // the caller's stream, which in turn waits for the last copy before the call synchronises it.
+// Compact result format of the host-buffer step (opt-in; the reference dtypes stay the default): rew f32 + ONE flag byte per env
+// (bit 0 = reset_buf != 0, bit 1 = time_outs) = 5 bytes of device->host traffic per env instead of 13 (8 of which are an int64
+// reset).  Mapped mode only: every buffer must be pinned (cudaHostAlloc / cudaHostRegister / torch pin_memory).
+int taco_env_step_host_compact(TacoEnv* env, const float* actions_host, float* rew_host, uint8_t* flags_host, void* stream) {
+    if (!env || !actions_host || !flags_host) return fail(TACO_E_INVALID, "taco_env_step_host_compact: null argument");
+    if (((uintptr_t)actions_host & 15u) != 0) return fail(TACO_E_INVALID, "taco_env_step_host_compact: actions must be 16-byte aligned");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    void* d_act = mapped_ptr(actions_host);
+    void* d_rew = mapped_ptr(rew_host);
+    void* d_flags = mapped_ptr(flags_host);
+    if (!d_act || (rew_host && !d_rew) || !d_flags)
+        return fail(TACO_E_INVALID, "taco_env_step_host_compact: the host buffers must be pinned (device-mapped); use taco_env_step_host for pageable memory");
+    StepParams& p = env->p;
+    const int rc = bind_history(env);
+    if (rc != TACO_OK) return rc;
+    p.actions = (const float4*)d_act;
+    p.host_rew = (float*)d_rew; p.host_flags = (uint8_t*)d_flags;
+    bind_step_index(env);
+    if (env->cfg.flags & TACO_F_STRICT_FP) launch_fpv_step_strict(p, s); else launch_fpv_step_fast(p, s);
+    const cudaError_t le = cudaGetLastError();
+    p.host_rew = nullptr; p.host_flags = nullptr;
+    TACO_CUDA(le);
+    advance_history(env);
+    TACO_CUDA(cudaStreamSynchronize(s));
+    return TACO_OK;
+}
+
 int taco_env_step_host(TacoEnv* env, const float* actions_host, float* rew_host, int64_t* reset_host, uint8_t* time_outs_host,
                        void* stream) {
     if (!env || !actions_host) return fail(TACO_E_INVALID, "taco_env_step_host: null argument");
@@ -575,7 +610,7 @@ int taco_env_graph_begin(TacoEnv* env, void* stream) {
     if (!env->step_counter) TACO_CUDA(cudaMalloc(&env->step_counter, sizeof(uint32_t)));
     if (!env->diff_dev) TACO_CUDA(cudaMalloc(&env->diff_dev, 9 * sizeof(float)));
     TACO_CUDA(upload_derived(env));
-    step_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->step_counter, env->step_index, 0);
+    step_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->step_counter, env->step_index, 0); TACO_LAUNCHED();
     TACO_CUDA(cudaGetLastError());
     env->graph_mode = true;
     env->graph_origin = env->step_index;
@@ -586,7 +621,7 @@ int taco_env_graph_begin(TacoEnv* env, void* stream) {
 int taco_env_graph_advance(TacoEnv* env, uint32_t steps, void* stream) {
     if (!env || !env->graph_mode) return fail(TACO_E_INVALID, "taco_env_graph_advance: call taco_env_graph_begin first");
     DeviceGuard guard(env->device);
-    step_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->step_counter, steps, 1);
+    step_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->step_counter, steps, 1); TACO_LAUNCHED();
     TACO_CUDA(cudaGetLastError());
     return TACO_OK;
 }
@@ -674,7 +709,7 @@ int taco_env_reset_all(TacoEnv* env, void* stream) {
         env->ring_cur = 0;
     }
     TACO_CUDA(cudaMemsetAsync(env->p.stats, 0, (size_t)kStatSlots * kStatStride * sizeof(double), s));
-    init_state_kernel<<<(env->n_pad + 255) / 256, 256, 0, s>>>(env->p);
+    init_state_kernel<<<(env->n_pad + 255) / 256, 256, 0, s>>>(env->p); TACO_LAUNCHED();
     TACO_CUDA(cudaGetLastError());
     env->step_index = 0;
     env->graph_mode = false;                                         // host-side counting again; taco_env_graph_begin re-arms
@@ -709,7 +744,7 @@ int taco_env_stats(TacoEnv* env, double* out_dev, double* out_host, void* stream
     DeviceGuard guard(env->device);
     cudaStream_t s = (cudaStream_t)stream;
     double* dst = out_dev ? out_dev : env->stats_out;
-    reduce_stats_kernel<<<1, 32, 0, s>>>(env->p.stats, dst);
+    reduce_stats_kernel<<<1, 32, 0, s>>>(env->p.stats, dst); TACO_LAUNCHED();
     TACO_CUDA(cudaGetLastError());
     if (out_host) {
         TACO_CUDA(cudaMemcpyAsync(out_host, dst, kNumStats * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -722,7 +757,7 @@ int taco_env_fill_random_actions(TacoEnv* env, float* actions_dev, uint32_t step
     if (!env || !actions_dev) return fail(TACO_E_INVALID, "taco_env_fill_random_actions: null argument");
     DeviceGuard guard(env->device);
     fill_actions_kernel<<<(env->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((float4*)actions_dev, env->n, env->p.env_offset, step_index,
-                                                                               env->p.seed_lo, env->p.seed_hi);
+                                                                               env->p.seed_lo, env->p.seed_hi); TACO_LAUNCHED();
     TACO_CUDA(cudaGetLastError());
     return TACO_OK;
 }
@@ -733,7 +768,7 @@ int taco_env_export_state(TacoEnv* env, float* out_host) {
     const size_t bytes = (size_t)env->n * TACO_STATE_WORDS * sizeof(float);
     if (!env->export_stage) TACO_CUDA(cudaMalloc(&env->export_stage, bytes));
     TACO_CUDA(cudaDeviceSynchronize());
-    export_state_kernel<<<(env->n + 255) / 256, 256>>>(env->p, env->export_stage);
+    export_state_kernel<<<(env->n + 255) / 256, 256>>>(env->p, env->export_stage); TACO_LAUNCHED();
     TACO_CUDA(cudaGetLastError());
     TACO_CUDA(cudaMemcpy(out_host, env->export_stage, bytes, cudaMemcpyDeviceToHost));
     return TACO_OK;
@@ -746,7 +781,7 @@ int taco_env_import_state(TacoEnv* env, const float* in_host) {
     if (!env->export_stage) TACO_CUDA(cudaMalloc(&env->export_stage, bytes));
     TACO_CUDA(cudaDeviceSynchronize());
     TACO_CUDA(cudaMemcpy(env->export_stage, in_host, bytes, cudaMemcpyHostToDevice));
-    import_state_kernel<<<(env->n + 255) / 256, 256>>>(env->p, env->export_stage);
+    import_state_kernel<<<(env->n + 255) / 256, 256>>>(env->p, env->export_stage); TACO_LAUNCHED();
     TACO_CUDA(cudaGetLastError());
     TACO_CUDA(cudaDeviceSynchronize());
     return TACO_OK;

@@ -11,6 +11,7 @@
 // all-reduces -- and a second, purely elementwise launch applies the normalisation from those moments.
 //
 // Compiled with -fmad=false: the recurrence is op-for-op the reference's float32 expression (bit-exact adv / ret).
+#include "launch_count.h"
 #include <cstdint>
 #include <string>
 
@@ -102,7 +103,7 @@ int taco_gae_advantages(int device, int32_t horizon, int32_t num_envs, const flo
     cudaError_t e = cudaMemsetAsync(moments_dev, 0, 3 * sizeof(double), s);
     if (e == cudaSuccess) {
         gae_scan_kernel<<<(num_envs + kThreads - 1) / kThreads, kThreads, 0, s>>>(horizon, num_envs, rew_dev, done_dev, time_outs_dev, value_dev,
-                                                                                   last_value_dev, gamma, lam, adv_dev, ret_dev, moments_dev);
+                                                                                   last_value_dev, gamma, lam, adv_dev, ret_dev, moments_dev); TACO_LAUNCHED();
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) return taco::fail(TACO_E_CUDA, std::string("taco_gae_advantages: ") + cudaGetErrorString(e));
@@ -115,7 +116,7 @@ int taco_gae_normalize(int device, float* adv_dev, int64_t count, const double* 
     DevGuard guard(device);
     const long long blocks = (count + 1023) / 1024;
     const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
-    gae_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(adv_dev, (long long)count, moments_dev);
+    gae_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(adv_dev, (long long)count, moments_dev); TACO_LAUNCHED();
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return taco::fail(TACO_E_CUDA, std::string("taco_gae_normalize: ") + cudaGetErrorString(e));
     return TACO_OK;

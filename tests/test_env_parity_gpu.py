@@ -186,6 +186,33 @@ def test_host_buffer_entry_point_matches_device_path(n, mode, monkeypatch):
     a_env.close(); b_env.close()
 
 
+def test_host_buffer_compact_result_format():
+    """taco_env_step_host_compact: rew f32 + one flag byte per env (bit 0 reset, bit 1 time-out) equals the device-path results;
+    pageable buffers are refused (mapped mode only)."""
+    import taco_b200
+    from taco_b200 import make_cfg
+    n = 4097
+    cfg = make_cfg("pos", n)
+    cfg["env"]["maxEpisodeLength"] = 5                       # time-outs inside the run
+    a_env = taco_b200.FpvVecTask(cfg, "cuda:0", "cuda:0", -1, True, seed=3)
+    b_env = taco_b200.FpvVecTask(cfg, "cuda:0", "cuda:0", -1, True, seed=3)
+    h_rew, h_flags = torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory()
+    seen = 0
+    for t in range(8):
+        act = a_env.random_actions(t)
+        o, r, x, e = a_env.step(act)
+        h_rew.fill_(-7.0); h_flags.fill_(77)
+        b_env.step_host_compact(act.cpu().pin_memory(), h_rew, h_flags)
+        assert torch.equal(r.cpu(), h_rew)
+        assert torch.equal((x.cpu() != 0).to(torch.uint8) | (e["time_outs"].cpu().to(torch.uint8) << 1), h_flags)
+        assert torch.equal(o["states"], b_env.states_buf) and torch.equal(x, b_env.reset_buf)
+        seen |= int(h_flags.max())
+    assert seen == 3
+    with pytest.raises(RuntimeError):
+        b_env.step_host_compact(torch.zeros(n, 4), h_rew, h_flags)
+    a_env.close(); b_env.close()
+
+
 def test_host_buffer_entry_point_without_result_buffers():
     """Every result pointer of taco_env_step_host may be NULL (actions only): the step still runs and the device buffers hold the
     results -- in mapped and in copy mode."""
