@@ -30,7 +30,11 @@
 #endif
 
 // difficulty-dependent scalars: by-value kernel parameters, or -- in graph mode -- their device copy (step_params.h)
+#ifdef TACO_NO_DIFF_DEV      // tuning builds only: graph-mode difficulty changes are then ignored
+#define TACO_DIFF(field, idx) p.field
+#else
 #define TACO_DIFF(field, idx) (p.diff_dev ? __ldg(p.diff_dev + (idx)) : p.field)
+#endif
 
 namespace taco {
 namespace TACO_VARIANT {   // distinct symbols per translation unit: the two builds must not be merged by the linker
@@ -153,7 +157,6 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
             const long long gg = p.env_offset + i;
             task = gg < p.mix_n1 ? TACO_TASK_POS : (gg < p.mix_n2 ? TACO_TASK_ROTATE : TACO_TASK_FLIP);
         }
-        const float d = TACO_DIFF(difficulty, 0);
         const bool at500 = (progress == 500);                   // fpv_asymmetry.py:152,597 (before counters clear)
 
         // pending-action runs live in a ring indexed by the RL step of the LAUNCH (slot = step_index & 15, the same for
@@ -166,6 +169,7 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
 
         // ------------------------------------------------------------------ lazy reset (fpv_asymmetry.py:475-517)
         if (R) {
+            const float d = TACO_DIFF(difficulty, 0);          // read where it is used: no register held across the step
             const uint4 b0 = philox4x32_10(g, t_rl, 0, STREAM_RESET, k0, k1);
             const uint4 b1 = philox4x32_10(g, t_rl, 1, STREAM_RESET, k0, k1);
             const uint4 b2 = philox4x32_10(g, t_rl, 2, STREAM_RESET, k0, k1);
@@ -520,6 +524,7 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
         for (int j = 0; j < 24; ++j) finite = finite && isfinite(fc[j]);
         finite = finite && isfinite(o25);
         if (obs_noise) {                                              // :402-410
+            const float d = TACO_DIFF(difficulty, 0);
             float z[12];
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
