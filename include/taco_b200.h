@@ -251,6 +251,60 @@ int taco_actor_act_counter(TacoActor* actor, const float* obs_dev, int32_t n, co
                            uint64_t seed, uint32_t step_index, const uint32_t* step_base_dev, float* mean_dev, float* action_dev,
                            float* clipped_dev, float* logp_dev, int32_t use_tensor_cores, void* stream);
 
+/* -- native PPO update: PPO.update of the reference (IsaacGymEnvs/algorithms/ppo_asymmetry.py:137-258) for the network
+ * configuration it trains with (README.md:60-66; nets_asymmetry.py:270-377): MLP actor (tanh mean, state-independent log_std,
+ * std = exp(log_std)^2), critic = MLP(LSTMEncoder(states)).  Forward / backward are tcgen05 GEMMs fed by TMA tensor maps (bf16
+ * operands, fp32 accumulation), master weights / Adam moments / losses in fp32; the KL early stop (:223-226) is decided on the
+ * device, so an update is a stream of launches without a host sync.  Per minibatch: taco_ppo_forward_loss -> [data parallel:
+ * all-reduce SUM the 8 doubles of taco_ppo_loss_sums] -> taco_ppo_decide -> taco_ppo_backward -> [data parallel: all-reduce SUM
+ * the flat gradient of taco_ppo_buffers] -> taco_ppo_apply (clip_grad_norm_ :244, Adam :117 with eps 1e-5, the spectral projection
+ * of the actor weights :248-249,:398-404).  sm_100 only; no fallback. */
+typedef struct TacoPPO TacoPPO;
+typedef struct TacoPPOCfg {
+    int32_t batch;               /* minibatch size (samples per optimiser step), multiple of 128 */
+    int32_t obs_dim;             /* flattened actor input: num_obs * len_obs */
+    int32_t act_dim;             /* <= 4 */
+    int32_t state_dim, seq_len;  /* critic input (N, seq_len, state_dim): num_states, len_states */
+    int32_t lstm_hidden;         /* 64 */
+    int32_t n_actor_hidden, actor_hidden[4];     /* hidden widths: multiples of 16 in [16, 256] */
+    int32_t n_critic_hidden, critic_hidden[4];
+} TacoPPOCfg;
+typedef struct TacoPPOHyper {
+    float lr, clip, target_kl, max_grad, pi_coef, vf_coef, ent_coef;
+    float lipschitz;             /* spectral bound c of this epoch (ppo_asymmetry.py:152-162) */
+    int32_t use_lipschitz;
+    int32_t world;               /* data-parallel ranks whose sums were all-reduced (1 = single process) */
+} TacoPPOHyper;
+int taco_ppo_create(int device, const TacoPPOCfg* cfg, TacoPPO** out);
+int taco_ppo_destroy(TacoPPO* ppo);
+int taco_ppo_num_params(TacoPPO* ppo, int64_t* n);
+/* offsets of the parameter tensors in the flat fp32 vector, in this order: log_std; actor (weight, bias) per layer; LSTM
+ * weight_ih_l0, weight_hh_l0, bias_ih_l0, bias_hh_l0; critic MLP (weight, bias) per layer -- every tensor in torch's layout */
+int taco_ppo_param_offsets(TacoPPO* ppo, int64_t* offsets, int32_t count, int32_t* n_out);
+/* device addresses of the flat vectors (n_params floats each) and of the int32 optimiser-step counter; any may be NULL */
+int taco_ppo_buffers(TacoPPO* ppo, float** params, float** grad, float** adam_m, float** adam_v, int32_t** step);
+/* after writing the parameter vector from outside: refresh the bf16 operand copies */
+int taco_ppo_params_changed(TacoPPO* ppo, void* stream);
+int taco_ppo_begin_update(TacoPPO* ppo, void* stream);
+/* rollout tensors as flat device views [N_total][...] (obs (N, obs_dim), states (N, seq_len, state_dim), act (N, act_dim),
+ * old_logp / adv / ret (N)); idx_dev = `batch` int64 row indices of the minibatch (buffer_asymmetry.py:34-47) */
+int taco_ppo_forward_loss(TacoPPO* ppo, const TacoPPOHyper* hyper, const float* obs, const float* states, const float* act,
+                          const float* old_logp, const float* adv, const float* ret, const int64_t* idx_dev, void* stream);
+int taco_ppo_loss_sums(TacoPPO* ppo, double** acc_dev);
+int taco_ppo_decide(TacoPPO* ppo, const TacoPPOHyper* hyper, void* stream);
+int taco_ppo_backward(TacoPPO* ppo, void* stream);
+int taco_ppo_apply(TacoPPO* ppo, const TacoPPOHyper* hyper, void* stream);
+/* synchronises; log rows of 8 floats per evaluated minibatch: policy-gradient loss, value loss, entropy loss, total loss, approx
+ * KL, gradient norm, stopped-here flag, clip coefficient */
+int taco_ppo_end_update(TacoPPO* ppo, float* log_host, int32_t max_rows, int32_t* n_rows, int32_t* optim_steps, int32_t* early_stop,
+                        void* stream);
+int taco_ppo_sigmas(TacoPPO* ppo, double* out_host);
+/* test hook: device addresses of the last forward results: action mean (batch, act_dim) and value (batch) */
+int taco_ppo_debug_outputs(TacoPPO* ppo, float** mean_dev, float** value_dev);
+/* self-test of the GEMM kernel: D (m, n) fp32 = A (m, k) B (n, k)^T for bf16 row-major device matrices, n <= 256, k % 8 == 0 */
+int taco_gemm_selftest(int device, const void* a_bf16, const void* b_bf16, float* d_f32, int32_t m, int32_t n, int32_t k, int32_t splits,
+                       void* stream);
+
 /* -- rollout-buffer post-processing: PPOReplayBuffer.compute_returns_and_advantage
  * (IsaacGymEnvs/algorithms/buffer_asymmetry.py:93-132) and the time-out bootstrap PPO applies to the reward it stores
  * (IsaacGymEnvs/algorithms/ppo_asymmetry.py:313-324).  All buffers are contiguous float32 (horizon, num_envs[, 1]) on

@@ -244,16 +244,21 @@ def ppo_update(ns):
     without __init__ (which needs an env and TensorBoard) and given exactly the attributes update() reads; the agent is the
     reference's PPO_ActorCritic (MLP actor, LSTM critic encoder); minibatch indices are fixed.  Two cases: plain, and with the
     spectral projection after every optimiser step."""
+    _ppo_update_cases(ns, 6, 16, 3, [32, 24], [20], 16, "ppo_update.npz")
+    # shapes the native update (taco_ppo_*, tcgen05 GEMMs) supports: LSTM width 64, hidden widths multiples of 16, minibatches of 256
+    _ppo_update_cases(ns, 8, 64, 2, [64, 48], [32], 64, "ppo_update_native.npz")
+
+
+def _ppo_update_cases(ns, H, N, mb, actor_hidden, critic_hidden, lstm_hidden, file_name):
     import io, contextlib, types
     import torch.nn as nn
     out = {}
-    H, N, mb = 6, 16, 3
     for tag, use_lip in (("plain", False), ("lip", True)):
         torch.manual_seed(900)
         para = {"actor_critic_mlp_dict": {"actor_input_dim": 26, "actor_output_dim": 4, "critic_input_dim": 26 * 5, "critic_output_dim": 1,
-                                          "actor_hidden_sizes": [32, 24], "critic_hidden_sizes": [20], "activation": nn.ReLU},
+                                          "actor_hidden_sizes": list(actor_hidden), "critic_hidden_sizes": list(critic_hidden), "activation": nn.ReLU},
                 "use_actor_encoder": False, "use_critic_encoder": True, "share_encoder": False, "critic_encoder_type": "LSTM",
-                "critic_encoder_dict": {"encoder_type": "LSTM", "input_size": 26, "output_size": 16, "num_layers": 1, "bidirectional": False}}
+                "critic_encoder_dict": {"encoder_type": "LSTM", "input_size": 26, "output_size": lstm_hidden, "num_layers": 1, "bidirectional": False}}
         with contextlib.redirect_stdout(io.StringIO()):
             agent = ns.nets.PPO_ActorCritic(para)
         with torch.no_grad():                                   # gains that make the projection bite on some layers only
@@ -297,7 +302,7 @@ def ppo_update(ns):
         out[f"{tag}_difficulty"] = torch.tensor(ppo.env.difficulty)
         for name, val in logged.items():
             out[f"{tag}_log__{name.split('/')[1].rstrip(':')}"] = torch.tensor(val)
-    np.savez(os.path.join(OUT, "ppo_update.npz"), **{k: np.asarray(t) for k, t in out.items()})
+    np.savez_compressed(os.path.join(OUT, file_name), **{k: np.asarray(t) for k, t in out.items()})
 
 
 def gae(ns):

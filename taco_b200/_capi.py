@@ -103,6 +103,22 @@ def lib():
         "taco_critic_load": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), vp]),
         "taco_critic_tc_available": (C.c_int, [vp]),
         "taco_critic_forward": (C.c_int, [vp, vp, vp, i32, i32, vp]),
+        "taco_ppo_create": (C.c_int, [C.c_int, vp, C.POINTER(vp)]),
+        "taco_ppo_destroy": (C.c_int, [vp]),
+        "taco_ppo_num_params": (C.c_int, [vp, C.POINTER(C.c_int64)]),
+        "taco_ppo_param_offsets": (C.c_int, [vp, C.POINTER(C.c_int64), i32, C.POINTER(i32)]),
+        "taco_ppo_buffers": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+        "taco_ppo_params_changed": (C.c_int, [vp, vp]),
+        "taco_ppo_begin_update": (C.c_int, [vp, vp]),
+        "taco_ppo_forward_loss": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "taco_ppo_loss_sums": (C.c_int, [vp, C.POINTER(vp)]),
+        "taco_ppo_decide": (C.c_int, [vp, vp, vp]),
+        "taco_ppo_backward": (C.c_int, [vp, vp]),
+        "taco_ppo_apply": (C.c_int, [vp, vp, vp]),
+        "taco_ppo_end_update": (C.c_int, [vp, vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), vp]),
+        "taco_ppo_sigmas": (C.c_int, [vp, vp]),
+        "taco_ppo_debug_outputs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
+        "taco_gemm_selftest": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, vp]),
         "taco_gae_advantages": (C.c_int, [C.c_int, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp]),
         "taco_gae_normalize": (C.c_int, [C.c_int, vp, C.c_int64, vp, vp]),
     }
@@ -119,6 +135,17 @@ def check(rc, what):
     if rc != 0:
         msg = lib().taco_last_error()
         raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+class TacoPPOCfg(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("state_dim", C.c_int32), ("seq_len", C.c_int32),
+                ("lstm_hidden", C.c_int32), ("n_actor_hidden", C.c_int32), ("actor_hidden", C.c_int32 * 4),
+                ("n_critic_hidden", C.c_int32), ("critic_hidden", C.c_int32 * 4)]
+
+
+class TacoPPOHyper(C.Structure):
+    _fields_ = [("lr", C.c_float), ("clip", C.c_float), ("target_kl", C.c_float), ("max_grad", C.c_float), ("pi_coef", C.c_float),
+                ("vf_coef", C.c_float), ("ent_coef", C.c_float), ("lipschitz", C.c_float), ("use_lipschitz", C.c_int32), ("world", C.c_int32)]
 
 
 class _CudaView:

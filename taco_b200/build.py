@@ -26,6 +26,7 @@ UNITS = [
     ("taco_actor.cu", []),
     ("taco_critic.cu", []),
     ("taco_gae.cu", ["-fmad=false"]),
+    ("taco_ppo.cu", []),
 ]
 
 

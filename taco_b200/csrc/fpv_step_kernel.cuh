@@ -29,12 +29,9 @@
 #error "define TACO_VARIANT (fast / strict) before including fpv_step_kernel.cuh"
 #endif
 
-// difficulty-dependent scalars: by-value kernel parameters, or -- in graph mode -- their device copy (step_params.h)
-#ifdef TACO_NO_DIFF_DEV      // tuning builds only: graph-mode difficulty changes are then ignored
-#define TACO_DIFF(field, idx) p.field
-#else
-#define TACO_DIFF(field, idx) (p.diff_dev ? __ldg(p.diff_dev + (idx)) : p.field)
-#endif
+// difficulty-dependent scalars: by-value kernel parameters, or -- in the kernel variants launched in graph mode (DEVDIFF) -- their
+// device copy (step_params.h), so that launches captured in a CUDA graph follow taco_env_set_difficulty
+#define TACO_DIFF(field, idx) (DEVDIFF ? __ldg(p.diff_dev + (idx)) : p.field)
 
 namespace taco {
 namespace TACO_VARIANT {   // distinct symbols per translation unit: the two builds must not be merged by the linker
@@ -94,7 +91,8 @@ __device__ __forceinline__ void write_rows(const float* __restrict__ in, float* 
 // TASK: task_mode (mix = per-env task from the global env id).  DR: per-env randomised model parameters live in the
 // D planes; when false the rotor polynomial / aero coefficients fold into instruction immediates.
 // SUB: physics sub-steps per simulate call (1 / 2 unrolled; 0 = runtime p.substeps).
-template <int TASK, bool DR, int SUB>
+// DEVDIFF: graph-mode variant (difficulty scalars from device memory; costs two spilled registers, so eager launches do not use it).
+template <int TASK, bool DR, int SUB, bool DEVDIFF = false>
 __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const StepParams p) {
     __shared__ float s_clean[kBlock * kFramePad];
     __shared__ float s_noisy[kBlock * kFramePad];
@@ -658,7 +656,15 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
 template <int TASK>
 static void launch_task(const StepParams& p, cudaStream_t stream) {
     const int grid = p.nblocks > 0 ? p.nblocks : p.n_pad / kBlock - p.block0;
-    if (p.has_dr) {
+    if (p.diff_dev != nullptr) {                       // graph mode (taco_env_graph_begin .. _end)
+        if (p.has_dr) {
+            if (p.substeps == 2) fpv_step_kernel<TASK, true, 2, true><<<grid, kBlock, 0, stream>>>(p);
+            else fpv_step_kernel<TASK, true, 0, true><<<grid, kBlock, 0, stream>>>(p);
+        } else {
+            if (p.substeps == 2) fpv_step_kernel<TASK, false, 2, true><<<grid, kBlock, 0, stream>>>(p);
+            else fpv_step_kernel<TASK, false, 0, true><<<grid, kBlock, 0, stream>>>(p);
+        }
+    } else if (p.has_dr) {
         if (p.substeps == 2) fpv_step_kernel<TASK, true, 2><<<grid, kBlock, 0, stream>>>(p);
         else if (p.substeps == 1) fpv_step_kernel<TASK, true, 1><<<grid, kBlock, 0, stream>>>(p);
         else fpv_step_kernel<TASK, true, 0><<<grid, kBlock, 0, stream>>>(p);

@@ -331,6 +331,8 @@ int taco_env_create(const TacoCfg* cfg, int device, TacoEnv** out) {
     p.lag_gain_fixed = (cfg->flags & TACO_F_ROTOR_RESPONSE) ? (1.0f / cfg->rotor_response_time) * 0.001f : (1.0f / 0.001f) * 0.001f;
     p.has_dr = (cfg->flags & (TACO_F_RANDOM_ROTORDYNAMIC_COE | TACO_F_RANDOM_ROTOR_RESPONSE | TACO_F_RANDOM_AERODYNAMIC_COE)) ? 1 : 0;
     refresh_derived(e);
+    if (cudaMalloc(&e->diff_dev, 9 * sizeof(float)) != cudaSuccess) { delete e; return fail(TACO_E_NOMEM, "cudaMalloc of the difficulty block failed"); }
+    if (upload_derived(e) != cudaSuccess) { cudaFree(e->diff_dev); delete e; return fail(TACO_E_CUDA, "upload of the difficulty block failed"); }
 
     // ---- one arena, every plane 512-byte aligned
     const size_t A = 512;
@@ -608,8 +610,6 @@ int taco_env_graph_begin(TacoEnv* env, void* stream) {
     if (!env) return fail(TACO_E_INVALID, "taco_env_graph_begin: null argument");
     DeviceGuard guard(env->device);
     if (!env->step_counter) TACO_CUDA(cudaMalloc(&env->step_counter, sizeof(uint32_t)));
-    if (!env->diff_dev) TACO_CUDA(cudaMalloc(&env->diff_dev, 9 * sizeof(float)));
-    TACO_CUDA(upload_derived(env));
     step_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(env->step_counter, env->step_index, 0); TACO_LAUNCHED();
     TACO_CUDA(cudaGetLastError());
     env->graph_mode = true;
