@@ -3,7 +3,9 @@
 (IsaacGymEnvs/train/train_fpv_asymmetry_ppo.py:363-538, IsaacGymEnvs/algorithms/ppo_asymmetry.py:260-342) with
   rollout  = GraphedRollout: actor kernel -> critic kernel -> fused env step, zero-copy into the RolloutBuffer, GAE on the device,
              the whole horizon replayed as ONE CUDA graph (--no-graph: the eager collect_rollout loop)
-  update   = taco_b200.ppo.ppo_update (PyTorch autograd; spectral projection on the device; gradients averaged over ranks)
+  update   = taco_b200.ppo_native.NativePPO (tcgen05 GEMM forward / backward, device-side KL early stop, Adam and spectral projection
+             kernels; loss sums and the flat gradient all-reduced over ranks); --update torch: taco_b200.ppo.ppo_update (PyTorch
+             autograd, the fp32 parity path)
 
     python examples/train_fpv_ppo.py --task pos --num-envs 4096 --epochs 60
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 examples/train_fpv_ppo.py --num-envs 65536
@@ -33,6 +35,7 @@ def main():
     ap.add_argument("--lstm-hidden", type=int, default=64)
     ap.add_argument("--lipschitz", type=float, default=4.0, help="README training command: --lipschitz_para=4; 0 disables")
     ap.add_argument("--tensor-cores", default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--update", default="native", choices=["native", "torch"])
     ap.add_argument("--no-graph", action="store_true", help="collect rollouts with the eager loop instead of one CUDA-graph replay per rollout")
     ap.add_argument("--seed", type=int, default=42)
     args = ap.parse_args()
@@ -41,7 +44,8 @@ def main():
     import torch.distributed as dist
     import taco_b200
     from taco_b200 import dist as tdist
-    from taco_b200.ppo import PPOConfig, TorchActorCritic, make_optimizer, ppo_update, sync_rollout_nets
+    from taco_b200.ppo import PPOConfig, TorchActorCritic, make_optimizer, ppo_update, sync_rollout_nets, sync_rollout_nets_native
+    from taco_b200.ppo_native import NativePPO
 
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -60,6 +64,10 @@ def main():
                     lipschitz_para=args.lipschitz, lip_epoch_index=[args.epochs // 5, args.epochs],
                     diff_epoch_index=[args.epochs // 5, args.epochs], lr_epoch_index=int(0.7 * args.epochs))
     opt = make_optimizer(agent, cfg)
+    native = None
+    if args.update == "native":
+        native = NativePPO(agent, n * args.horizon // args.mini_batch_num, device=dev)
+        native._create(env.len_states)
     actor = taco_b200.ActorMLP(26 * env.len_obs, a_hid, 4, device=dev)
     critic = taco_b200.CriticLSTM(26, env.len_states, args.lstm_hidden, c_hid, device=dev)
     buf = taco_b200.RolloutBuffer(n, 26, env.len_obs, 26, env.len_states, 4, args.horizon, args.mini_batch_num, 0.99, 0.95, dev)
@@ -69,7 +77,10 @@ def main():
     graphed = None
     for epoch in range(args.epochs):
         ts = time.perf_counter()
-        sync_rollout_nets(agent, actor, critic)
+        if native is not None:
+            sync_rollout_nets_native(native, actor, critic)
+        else:
+            sync_rollout_nets(agent, actor, critic)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         if args.no_graph:
@@ -83,7 +94,10 @@ def main():
         t1 = time.perf_counter()
         n_s = n * args.horizon
         idx = torch.randperm(n_s, device=dev).view(args.mini_batch_num, -1)
-        out = ppo_update(agent, opt, buf, cfg, epoch, env=env, batch_idx=list(idx))
+        if native is not None:
+            out = native.update(buf, cfg, epoch, env=env, batch_idx=list(idx))
+        else:
+            out = ppo_update(agent, opt, buf, cfg, epoch, env=env, batch_idx=list(idx))
         torch.cuda.synchronize()
         t2 = time.perf_counter()
         if rank == 0:
@@ -93,9 +107,12 @@ def main():
                               "pg_loss": out["policy_gradient_loss"], "value_loss": out["value_loss"], "kl": out["approx_kl"],
                               "optim_steps": out["optim_steps"], "sync_s": t0 - ts, "rollout_s": t1 - t0, "update_s": t2 - t1,
                               "rollout_env_steps_per_s": world * n_s / (t1 - t0), "loop_env_steps_per_s": world * n_s / (t2 - ts),
-                              "tensor_cores": bool(tc), "world": world}), flush=True)
+                              "tensor_cores": bool(tc), "update": args.update, "early_stop": out["early_stop"], "world": world}), flush=True)
     if graphed is not None:
         graphed.close()
+    if native is not None:
+        native.store_to(agent, opt)                 # the torch module / optimiser hold the trained state again (checkpoints, export)
+        native.close()
     env.close(); actor.close(); critic.close()
     if world > 1:
         dist.destroy_process_group()

@@ -187,7 +187,7 @@ typedef struct TacoActor TacoActor;
 /* sizes = [in, h1, ..., hL, out] (n_sizes entries, out <= 4 = num_acts) */
 int taco_actor_create(int device, const int32_t* sizes, int32_t n_sizes, TacoActor** out);
 int taco_actor_destroy(TacoActor* actor);
-/* weights/biases: host float32, row-major (out,in) per layer like nn.Linear.  With lipschitz_const > 0 every weight
+/* weights/biases: float32 arrays in HOST OR DEVICE memory (unified addressing), row-major (out,in) per layer like nn.Linear.  With lipschitz_const > 0 every weight
  * matrix whose largest singular value sigma exceeds it is scaled by lipschitz_const / sigma on the device (power
  * iteration in double precision) -- the reference does this after each optimiser step, so calling it once per update
  * gives rollouts pre-normalised weights; lipschitz_const = 0 only measures the norms (taco_actor_sigmas), a negative value skips
@@ -233,7 +233,7 @@ typedef struct TacoCritic TacoCritic;
 int taco_critic_create(int device, int32_t in_dim, int32_t seq_len, int32_t lstm_hidden, int32_t lstm_layers,
                        const int32_t* mlp_sizes, int32_t n_mlp_sizes, TacoCritic** out);
 int taco_critic_destroy(TacoCritic* critic);
-/* lstm_host: 4 host float32 arrays per LSTM layer, bottom layer first, in torch's nn.LSTM layout and order: weight_ih (4H, in),
+/* lstm_host: 4 float32 arrays (host or device memory) per LSTM layer, bottom layer first, in torch's nn.LSTM layout and order: weight_ih (4H, in),
  * weight_hh (4H, H), bias_ih (4H), bias_hh (4H); gate row blocks i, f, g, o.  mlp weights/biases as in taco_actor_load.
  * Synchronises the stream (the host buffers are free on return). */
 int taco_critic_load(TacoCritic* critic, const float* const* lstm_host, const float* const* mlp_weights_host,

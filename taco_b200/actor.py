@@ -16,6 +16,21 @@ import torch
 from . import _capi
 
 
+def _as_f32(x, device_id):
+    """Contiguous float32 view for the loaders: CUDA tensors on the kernels' device are passed as they are (device pointer, no host
+    round trip); anything else becomes a numpy array."""
+    if isinstance(x, torch.Tensor):
+        x = x.detach()
+        if x.device.type == "cuda" and (x.device.index or 0) == device_id:
+            return x.to(torch.float32).contiguous()
+        return np.ascontiguousarray(x.cpu().numpy(), dtype=np.float32)
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def _ptr(x):
+    return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
+
+
 class ActorMLP:
     def __init__(self, input_size, hidden_size, output_size=_capi.NUM_ACTS, device="cuda:0"):
         if not torch.cuda.is_available():
@@ -51,13 +66,12 @@ class ActorMLP:
             raise ValueError(f"expected {self.n_layers} layers")
         ws, bs = [], []
         for l in range(self.n_layers):
-            w = np.ascontiguousarray(weights[l].detach().cpu().numpy() if isinstance(weights[l], torch.Tensor) else weights[l], dtype=np.float32)
-            b = np.ascontiguousarray(biases[l].detach().cpu().numpy() if isinstance(biases[l], torch.Tensor) else biases[l], dtype=np.float32)
-            if w.shape != (self.sizes[l + 1], self.sizes[l]) or b.shape != (self.sizes[l + 1],):
+            w, b = _as_f32(weights[l], self.device_id), _as_f32(biases[l], self.device_id)
+            if tuple(w.shape) != (self.sizes[l + 1], self.sizes[l]) or tuple(b.shape) != (self.sizes[l + 1],):
                 raise ValueError(f"layer {l}: expected weight {(self.sizes[l + 1], self.sizes[l])}, bias {(self.sizes[l + 1],)}")
             ws.append(w); bs.append(b)
-        wp = (C.c_void_p * self.n_layers)(*[w.ctypes.data for w in ws])
-        bp = (C.c_void_p * self.n_layers)(*[b.ctypes.data for b in bs])
+        wp = (C.c_void_p * self.n_layers)(*[_ptr(w) for w in ws])
+        bp = (C.c_void_p * self.n_layers)(*[_ptr(b) for b in bs])
         _capi.check(self._lib.taco_actor_load(self._h, wp, bp, float(lipschitz_const), self._stream()), "taco_actor_load")
         if log_std is not None:
             self.set_log_std(log_std)

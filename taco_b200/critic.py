@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from . import _capi
+from .actor import _as_f32, _ptr
 
 
 def _np(t):
@@ -60,19 +61,19 @@ class CriticLSTM:
         flat = []
         for l, prm in enumerate(lstm_params):
             in_l = self.input_size if l == 0 else H
-            w_ih, w_hh, b_ih, b_hh = (_np(x) for x in prm)
-            if w_ih.shape != (4 * H, in_l) or w_hh.shape != (4 * H, H) or b_ih.shape != (4 * H,) or b_hh.shape != (4 * H,):
+            w_ih, w_hh, b_ih, b_hh = (_as_f32(x, self.device_id) for x in prm)
+            if tuple(w_ih.shape) != (4 * H, in_l) or tuple(w_hh.shape) != (4 * H, H) or tuple(b_ih.shape) != (4 * H,) or tuple(b_hh.shape) != (4 * H,):
                 raise ValueError(f"LSTM layer {l}: expected weight_ih {(4 * H, in_l)}, weight_hh {(4 * H, H)}, biases {(4 * H,)}")
             flat += [w_ih, w_hh, b_ih, b_hh]
         ws, bs = [], []
         for l in range(self.n_mlp_layers):
-            w, b = _np(mlp_weights[l]), _np(mlp_biases[l])
-            if w.shape != (self.mlp_sizes[l + 1], self.mlp_sizes[l]) or b.shape != (self.mlp_sizes[l + 1],):
+            w, b = _as_f32(mlp_weights[l], self.device_id), _as_f32(mlp_biases[l], self.device_id)
+            if tuple(w.shape) != (self.mlp_sizes[l + 1], self.mlp_sizes[l]) or tuple(b.shape) != (self.mlp_sizes[l + 1],):
                 raise ValueError(f"MLP layer {l}: expected weight {(self.mlp_sizes[l + 1], self.mlp_sizes[l])}, bias {(self.mlp_sizes[l + 1],)}")
             ws.append(w); bs.append(b)
-        lp = (C.c_void_p * len(flat))(*[a.ctypes.data for a in flat])
-        wp = (C.c_void_p * len(ws))(*[a.ctypes.data for a in ws])
-        bp = (C.c_void_p * len(bs))(*[a.ctypes.data for a in bs])
+        lp = (C.c_void_p * len(flat))(*[_ptr(a) for a in flat])
+        wp = (C.c_void_p * len(ws))(*[_ptr(a) for a in ws])
+        bp = (C.c_void_p * len(bs))(*[_ptr(a) for a in bs])
         _capi.check(self._lib.taco_critic_load(self._h, lp, wp, bp, self._stream()), "taco_critic_load")
 
     def load_modules(self, critic_encoder, critic_mlp):

@@ -362,8 +362,8 @@ int taco_actor_load(TacoActor* a, const float* const* weights_host, const float*
     cudaStream_t s = (cudaStream_t)stream;
     for (int l = 0; l < a->n_layers; ++l) {
         const int in = a->sizes[l], out = a->sizes[l + 1];
-        ACT_CUDA(cudaMemcpyAsync(a->w_f32 + a->w_off[l], weights_host[l], (size_t)in * out * sizeof(float), cudaMemcpyHostToDevice, s));
-        ACT_CUDA(cudaMemcpyAsync(a->b_f32 + a->b_off[l], biases_host[l], (size_t)out * sizeof(float), cudaMemcpyHostToDevice, s));
+        ACT_CUDA(cudaMemcpyAsync(a->w_f32 + a->w_off[l], weights_host[l], (size_t)in * out * sizeof(float), cudaMemcpyDefault, s));
+        ACT_CUDA(cudaMemcpyAsync(a->b_f32 + a->b_off[l], biases_host[l], (size_t)out * sizeof(float), cudaMemcpyDefault, s));
     }
     // spectral projection of every weight matrix (ppo_asymmetry.py:398-404); also records sigma when lipschitz_const <= 0
     for (int l = 0; l < a->n_layers && lipschitz_const >= 0.0f; ++l) {        // negative: weights are known to be projected, skip the measurement

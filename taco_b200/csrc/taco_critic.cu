@@ -337,12 +337,12 @@ int taco_critic_load(TacoCritic* c, const float* const* lstm_host, const float* 
         const int in_l = l == 0 ? c->in_dim : H;
         const size_t sz[4] = {(size_t)4 * H * in_l, (size_t)4 * H * H, (size_t)4 * H, (size_t)4 * H};
         for (int q = 0; q < 4; ++q)
-            CRT_CUDA(cudaMemcpyAsync(c->lstm_f32 + c->lstm_off[4 * l + q], lstm_host[4 * l + q], sz[q] * sizeof(float), cudaMemcpyHostToDevice, s));
+            CRT_CUDA(cudaMemcpyAsync(c->lstm_f32 + c->lstm_off[4 * l + q], lstm_host[4 * l + q], sz[q] * sizeof(float), cudaMemcpyDefault, s));
     }
     for (int l = 0; l < c->n_mlp; ++l) {
         const int in = c->mlp_sizes[l], out = c->mlp_sizes[l + 1];
-        CRT_CUDA(cudaMemcpyAsync(c->w_f32 + c->w_off[l], mlp_weights_host[l], (size_t)in * out * sizeof(float), cudaMemcpyHostToDevice, s));
-        CRT_CUDA(cudaMemcpyAsync(c->b_f32 + c->b_off[l], mlp_biases_host[l], (size_t)out * sizeof(float), cudaMemcpyHostToDevice, s));
+        CRT_CUDA(cudaMemcpyAsync(c->w_f32 + c->w_off[l], mlp_weights_host[l], (size_t)in * out * sizeof(float), cudaMemcpyDefault, s));
+        CRT_CUDA(cudaMemcpyAsync(c->b_f32 + c->b_off[l], mlp_biases_host[l], (size_t)out * sizeof(float), cudaMemcpyDefault, s));
     }
     if (c->tc_ok) {
         const int n_hidden = c->n_mlp - 1;

@@ -100,35 +100,53 @@ struct GatherParams {
     float* g_act; float* g_logp; float* g_adv; float* g_ret;
     const int* stop;
 };
-__global__ void gather_kernel(const GatherParams p) {
+// one operand matrix for the 32 samples of a CTA: features [0, n_src) come from the sample's source row, [n_src, n_src + n_one) are
+// the constant 1, the rest up to n_out is 0; written batch-major (rows of the samples) and feature-major (runs of 32 samples), both
+// in 64-byte segments, through a shared-memory tile
+__device__ __forceinline__ void gather_matrix(float (*tile)[33], const float* src, long long src_stride, const long long* rows, int n_valid,
+                                              int n_src, int n_one, int n_out, bf16* bm, long long ld_bm, bf16* fm, long long ld_fm) {
+    for (int f0 = 0; f0 < n_out; f0 += 64) {
+        const int nf = min(64, n_out - f0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < 32 * nf; e += blockDim.x) {
+            const int sidx = e / nf, j = e % nf, f = f0 + j;
+            float v = 0.0f;
+            if (sidx < n_valid) v = f < n_src ? __ldg(src + rows[sidx] * src_stride + f) : (f < n_src + n_one ? 1.0f : 0.0f);
+            tile[j][sidx] = v;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < 32 * nf; e += blockDim.x) {
+            const int sidx = e / nf, j = e % nf;
+            if (sidx < n_valid) bm[(long long)sidx * ld_bm + f0 + j] = __float2bfloat16_rn(tile[j][sidx]);
+        }
+        for (int e = threadIdx.x; e < 32 * nf; e += blockDim.x) {
+            const int j = e >> 5, sidx = e & 31;
+            if (sidx < n_valid) fm[(long long)(f0 + j) * ld_fm + sidx] = __float2bfloat16_rn(tile[j][sidx]);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) gather_kernel(const GatherParams p) {
     if (p.stop && *p.stop) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.B) return;
-    const long long r = p.idx[i];
-    const float* o = p.obs + r * p.obs_dim;
-    const int kx = (p.obs_dim + 7) & ~7;
-    for (int j = 0; j < kx; ++j) {
-        const bf16 v = __float2bfloat16_rn(j < p.obs_dim ? __ldg(o + j) : 0.0f);
-        p.x0_bm[(long long)i * p.ld_x0 + j] = v;
-        p.x0_fm[(long long)j * p.B + i] = v;
-    }
+    __shared__ float tile[64][33];
+    __shared__ long long rows[32];
+    const int i0 = blockIdx.x * 32;
+    const int nv = min(32, p.B - i0);
+    if (threadIdx.x < 32) rows[threadIdx.x] = threadIdx.x < nv ? p.idx[i0 + threadIdx.x] : 0;
+    __syncthreads();
+    gather_matrix(tile, p.obs, p.obs_dim, rows, nv, p.obs_dim, 0, (p.obs_dim + 7) & ~7, p.x0_bm + (long long)i0 * p.ld_x0, p.ld_x0, p.x0_fm + i0, p.B);
     const long long SB = (long long)p.seq * p.B;
-    for (int t = 0; t < p.seq; ++t) {
-        const float* s = p.states + (r * p.seq + t) * p.state_dim;
-        bf16* ub = p.u_bm + ((long long)t * p.B + i) * p.ld_u;
-        for (int j = kH; j < p.ld_u; ++j) {
-            const int c = j - kH;
-            const float v = c < p.state_dim ? __ldg(s + c) : (c < p.state_dim + 2 ? 1.0f : 0.0f);     // two constant-1 inputs carry the bias (hi + lo)
-            const bf16 b = __float2bfloat16_rn(v);
-            ub[j] = b;
-            p.u_fm[(long long)j * SB + (long long)t * p.B + i] = b;
-        }
-        if (t == 0) {                                                   // h_0 = 0 (nets_asymmetry.py:132: default zero initial state)
-            for (int j = 0; j < kH; ++j) { ub[j] = __float2bfloat16_rn(0.0f); p.u_fm[(long long)j * SB + i] = __float2bfloat16_rn(0.0f); }
-        }
+    // U_t = [h_{t-1} (64, written by the previous LSTM step; h_0 = 0 stays as allocated) | x_t | 1 1 | 0]: two constant-1 inputs carry the bias
+    for (int t = 0; t < p.seq; ++t)
+        gather_matrix(tile, p.states + (long long)t * p.state_dim, (long long)p.seq * p.state_dim, rows, nv, p.state_dim, 2, p.ld_u - kH,
+                      p.u_bm + ((long long)t * p.B + i0) * p.ld_u + kH, p.ld_u, p.u_fm + (long long)kH * SB + (long long)t * p.B + i0, SB);
+    for (int e = threadIdx.x; e < nv * (p.act_dim + 3); e += blockDim.x) {
+        const int sidx = e / (p.act_dim + 3), c = e % (p.act_dim + 3);
+        const long long r = rows[sidx];
+        if (c < p.act_dim) p.g_act[(long long)(i0 + sidx) * p.act_dim + c] = __ldg(p.act + r * p.act_dim + c);
+        else if (c == p.act_dim) p.g_logp[i0 + sidx] = __ldg(p.logp + r);
+        else if (c == p.act_dim + 1) p.g_adv[i0 + sidx] = __ldg(p.adv + r);
+        else p.g_ret[i0 + sidx] = __ldg(p.ret + r);
     }
-    for (int a = 0; a < p.act_dim; ++a) p.g_act[(long long)i * p.act_dim + a] = __ldg(p.act + r * p.act_dim + a);
-    p.g_logp[i] = __ldg(p.logp + r); p.g_adv[i] = __ldg(p.adv + r); p.g_ret[i] = __ldg(p.ret + r);
 }
 
 // PPO_ActorCritic.evaluate + losses (nets_asymmetry.py:356-377, ppo_asymmetry.py:190-221), one thread per sample
@@ -540,6 +558,11 @@ static int launch_gemm(TacoPPO* t, const CUtensorMap& a, const CUtensorMap& b, G
     p.kb_per_split = (kb_total + p.splits - 1) / p.splits;
     p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;       // no empty split
     p.stop = t->stop;
+    if (const char* dbg = getenv("TACO_PPO_DEBUG_SKIP")) {            // timing experiments only (wrong results): drop one of the output copies
+        if (strstr(dbg, "fm")) p.out_fm = nullptr;
+        if (strstr(dbg, "bm")) p.out_bm = nullptr;
+        if (strstr(dbg, "hfm")) p.lstm.h_fm = nullptr;
+    }
     const int total = ((p.m + BM - 1) / BM) * p.splits;
     const int grid = total < t->num_sms ? total : t->num_sms;
     gemm_tc_kernel<<<grid, kGemmThreads, kGemmSmem, s>>>(a, b, p); TACO_LAUNCHED();
@@ -836,7 +859,7 @@ int taco_ppo_forward_loss(TacoPPO* t, const TacoPPOHyper* hyper, const float* ob
     g.x0_bm = t->actor.x_bm[0]; g.ld_x0 = t->actor.ld_x[0]; g.x0_fm = t->actor.x_fm[0];
     g.u_bm = t->u_bm; g.u_fm = t->u_fm; g.ld_u = t->ld_u;
     g.g_act = t->g_act; g.g_logp = t->g_logp; g.g_adv = t->g_adv; g.g_ret = t->g_ret; g.stop = t->stop;
-    gather_kernel<<<(B + 127) / 128, 128, 0, s>>>(g); TACO_LAUNCHED();
+    gather_kernel<<<(B + 31) / 32, 256, 0, s>>>(g); TACO_LAUNCHED();
     int rc = mlp_forward(t, t->actor, true, s);
     if (rc != TACO_OK) return rc;
     // critic: seq LSTM steps, each one GEMM [h_{t-1} | x_t | 1 1] Wcat^T with the gate math in the epilogue

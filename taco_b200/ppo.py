@@ -239,6 +239,20 @@ def ppo_update(agent, optimizer, buffer, cfg, epoch, env=None, batch_idx=None, g
             "early_stop": not keep_going}
 
 
+def sync_rollout_nets_native(native, actor=None, critic=None):
+    """``sync_rollout_nets`` for a ``NativePPO``: the rollout kernels load straight from the trainer's flat device parameter vector
+    (device-to-device copies; no torch module, no host round trip)."""
+    v = native._views(native.params)
+    if actor is not None:
+        n = native._cfg.n_actor_hidden + 1
+        actor.load([v[f"actor_mlp.layers.{2 * l}.weight"] for l in range(n)], [v[f"actor_mlp.layers.{2 * l}.bias"] for l in range(n)],
+                   lipschitz_const=-1.0, log_std=v["log_std"])
+    if critic is not None:
+        n = native._cfg.n_critic_hidden + 1
+        critic.load([tuple(v[f"critic_encoder.layers.{k}_l0"] for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))],
+                    [v[f"critic_mlp.layers.{2 * l}.weight"] for l in range(n)], [v[f"critic_mlp.layers.{2 * l}.bias"] for l in range(n)])
+
+
 def sync_rollout_nets(agent, actor=None, critic=None):
     """Copy the trained weights into the rollout kernels: once per update (the stored actor weights are already projected)."""
     if actor is not None:

@@ -31,4 +31,4 @@ for f in sorted(glob.glob('gpurun_out/windows_flip_r02e_*.json')):
         d=json.load(open(f)); print(f, [w['ms_per_step'] for w in d['windows']])
     except Exception as e: print(f, 'ERR', e)
 PY
-timeout 600 python -m pytest tests -m gpu -q -x -k "rollout or graphed or checkpoint" 2>&1 | tail -3
+timeout 900 python -m pytest tests -m gpu -q -x -k "rollout or graphed or checkpoint or ppo_native" 2>&1 | tail -15
