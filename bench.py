@@ -472,6 +472,42 @@ def policy_loop_point(torch, dist, taco_b200, dev, rank, world, n, hidden, horiz
             "episodes_finished_last_rollout": float(stats[1].item())}
 
 
+def native_update_point(torch, dev, hidden, n=4096, horizon=64, mb=4, iters=4, reps=3):
+    """SURVEY.md section 8f row 4 at the reference's scale (README.md:41: 4096 envs): one PPO.update (ppo_asymmetry.py:137-258) =
+    mb x iters optimiser steps on the rollout of n envs x horizon steps, on the native kernels (taco_ppo_*: tcgen05 GEMM forward /
+    backward, device-side KL early stop, Adam, spectral projection) and on the PyTorch-autograd twin."""
+    import types
+    from taco_b200.ppo import PPOConfig, TorchActorCritic, make_optimizer, ppo_update
+    from taco_b200.ppo_native import NativePPO
+    agent = TorchActorCritic(26, 4, list(hidden), 26, 64, list(hidden)).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(SEED)
+    rnd = lambda *sh: torch.randn(*sh, device=dev, generator=gen)
+    buf = types.SimpleNamespace(obs_buf=rnd(horizon, n, 1, 26) * 0.5, states_buf=rnd(horizon, n, 5, 26) * 0.5, act_buf=rnd(horizon, n, 4).clamp(-1, 1),
+                                value_buf=torch.zeros(horizon, n, 1, device=dev), ret_buf=rnd(horizon, n, 1) * 0.3, adv_buf=rnd(horizon, n, 1))
+    with torch.no_grad():
+        buf.logp_buf = agent.evaluate(buf.obs_buf.view(-1, 1, 26), buf.states_buf.view(-1, 5, 26), buf.act_buf.view(-1, 4))[0].view(horizon, n, 1)
+    cfg = PPOConfig(train_iters=iters, use_lipschitz=True, lipschitz_para=4.0, target_kl=1e9)
+    perm = torch.randperm(horizon * n, device=dev, generator=gen).view(mb, -1)
+    idx = [perm[i] for i in range(mb)]
+    nat = NativePPO(agent, perm.shape[1], device=dev)
+    nat.update(buf, cfg, 0, batch_idx=idx)
+    ms = _timed(torch, lambda: nat.update(buf, cfg, 1, batch_idx=idx), reps, warm=1)
+    nat.close()
+    opt = make_optimizer(agent, cfg)
+    ppo_update(agent, opt, buf, cfg, 0, batch_idx=idx)
+    ms_t = _timed(torch, lambda: ppo_update(agent, opt, buf, cfg, 1, batch_idx=idx), 1, warm=0)
+    sizes = [26] + list(hidden) + [4]
+    csz = [64] + list(hidden) + [1]
+    flops = 3.0 * (2.0 * sum(sizes[i] * sizes[i + 1] for i in range(len(sizes) - 1)) + 5 * 2.0 * (26 + 64) * 256
+                   + 2.0 * sum(csz[i] * csz[i + 1] for i in range(len(csz) - 1)))
+    steps = mb * iters
+    return {"workload": f"PPO.update on {n} envs x {horizon} steps: {mb} minibatches x {iters} iterations = {steps} optimiser steps of {perm.shape[1]} samples; "
+                        f"actor {'-'.join(map(str, sizes))}, critic LSTM 64 + MLP {'-'.join(map(str, csz))}, spectral projection on (sizes are OUR stated default)",
+            "native_update_ms": ms, "native_ms_per_optim_step": ms / steps, "autograd_update_ms": ms_t, "speedup_vs_autograd": ms_t / ms,
+            "flops_per_sample_fwd_bwd": flops, "achieved_tflops": flops * perm.shape[1] * steps / (ms * 1e-3) / 1e12,
+            "samples_per_s": perm.shape[1] * steps / (ms * 1e-3)}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -628,6 +664,10 @@ def main():
     actor_pt = None
     if not args.no_actor and world == 1:
         actor_pt = actor_rollout_point(torch, taco_b200, dev, args.actor_envs, hidden, strict, peaks)
+        try:
+            extra["ppo_update_4096x64"] = native_update_point(torch, dev, hidden)
+        except Exception as exc:
+            extra["ppo_update_4096x64"] = {"error": repr(exc)}
     if rank == 0:
         algo = ALGO_BYTES_DR if args.dr else ALGO_BYTES_NO_DR
         kernel_ms = ms / args.steps

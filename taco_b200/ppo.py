@@ -180,6 +180,7 @@ def ppo_update(agent, optimizer, buffer, cfg, epoch, env=None, batch_idx=None, g
     ``project(params, c)``: the spectral projection (default: the device kernel, ``taco_b200.spectral_normalize_``).
     Returns the scalars the reference logs (``log_update``, :438-450)."""
     agent.train()
+    torch.cuda.nvtx.range_push("taco.update_autograd") if torch.cuda.is_available() else None
     lr, lip, diff = schedules(cfg, epoch)
     optimizer.param_groups[0]["lr"] = lr
     if env is not None:
@@ -233,6 +234,7 @@ def ppo_update(agent, optimizer, buffer, cfg, epoch, env=None, batch_idx=None, g
         if not keep_going:
             break
     agent.eval()
+    torch.cuda.nvtx.range_pop() if torch.cuda.is_available() else None
     mean = lambda xs: float(sum(xs) / max(len(xs), 1))
     return {"policy_gradient_loss": mean(pg_l), "value_loss": mean(v_l), "entropy_loss": mean(e_l), "sum_loss": mean(s_l),
             "approx_kl": mean(kls), "learning_rate": lr, "lipschitz_para": lip, "difficulty": diff, "optim_steps": steps,

@@ -133,6 +133,13 @@ class NativePPO:
         lr, lip, diff = schedules(cfg, epoch)
         if env is not None:
             env.difficulty = diff
+        torch.cuda.nvtx.range_push("taco.update")
+        try:
+            return self._update(buffer, cfg, lr, lip, diff, batch_idx, group)
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    def _update(self, buffer, cfg, lr, lip, diff, batch_idx, group):
         flat = lambda t: t.reshape(-1, *t.shape[2:]).contiguous()
         obs, states, act = flat(buffer.obs_buf), flat(buffer.states_buf), buffer.act_buf.reshape(-1, buffer.act_buf.size(-1)).contiguous()
         ret, old_logp, adv = buffer.ret_buf.reshape(-1).contiguous(), buffer.logp_buf.reshape(-1).contiguous(), buffer.adv_buf.reshape(-1).contiguous()

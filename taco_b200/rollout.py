@@ -150,6 +150,7 @@ def collect_rollout(env, actor, buffer, value_fn, seed=0, tensor_cores=True, gro
     env's device-side vector, all-reduced once.  Returns the (8,) float64 statistics tensor (see taco_b200.dist.STAT_NAMES)."""
     from . import dist as tdist
     from .critic import CriticLSTM
+    torch.cuda.nvtx.range_push("taco.rollout")                    # NVTX: rollout / gae / update ranges (SURVEY.md section 5)
     if env.rollout_buffer is not buffer:
         env.attach_rollout(buffer)
     else:
@@ -176,7 +177,10 @@ def collect_rollout(env, actor, buffer, value_fn, seed=0, tensor_cores=True, gro
         last_value = value_fn.forward(buffer.states_ring[H], tensor_cores=critic_tc)
     else:
         last_value = value_fn(buffer.obs_ring[H], buffer.states_ring[H])
+    torch.cuda.nvtx.range_pop()
+    torch.cuda.nvtx.range_push("taco.gae")
     buffer.compute_returns_and_advantage(last_value, group=group)
+    torch.cuda.nvtx.range_pop()
     return tdist.allreduce_rollout_stats(env.stats(), group=group)
 
 
@@ -256,7 +260,9 @@ class GraphedRollout:
 
     def run(self):
         """One rollout.  Returns the (8,) float64 statistics tensor (all-reduced under torch.distributed)."""
+        torch.cuda.nvtx.range_push("taco.rollout_graph")
         self.graph.replay()
+        torch.cuda.nvtx.range_pop()
         self.replays += 1
         self.env.step_count += self.buffer.horizon_len
         if self.world > 1:
