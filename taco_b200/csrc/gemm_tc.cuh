@@ -5,7 +5,8 @@
 //   tile       128 (M) x n_tile (N <= 256, multiple of 16) per work item; K in blocks of 64 (one 128-byte swizzle row), 16 per MMA
 //   work item  (m_tile, k_split): split-K gives the K = batch GEMMs of the weight gradients (2 output tiles) enough CTAs; every
 //              split writes its own fp32 partial, which the gradient-norm kernel sums in a fixed order (bit-reproducible)
-//   pipeline   persistent CTAs; warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..5 = epilogue;
+//   pipeline   persistent CTAs; warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..9 = epilogue (two per
+//              TMEM lane quarter, alternating 32-column chunks: the epilogue is latency-bound, so two warps per scheduler);
 //              4 smem stages (full / empty mbarriers), 2 accumulators of 256 TMEM columns (tmem_full / tmem_empty), so the
 //              epilogue of one work item overlaps the MMAs of the next
 //   epilogues  EPI_F32            out_f32[split][m][n] = acc (+ bias[n])
@@ -33,10 +34,10 @@ using namespace taco::actor;
 
 constexpr int BM = 128, BK = 64;
 constexpr int kStages = 4;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 column halves x 4 TMEM lane quarters)
 constexpr int kStageA = BM * BK * 2;          // 16 KB
 constexpr int kStageB = 256 * BK * 2;         // 32 KB (n_tile <= 256)
-constexpr int kGemmSmem = 1024 + kStages * (kStageA + kStageB) + 256;
+constexpr int kGemmSmem = 1024 + kStages * (kStageA + kStageB) + 256 + 1024 + 2 * 2 * 32 * BM * 2;
 constexpr int kAccCols = 256;
 
 enum : int { EPI_F32 = 0, EPI_BIAS_RELU_DUAL = 1, EPI_RELUBWD_DUAL = 2, EPI_TANH_F32 = 3, EPI_LSTM = 4 };
@@ -81,13 +82,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
-__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* dst, const float* v) {
-    uint4 u;
-    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]); u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>(dst) = u;
+// 8 bf16 = 4 packed pairs -> one 16-byte store
+__device__ __forceinline__ void st_u4(__nv_bfloat16* dst, const uint32_t* pk) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
+// the 128 epilogue threads of one column half (named barrier 1 + half); all 256 epilogue threads (barrier 3)
+__device__ __forceinline__ void epi_barrier(int half) { asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory"); }
+__device__ __forceinline__ void epi_barrier_all() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
+// gate non-linearities from ex2.approx + rcp.approx (2 MUFU each, ~1e-6 accurate): close enough to the exact functions that the
+// bf16 roundings downstream agree with the emulation oracle (tanh.approx.f32 is 2^-11 accurate: measurably more ReLU-mask flips)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -97,11 +103,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kStageA + kStageB));
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages, bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    float* s_bias = reinterpret_cast<float*>(smem + kStages * (kStageA + kStageB) + 256);           // [256]
+    uint16_t* s_stage = reinterpret_cast<uint16_t*>(smem + kStages * (kStageA + kStageB) + 256 + 1024);   // [half][2][32][128] bf16: feature-major copy-out
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 8); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(s_tmem), 2 * kAccCols);
@@ -164,7 +172,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================== epilogue: thread <-> accumulator row (TMEM lane)
         const int quad = warp & 3;                                        // a warp may only touch TMEM lanes 32 * (warp % 4) .. + 31
         const int r = (quad << 5) | lane;
-        uint32_t buf = 0, acc_phase = 0;
+        const int half = (warp - 2) >> 2;                                 // warps 2..5 take the even 32-column chunks, 6..9 the odd ones
+        const int te = (((warp - 2) & 3) << 5) | lane;                    // 0..127: linear index inside the half's thread group
+        uint16_t* const s_stage_h = s_stage + half * (2 * 32 * BM);
+        uint32_t buf = 0, acc_phase = 0, sb = 0;
+        // column-wise constants once per CTA (the bias of the layer)
+        if (p.bias != nullptr)
+            for (int c = (int)threadIdx.x - 64; c < p.n_tile; c += 256) s_bias[c] = c < p.n ? __ldg(p.bias + c) : 0.0f;
+        epi_barrier_all();
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
             const int mt = w % m_tiles, sp = w / m_tiles;
             const long long m = (long long)mt * BM + r;
@@ -175,91 +190,137 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.epi == EPI_LSTM) {
                 const LstmEpi& L = p.lstm;
 #pragma unroll 1
-                for (int j0 = 0; j0 < 64; j0 += 16) {
+                for (int j0 = 32 * half; j0 < 32 * half + 32; j0 += 16) {
                     uint32_t vi[16], vf[16], vg[16], vo[16];
                     tmem_ld16(t_row + j0, vi); tmem_ld16(t_row + 64 + j0, vf); tmem_ld16(t_row + 128 + j0, vg); tmem_ld16(t_row + 192 + j0, vo);
+                    float cp[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 c4 = (L.c_prev && row_ok) ? *reinterpret_cast<const float4*>(L.c_prev + m * 64 + j0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        cp[4 * q] = c4.x; cp[4 * q + 1] = c4.y; cp[4 * q + 2] = c4.z; cp[4 * q + 3] = c4.w;
+                    }
                     tmem_ld_wait();
+                    uint32_t pi[8], pf[8], pg[8], po[8], ph[8];
+                    float cc[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2) {
+                        float gi[2], gf[2], gg[2], go[2], hh[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            gi[e] = sigmoid_fast(__uint_as_float(vi[j + e])); gf[e] = sigmoid_fast(__uint_as_float(vf[j + e]));
+                            gg[e] = tanh_fast(__uint_as_float(vg[j + e])); go[e] = sigmoid_fast(__uint_as_float(vo[j + e]));
+                            cc[j + e] = gf[e] * cp[j + e] + gi[e] * gg[e];
+                            hh[e] = go[e] * tanh_fast(cc[j + e]);
+                        }
+                        pi[j >> 1] = pack_bf16x2(gi[0], gi[1]); pf[j >> 1] = pack_bf16x2(gf[0], gf[1]);
+                        pg[j >> 1] = pack_bf16x2(gg[0], gg[1]); po[j >> 1] = pack_bf16x2(go[0], go[1]);
+                        ph[j >> 1] = pack_bf16x2(hh[0], hh[1]);
+                    }
                     if (row_ok) {
-                        float cp[16], gi[16], gf[16], gg[16], go[16], hh[16], cc[16];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 c4 = L.c_prev ? *reinterpret_cast<const float4*>(L.c_prev + m * 64 + j0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            cp[4 * q] = c4.x; cp[4 * q + 1] = c4.y; cp[4 * q + 2] = c4.z; cp[4 * q + 3] = c4.w;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            gi[j] = sigmoidf_(__uint_as_float(vi[j])); gf[j] = sigmoidf_(__uint_as_float(vf[j]));
-                            gg[j] = tanhf(__uint_as_float(vg[j])); go[j] = sigmoidf_(__uint_as_float(vo[j]));
-                            cc[j] = gf[j] * cp[j] + gi[j] * gg[j];
-                            hh[j] = go[j] * tanhf(cc[j]);
-                        }
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
                             *reinterpret_cast<float4*>(L.c_out + m * 64 + j0 + 4 * q) = make_float4(cc[4 * q], cc[4 * q + 1], cc[4 * q + 2], cc[4 * q + 3]);
                         __nv_bfloat16* g = L.gates_out + m * 256 + j0;
-                        store_bf16x8(g, gi); store_bf16x8(g + 8, gi + 8);
-                        store_bf16x8(g + 64, gf); store_bf16x8(g + 72, gf + 8);
-                        store_bf16x8(g + 128, gg); store_bf16x8(g + 136, gg + 8);
-                        store_bf16x8(g + 192, go); store_bf16x8(g + 200, go + 8);
-                        if (L.h_bm) { store_bf16x8(L.h_bm + m * L.ld_h_bm + j0, hh); store_bf16x8(L.h_bm + m * L.ld_h_bm + j0 + 8, hh + 8); }
-                        if (L.h_fm) {
+                        st_u4(g, pi); st_u4(g + 8, pi + 4); st_u4(g + 64, pf); st_u4(g + 72, pf + 4);
+                        st_u4(g + 128, pg); st_u4(g + 136, pg + 4); st_u4(g + 192, po); st_u4(g + 200, po + 4);
+                        if (L.h_bm) { st_u4(L.h_bm + m * L.ld_h_bm + j0, ph); st_u4(L.h_bm + m * L.ld_h_bm + j0 + 8, ph + 4); }
+                    }
+                    if (L.h_fm) {                                         // feature-major copy of h through the staging tile (16 units x 128 samples)
+                        uint16_t* st = s_stage_h + sb * (32 * BM);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) L.h_fm[(long long)(j0 + j) * L.ld_h_fm + m] = __float2bfloat16_rn(hh[j]);
+                        for (int j = 0; j < 16; ++j) st[j * BM + r] = (uint16_t)((j & 1) ? (ph[j >> 1] >> 16) : (ph[j >> 1] & 0xFFFFu));
+                        epi_barrier(half);
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            const int j = q * 8 + (te >> 4), seg = te & 15;
+                            const long long mm = (long long)mt * BM + seg * 8;
+                            if (mm < p.m)
+                                *reinterpret_cast<uint4*>(L.h_fm + (long long)(j0 + j) * L.ld_h_fm + mm) = *reinterpret_cast<const uint4*>(st + j * BM + seg * 8);
                         }
+                        sb ^= 1u;
+                    }
+                }
+            } else if (p.epi == EPI_BIAS_RELU_DUAL || p.epi == EPI_RELUBWD_DUAL) {
+#pragma unroll 1
+                for (int c0 = 32 * half; c0 < p.n_valid; c0 += 64) {
+                    uint32_t v[32];
+                    tmem_ld32(t_row + c0, v);
+                    uint32_t amask[16];
+                    if (p.epi == EPI_RELUBWD_DUAL) {                      // the activations whose sign is the ReLU mask: issued under the TMEM load
+                        const __nv_bfloat16* a = p.act + m * p.ld_act + c0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 u = (row_ok && c0 + 8 * q < p.n_valid) ? *reinterpret_cast<const uint4*>(a + 8 * q) : make_uint4(0u, 0u, 0u, 0u);
+                            amask[4 * q] = u.x; amask[4 * q + 1] = u.y; amask[4 * q + 2] = u.z; amask[4 * q + 3] = u.w;
+                        }
+                    }
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+                    if (p.epi == EPI_BIAS_RELU_DUAL) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
+                            pk[2 * q] = pack_bf16x2(fmaxf(__uint_as_float(v[4 * q]) + b4.x, 0.0f), fmaxf(__uint_as_float(v[4 * q + 1]) + b4.y, 0.0f));
+                            pk[2 * q + 1] = pack_bf16x2(fmaxf(__uint_as_float(v[4 * q + 2]) + b4.z, 0.0f), fmaxf(__uint_as_float(v[4 * q + 3]) + b4.w, 0.0f));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            // bf16 > 0  <=>  sign clear and not zero (activations are post-ReLU: never negative, never NaN)
+                            const uint32_t a = amask[i];
+                            const bool lo = (a & 0x7FFFu) != 0u && !(a & 0x8000u), hi = (a & 0x7FFF0000u) != 0u && !(a & 0x80000000u);
+                            pk[i] = pack_bf16x2(lo ? __uint_as_float(v[2 * i]) : 0.0f, hi ? __uint_as_float(v[2 * i + 1]) : 0.0f);
+                        }
+                    }
+                    const int nv = min(32, p.n_valid - c0);               // multiple of 8
+                    if (p.out_bm && row_ok) {
+                        __nv_bfloat16* o = p.out_bm + m * p.ld_bm + c0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (8 * q < nv) st_u4(o + 8 * q, pk + 4 * q);
+                    }
+                    if (p.out_fm) {                                       // feature-major copy through the staging tile (32 features x 128 samples)
+                        uint16_t* st = s_stage_h + sb * (32 * BM);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) st[j * BM + r] = (uint16_t)((j & 1) ? (pk[j >> 1] >> 16) : (pk[j >> 1] & 0xFFFFu));
+                        epi_barrier(half);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int j = q * 8 + (te >> 4), seg = te & 15;
+                            const long long mm = (long long)mt * BM + seg * 8;
+                            if (j < nv && mm < p.m)
+                                *reinterpret_cast<uint4*>(p.out_fm + (long long)(c0 + j) * p.ld_fm + mm) = *reinterpret_cast<const uint4*>(st + j * BM + seg * 8);
+                        }
+                        sb ^= 1u;
                     }
                 }
             } else {
-                for (int c0 = 0; c0 < p.n_valid; c0 += 32) {
+                for (int c0 = 32 * half; c0 < p.n_valid; c0 += 64) {
                     uint32_t v[32];
                     tmem_ld32(t_row + c0, v);
                     tmem_ld_wait();
                     if (!row_ok) continue;
-                    float y[32];
                     const int nv = min(32, p.n_valid - c0);
                     if (p.epi == EPI_F32) {
                         float* o = p.out_f32 + (long long)sp * p.split_stride + m * p.ldc + c0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]) + ((p.bias && j < nv) ? __ldg(p.bias + c0 + j) : 0.0f);
                         if (nv == 32 && ((reinterpret_cast<uintptr_t>(o) & 15u) == 0)) {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(o + 4 * q) = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-                        } else {
-                            for (int j = 0; j < nv; ++j) o[j] = y[j];
-                        }
-                    } else if (p.epi == EPI_TANH_F32) {
-                        float* o = p.out_f32 + m * p.ldc + c0;
-                        for (int j = 0; j < nv; ++j) o[j] = tanhf(__uint_as_float(v[j]) + __ldg(p.bias + c0 + j));
-                    } else {
-                        if (p.epi == EPI_BIAS_RELU_DUAL) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) y[j] = (j < nv) ? fmaxf(__uint_as_float(v[j]) + __ldg(p.bias + c0 + j), 0.0f) : 0.0f;
-                        } else {                                      // EPI_RELUBWD_DUAL
-                            const __nv_bfloat16* a = p.act + m * p.ld_act + c0;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 u = make_uint4(0u, 0u, 0u, 0u);
-                                if (8 * q < nv) u = *reinterpret_cast<const uint4*>(a + 8 * q);
-                                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    // bf16 > 0  <=>  sign clear and not zero (activations are post-ReLU: never negative, never NaN)
-                                    const bool lo = (w4[e] & 0x7FFFu) != 0u && !(w4[e] & 0x8000u), hi = (w4[e] & 0x7FFF0000u) != 0u && !(w4[e] & 0x80000000u);
-                                    y[8 * q + 2 * e] = lo ? __uint_as_float(v[8 * q + 2 * e]) : 0.0f;
-                                    y[8 * q + 2 * e + 1] = hi ? __uint_as_float(v[8 * q + 2 * e + 1]) : 0.0f;
-                                }
+                            for (int q = 0; q < 8; ++q) {
+                                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (p.bias) b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
+                                *reinterpret_cast<float4*>(o + 4 * q) = make_float4(__uint_as_float(v[4 * q]) + b4.x, __uint_as_float(v[4 * q + 1]) + b4.y,
+                                                                                    __uint_as_float(v[4 * q + 2]) + b4.z, __uint_as_float(v[4 * q + 3]) + b4.w);
                             }
-                        }
-                        if (p.out_bm) {
-                            __nv_bfloat16* o = p.out_bm + m * p.ld_bm + c0;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (8 * q < nv) store_bf16x8(o + 8 * q, y + 8 * q);
-                        }
-                        if (p.out_fm) {
+                        } else {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (j < nv) p.out_fm[(long long)(c0 + j) * p.ld_fm + m] = __float2bfloat16_rn(y[j]);
+                                if (j < nv) o[j] = __uint_as_float(v[j]) + (p.bias ? s_bias[c0 + j] : 0.0f);
                         }
+                    } else {                                              // EPI_TANH_F32
+                        float* o = p.out_f32 + m * p.ldc + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < nv) o[j] = tanhf(__uint_as_float(v[j]) + s_bias[c0 + j]);
                     }
                 }
             }

@@ -539,6 +539,10 @@ struct TacoPPO {
     int max_log = 4096;
     float* spec_v[kMaxHiddenL + 1] = {nullptr}; double* spec_sigma = nullptr;
     bool spec_cold = true;
+    // the spectral projection + re-pack of the ACTOR runs on a side stream under the next minibatch's gather and critic forward
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_adam = nullptr, ev_actor = nullptr;
+    bool actor_pending = false;
     std::vector<void*> allocs;
 };
 
@@ -706,6 +710,9 @@ int taco_ppo_create(int device, const TacoPPOCfg* cfg, TacoPPO** out) {
     if (!ok) return bail(TACO_E_CUDA, "taco_ppo_create: cuTensorMapEncodeTiled failed");
     if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem) != cudaSuccess)
         return bail(TACO_E_CUDA, "taco_ppo_create: cudaFuncSetAttribute failed");
+    if (cudaStreamCreateWithFlags(&t->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&t->ev_adam, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->ev_actor, cudaEventDisableTiming) != cudaSuccess)
+        return bail(TACO_E_CUDA, "taco_ppo_create: stream / event creation failed");
     *out = t;
     return TACO_OK;
 }
@@ -714,6 +721,9 @@ int taco_ppo_destroy(TacoPPO* t) {
     if (!t) return TACO_OK;
     DevGuard guard(t->device);
     for (void* p : t->allocs) cudaFree(p);
+    if (t->side) cudaStreamDestroy(t->side);
+    if (t->ev_adam) cudaEventDestroy(t->ev_adam);
+    if (t->ev_actor) cudaEventDestroy(t->ev_actor);
     delete t;
     return TACO_OK;
 }
@@ -751,10 +761,21 @@ int taco_ppo_buffers(TacoPPO* t, float** params, float** grad, float** adam_m, f
     return TACO_OK;
 }
 
-static int repack(TacoPPO* t, cudaStream_t s, bool honour_stop) {
+// the caller's stream waits for the actor's projection / re-pack still running on the side stream
+static int join_actor(TacoPPO* t, cudaStream_t s) {
+    if (t->actor_pending) {
+        PPO_CUDA(cudaStreamWaitEvent(s, t->ev_actor, 0));
+        t->actor_pending = false;
+    }
+    return TACO_OK;
+}
+
+// which: 0 = everything, 1 = the actor's matrices only, 2 = critic MLP + LSTM only
+static int repack(TacoPPO* t, cudaStream_t s, bool honour_stop, int which = 0) {
     PackParams pp;
     memset(&pp, 0, sizeof(pp));
     for (int k = 0; k < 2; ++k) {
+        if ((which == 1 && k == 1) || (which == 2 && k == 0)) continue;
         MlpNet& n = k == 0 ? t->actor : t->critic;
         for (int l = 0; l < n.L; ++l) {
             PackSeg& S = pp.seg[pp.n_seg++];
@@ -764,8 +785,10 @@ static int repack(TacoPPO* t, cudaStream_t s, bool honour_stop) {
     }
     pp.stop = honour_stop ? t->stop : nullptr;
     pack_kernel<<<dim3(32, pp.n_seg), 256, 0, s>>>(pp); TACO_LAUNCHED();
-    pack_lstm_kernel<<<64, 256, 0, s>>>(t->prm + t->off_wih, t->prm + t->off_whh, t->prm + t->off_bih, t->prm + t->off_bhh, t->sd, t->ld_u, t->wcat,
-                                        t->whh_t, honour_stop ? t->stop : nullptr); TACO_LAUNCHED();
+    if (which != 1) {
+        pack_lstm_kernel<<<64, 256, 0, s>>>(t->prm + t->off_wih, t->prm + t->off_whh, t->prm + t->off_bih, t->prm + t->off_bhh, t->sd, t->ld_u, t->wcat,
+                                            t->whh_t, honour_stop ? t->stop : nullptr); TACO_LAUNCHED();
+    }
     return cudaGetLastError() == cudaSuccess ? TACO_OK : ppo_fail(TACO_E_CUDA, "pack kernels failed");
 }
 
@@ -773,6 +796,8 @@ static int repack(TacoPPO* t, cudaStream_t s, bool honour_stop) {
 int taco_ppo_params_changed(TacoPPO* t, void* stream) {
     if (!t) return ppo_fail(TACO_E_INVALID, "taco_ppo_params_changed: null argument");
     DevGuard guard(t->device);
+    const int rcj = join_actor(t, (cudaStream_t)stream);
+    if (rcj != TACO_OK) return rcj;
     return repack(t, (cudaStream_t)stream, false);
 }
 
@@ -860,9 +885,9 @@ int taco_ppo_forward_loss(TacoPPO* t, const TacoPPOHyper* hyper, const float* ob
     g.u_bm = t->u_bm; g.u_fm = t->u_fm; g.ld_u = t->ld_u;
     g.g_act = t->g_act; g.g_logp = t->g_logp; g.g_adv = t->g_adv; g.g_ret = t->g_ret; g.stop = t->stop;
     gather_kernel<<<(B + 31) / 32, 256, 0, s>>>(g); TACO_LAUNCHED();
-    int rc = mlp_forward(t, t->actor, true, s);
-    if (rc != TACO_OK) return rc;
-    // critic: seq LSTM steps, each one GEMM [h_{t-1} | x_t | 1 1] Wcat^T with the gate math in the epilogue
+    int rc = TACO_OK;
+    // critic first: seq LSTM steps, each one GEMM [h_{t-1} | x_t | 1 1] Wcat^T with the gate math in the epilogue, then its MLP.  The
+    // previous optimiser step's projection + re-pack of the ACTOR may still be running on the side stream under these launches.
     for (int k = 0; k < t->seq; ++k) {
         GemmParams p;
         memset(&p, 0, sizeof(p));
@@ -881,6 +906,10 @@ int taco_ppo_forward_loss(TacoPPO* t, const TacoPPOHyper* hyper, const float* ob
         if (rc != TACO_OK) return rc;
     }
     rc = mlp_forward(t, t->critic, false, s);
+    if (rc != TACO_OK) return rc;
+    rc = join_actor(t, s);
+    if (rc != TACO_OK) return rc;
+    rc = mlp_forward(t, t->actor, true, s);
     if (rc != TACO_OK) return rc;
     LossParams L;
     memset(&L, 0, sizeof(L));
@@ -1014,16 +1043,23 @@ int taco_ppo_apply(TacoPPO* t, const TacoPPOHyper* hyper, void* stream) {
     if (h.use_lipschitz) {
         SpecParams sp;
         memset(&sp, 0, sizeof(sp));
-        int mx = 0;
         for (int l = 0; l < t->actor.L; ++l) {
             SpecSeg& S = sp.seg[sp.n_seg++];
             S.w = t->prm + t->actor.w_off[l]; S.rows = t->actor.s[l + 1]; S.cols = t->actor.s[l]; S.v = t->spec_v[l]; S.sigma = t->spec_sigma + l;
-            mx = S.rows + S.cols > mx ? S.rows + S.cols : mx;
         }
         sp.lipschitz = h.lipschitz; sp.max_iter = t->spec_cold ? 4000 : 200; sp.stop = t->stop;
         t->spec_cold = false;
-        (void)mx;
-        spectral_kernel<<<sp.n_seg, 512, 0, s>>>(sp); TACO_LAUNCHED();
+        // actor: projection, then the bf16 copies of the projected matrices, on the side stream (4 CTAs of latency-bound power
+        // iteration); the caller's stream goes on with the critic's copies and the next minibatch until it needs the actor
+        PPO_CUDA(cudaEventRecord(t->ev_adam, s));
+        PPO_CUDA(cudaStreamWaitEvent(t->side, t->ev_adam, 0));
+        spectral_kernel<<<sp.n_seg, 512, 0, t->side>>>(sp); TACO_LAUNCHED();
+        PPO_CUDA(cudaGetLastError());
+        int rc = repack(t, t->side, true, 1);
+        if (rc != TACO_OK) return rc;
+        PPO_CUDA(cudaEventRecord(t->ev_actor, t->side));
+        t->actor_pending = true;
+        return repack(t, s, true, 2);
     }
     PPO_CUDA(cudaGetLastError());
     return repack(t, s, true);
@@ -1036,6 +1072,10 @@ int taco_ppo_end_update(TacoPPO* t, float* log_host, int32_t max_rows, int32_t* 
     if (!t) return ppo_fail(TACO_E_INVALID, "taco_ppo_end_update: null argument");
     DevGuard guard(t->device);
     cudaStream_t s = (cudaStream_t)stream;
+    {
+        const int rcj = join_actor(t, s);
+        if (rcj != TACO_OK) return rcj;
+    }
     int h[3] = {0, 0, 0};
     PPO_CUDA(cudaMemcpyAsync(&h[0], t->n_logged, sizeof(int), cudaMemcpyDeviceToHost, s));
     PPO_CUDA(cudaMemcpyAsync(&h[1], t->step, sizeof(int), cudaMemcpyDeviceToHost, s));

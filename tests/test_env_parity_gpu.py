@@ -299,3 +299,49 @@ def test_delay_beyond_the_reference_buffer_is_flagged():
     assert (st[:, 37] == 1).all() and bool(ref.overflow.all())
     assert gpu.stats().cpu().numpy()[6] == 256
     gpu.close()
+
+
+def _hover_actions(ref):
+    """A small cascaded controller (position -> tilt -> body rates, altitude -> throttle) evaluated on the ORACLE's state: keeps part
+    of the envs alive for whole episodes, so that the lock-step run below crosses progress == 500 and natural time-outs.  The actions
+    are just inputs: both implementations receive the same tensor."""
+    import math
+    from oracle.leaf_math import euler_xyz, qconj, qrot
+    roll, pitch, _ = euler_xyz(ref.quat)
+    qc = qconj(ref.quat)
+    e = qrot(qc, ref.tpos - ref.pos)                       # position error in the body frame
+    v = qrot(qc, ref.linvel)
+    ax = torch.clamp(1.2 * e[:, 0] - 1.8 * v[:, 0], -3.0, 3.0)
+    ay = torch.clamp(1.2 * e[:, 1] - 1.8 * v[:, 1], -3.0, 3.0)
+    rate_x = torch.clamp(6.0 * (-ay / 9.81 - roll), -8.0, 8.0)
+    rate_y = torch.clamp(6.0 * (ax / 9.81 - pitch), -8.0, 8.0)
+    thr = torch.clamp(-0.45 + 0.35 * (ref.tpos[:, 2] - ref.pos[:, 2]) - 0.25 * ref.linvel[:, 2], -1.0, 1.0)
+    return torch.stack((thr, rate_x / 20.0, rate_y / 20.0, torch.zeros_like(thr)), dim=1).to(torch.float32).contiguous()
+
+
+def test_1100_step_lockstep_crosses_progress_500_and_natural_timeouts():
+    """maxEpisodeLength = 1000 (train_fpv_asymmetry_ppo.py:342), 1100 steps in lock-step with the oracle under a stabilising
+    controller: envs live through the progress == 500 command re-draw (fpv_asymmetry.py:152,587-603) and reach the time-out at
+    progress 999 (vec_task_asymmetry.py:323) without any state surgery.  Integer fields / masks / delayed actions exact at every step;
+    floats stay within 2e-3 over whole 1000-step episodes (the controller is evaluated on the oracle's state, so the kernel runs
+    these actions open-loop)."""
+    import parity_util as pu
+    from taco_b200 import make_cfg
+    n = 96
+    gpu, ref = pu.make_pair(make_cfg("mix", n, random_copter_quat=False, random_copter_vel=False))
+    worst, n_to, crossed = 0.0, 0, 0
+    for t in range(1100):
+        a = _hover_actions(ref)
+        o_g, r_g, x_g, e_g = gpu.step(a.cuda())
+        crossed += int((ref.progress_buf == 500).sum())                    # evaluated by the step just taken (pre-physics)
+        o_r, r_r, x_r, e_r = ref.step(a)
+        fin = torch.isfinite(o_r["states"]).all(dim=2).all(dim=1).numpy() & ~ref.overflow.numpy()
+        errs, mism = pu.compare(gpu, ref, o_g, r_g, x_g, e_g["time_outs"], o_r, r_r, x_r, e_r["time_outs"], mask=fin)
+        assert all(v == 0 for v in mism.values()), (t, mism)
+        assert int((gpu.debug_delay()[fin] != ref.last_delayed_actions.numpy()[fin]).sum()) == 0, t
+        worst = max(worst, max(errs.values()))
+        n_to += int(e_r["time_outs"].sum())
+    assert crossed > 0 and n_to > 0, (crossed, n_to)
+    assert worst <= 2e-3, worst
+    print("1100-step lock-step: worst relative error", worst, "time-outs", n_to, "envs at progress 500:", crossed)
+    gpu.close()
