@@ -52,6 +52,22 @@ def rel_err(a, b, scale):
     return np.where(np.isnan(err), np.inf, err)
 
 
+def elem_rel_err(a, b, floor):
+    """Element-wise relative error max_i |a_i - b_i| / max(|b_i|, floor): the literal "relative error" of the north star, with a floor
+    below which an element is measured absolutely (a component that is exactly zero in one implementation has no relative error)."""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    ok = np.isfinite(a) & np.isfinite(b)
+    return float((np.abs(a - b)[ok] / np.maximum(np.abs(b)[ok], floor)).max()) if ok.any() else 0.0
+
+
+def elementwise_errors(obs_gpu, rew_gpu, obs_ref, rew_ref, mask=None):
+    """{obs, states, rew}: element-wise relative errors (floors 1e-2 of the field's unit scale)."""
+    m = slice(None) if mask is None else np.asarray(mask)
+    return dict(obs=elem_rel_err(obs_gpu["obs"].cpu().numpy()[m], obs_ref["obs"].numpy()[m], 1e-2),
+                states=elem_rel_err(obs_gpu["states"].cpu().numpy()[m], obs_ref["states"].numpy()[m], 1e-2),
+                rew=elem_rel_err(rew_gpu.cpu().numpy()[m], rew_ref.numpy()[m], 1e-4))
+
+
 def compare(gpu_env, ref_env, obs_gpu, rew_gpu, reset_gpu, tout_gpu, obs_ref, rew_ref, reset_ref, tout_ref, mask=None):
     """Returns ({field: max relative error}, {int field: mismatch count}).  ``mask`` restricts the
     comparison to a subset of envs (e.g. finite, in-domain)."""
@@ -108,6 +124,8 @@ def run_lockstep(gpu, ref, steps, check_delay=True, on_step=None):
             # oracle: the dense buffer was shifted by 10 after the reads, so re-derive from the log
             ref_dd = ref.last_delayed_actions.numpy()
             dmis = int((dd[finite] != ref_dd[finite]).sum())
+        if t == 0:
+            ref.first_step_elementwise = elementwise_errors(o_g, r_g, o_r, r_r, mask=finite)
         out.append((errs, mism, dmis, int(finite.sum())))
         if on_step:
             on_step(t, errs, mism, dmis)

@@ -25,10 +25,11 @@ for name, kw, strict in [
         for k, v in mism.items():
             allmis[k] = allmis.get(k, 0) + v
         allmis["delayed_action"] = allmis.get("delayed_action", 0) + dmis
-    report[name] = dict(step1=worst_1[0], step2=res[1][0], stepN=res[-1][0], mismatches=allmis, finite_last=res[-1][3],
+    report[name] = dict(step1_elementwise=ref.first_step_elementwise, step1=worst_1[0], step2=res[1][0], stepN=res[-1][0], mismatches=allmis, finite_last=res[-1][3],
                         stats_ref=ref.stats, stats_gpu=gpu.stats().cpu().tolist())
     print("==", name)
     print("  step 1 max rel err:", {k: "%.2e" % v for k, v in worst_1[0].items()})
+    print("  step 1 element-wise rel err (floor 1e-2 / 1e-4):", {k: "%.2e" % v for k, v in ref.first_step_elementwise.items()})
     print("  step 2 max rel err:", {k: "%.2e" % v for k, v in res[1][0].items()})
     print("  step %d max rel err:" % steps, {k: "%.2e" % v for k, v in res[-1][0].items()})
     print("  integer/mask mismatches over all steps:", allmis, " finite envs at end:", res[-1][3])
