@@ -273,6 +273,12 @@ def actor_rollout_point(torch, taco_b200, dev, n, hidden, strict_fp, peaks, iter
     tc = actor.tensor_cores_available
     ms_fp32 = _timed(torch, lambda: actor.forward(obs, tensor_cores=False, out=mean), max(iters // 5, 5))
     ms_tc = _timed(torch, lambda: actor.forward(obs, tensor_cores=True, out=mean), iters) if tc else None
+    precision = None
+    if tc:            # the bf16-operand kernel against the FP32 kernel (the reference computes in FP32) on this batch of real observations
+        d = (actor.forward(obs, tensor_cores=True) - actor.forward(obs, tensor_cores=False)).abs()
+        precision = {"max_abs_err": float(d.max()), "mean_abs_err": float(d.mean()), "action_range": [-1.0, 1.0],
+                     "policy_std_at_init": 1.0, "note": "action mean of the tcgen05 (bf16 operands, fp32 accumulation) kernel minus the FP32 CUDA-core kernel "
+                                                        "on the bench's observation batch; the sampled action adds N(0, std^2) noise with std = exp(2 log_std)"}
     k = [0]
 
     def env_only():
@@ -330,7 +336,7 @@ def actor_rollout_point(torch, taco_b200, dev, n, hidden, strict_fp, peaks, iter
                        "random-init policy, spectral projection c=4 once per update, act -> clip -> step every step",
            "value": n / (ms_loop * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_loop, "env_step_ms": ms_env,
            "actor_fp32_ms": ms_fp32, "actor_tc_ms": ms_tc, "actor_flops_per_env": flops, "gpu_launches_per_step": 2,
-           "with_critic": crit}
+           "actor_tc_precision": precision, "with_critic": crit}
     if ms_tc:
         ach = flops * n / (ms_tc * 1e-3) / 1e12
         peak = float(peaks.get("bf16_tflops", 1590.0))

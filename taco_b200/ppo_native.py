@@ -145,7 +145,8 @@ class NativePPO:
         ret, old_logp, adv = buffer.ret_buf.reshape(-1).contiguous(), buffer.logp_buf.reshape(-1).contiguous(), buffer.adv_buf.reshape(-1).contiguous()
         if self._h is None:
             self._create(states.shape[1])
-        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        # group=False: no collectives even when a process group exists (a rank-local update, e.g. a single-process comparison run)
+        world = dist.get_world_size(group) if (group is not False and dist.is_available() and dist.is_initialized()) else 1
         hy = _capi.TacoPPOHyper(lr=lr, clip=cfg.clip, target_kl=cfg.target_kl, max_grad=cfg.max_grad, pi_coef=cfg.pi_coef, vf_coef=cfg.vf_coef,
                                 ent_coef=cfg.ent_coef, lipschitz=lip, use_lipschitz=1 if cfg.use_lipschitz else 0, world=world)
         if batch_idx is None:

@@ -38,7 +38,7 @@ dist.all_gather(gathered, mine)
 res = {"world": world, "ranks_bit_identical": all(torch.equal(g, gathered[0]) for g in gathered), "optim_steps": out["optim_steps"], "kl": out["approx_kl"]}
 if rank == 0:
     single = NativePPO(agent, perm.shape[1], device=dev)
-    o1 = single.update(buf, cfg, 3, batch_idx=[perm[i] for i in range(mb)])
+    o1 = single.update(buf, cfg, 3, batch_idx=[perm[i] for i in range(mb)], group=False)
     init = torch.cat([p.detach().flatten() for n, p in agent.named_parameters()])      # order differs from the flat vector: compare deltas by name
     vs, vm = single._views(single.params), nat._views(mine)
     sd = dict(agent.named_parameters())

@@ -67,9 +67,35 @@ def gae_part():
     print("gae ok")
 
 
+def ppo_part():
+    # the native PPO update: TMA-fed tcgen05 GEMM (all epilogues, split-K), gather, loss, LSTM backward, reductions, Adam, projection
+    import types
+    from taco_b200.ppo import PPOConfig, TorchActorCritic
+    from taco_b200.ppo_native import NativePPO, gemm_selftest
+    for (m, n, k, sp) in ((300, 48, 96, 1), (256, 32, 2048, 7), (4, 256, 1024, 5)):
+        a = (torch.randn(m, k, device="cuda") * 0.5).bfloat16()
+        b = (torch.randn(n, k, device="cuda") * 0.5).bfloat16()
+        gemm_selftest(a, b, sp)
+    agent = TorchActorCritic(26, 4, [64, 48], 26, 64, [32]).cuda()
+    H, N = 4, 128
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    buf = types.SimpleNamespace(obs_buf=rnd(H, N, 1, 26), states_buf=rnd(H, N, 5, 26), act_buf=rnd(H, N, 4).clamp(-1, 1), value_buf=rnd(H, N, 1),
+                                ret_buf=rnd(H, N, 1), adv_buf=rnd(H, N, 1), logp_buf=rnd(H, N, 1) * 0.1 - 4.0)
+    nat = NativePPO(agent, 256)
+    perm = torch.randperm(H * N, device="cuda").view(2, -1)
+    nat.update(buf, PPOConfig(train_iters=2, use_lipschitz=True, lipschitz_para=1.0, target_kl=1e9), 0, batch_idx=[perm[0], perm[1]])
+    nat.update(buf, PPOConfig(train_iters=2, target_kl=1e-9), 1, batch_idx=[perm[0], perm[1]])        # early stop: the no-op launches
+    torch.cuda.synchronize()
+    nat.close()
+    print("ppo ok")
+
+
 if part in ("all", "step"):
     step_part()
 if part in ("all", "nets"):
     nets_part()
 if part in ("all", "gae"):
     gae_part()
+if part in ("all", "ppo"):
+    ppo_part()
