@@ -174,6 +174,16 @@ def _allreduce_grads(params, group):
         off += n
 
 
+def value_log(buffer, idx):
+    """``mean_value`` and ``explained_variance`` as PPO.update logs them (ppo_asymmetry.py:252-254,406-423): computed on the old values /
+    returns of the LAST evaluated minibatch (numpy, population variance)."""
+    idx = idx if isinstance(idx, torch.Tensor) else torch.as_tensor(idx)
+    v = buffer.value_buf.reshape(-1)[idx.to(buffer.value_buf.device)].detach().cpu().numpy().flatten()
+    r = buffer.ret_buf.reshape(-1)[idx.to(buffer.ret_buf.device)].detach().cpu().numpy().flatten()
+    var_y = r.var()
+    return float(v.mean()), (float("nan") if var_y == 0 else float(1 - (r - v).var() / var_y))
+
+
 def ppo_update(agent, optimizer, buffer, cfg, epoch, env=None, batch_idx=None, group=None, project=None):
     """``PPO.update(epoch)`` (ppo_asymmetry.py:137-258) on the tensors of ``buffer`` (a ``RolloutBuffer`` or anything with the
     reference buffer's attributes).  ``batch_idx``: minibatch index lists / tensors (default: ``buffer.batch_idx_generator()``).
@@ -196,10 +206,11 @@ def ppo_update(agent, optimizer, buffer, cfg, epoch, env=None, batch_idx=None, g
     old_value, ret = buffer.value_buf.view(-1, 1), buffer.ret_buf.view(-1, 1)
     old_logp, adv = buffer.logp_buf.view(-1, 1), buffer.adv_buf.view(-1, 1)
     pg_l, v_l, e_l, s_l, kls = [], [], [], [], []
-    keep_going, steps = True, 0
+    keep_going, steps, last_idx = True, 0, None
     for it in range(cfg.train_iters):
         for indices in batch_idx:
             idx = indices if isinstance(indices, torch.Tensor) else torch.as_tensor(indices, device=obs.device)
+            last_idx = idx
             logp, entropy, value, _, _ = agent.evaluate(obs[idx], states[idx], act[idx])
             adv_b, old_logp_b, ret_b, old_value_b = adv[idx].squeeze(1), old_logp[idx].squeeze(1), ret[idx], old_value[idx]
             ratio = torch.exp(logp - old_logp_b)
@@ -236,9 +247,10 @@ def ppo_update(agent, optimizer, buffer, cfg, epoch, env=None, batch_idx=None, g
     agent.eval()
     torch.cuda.nvtx.range_pop() if torch.cuda.is_available() else None
     mean = lambda xs: float(sum(xs) / max(len(xs), 1))
+    mean_value, explained_var = value_log(buffer, last_idx) if last_idx is not None else (0.0, float("nan"))
     return {"policy_gradient_loss": mean(pg_l), "value_loss": mean(v_l), "entropy_loss": mean(e_l), "sum_loss": mean(s_l),
             "approx_kl": mean(kls), "learning_rate": lr, "lipschitz_para": lip, "difficulty": diff, "optim_steps": steps,
-            "early_stop": not keep_going}
+            "early_stop": not keep_going, "mean_value": mean_value, "explained_variance": explained_var}
 
 
 def sync_rollout_nets_native(native, actor=None, critic=None):

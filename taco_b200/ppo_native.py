@@ -17,7 +17,7 @@ import torch
 import torch.distributed as dist
 
 from . import _capi
-from .ppo import schedules
+from .ppo import schedules, value_log
 
 
 def _linears(mlp):
@@ -181,7 +181,9 @@ class NativePPO:
         self._steps_total = int(steps.value)
         log = log[:n_rows.value]
         mean = lambda c: float(log[:, c].mean()) if len(log) else 0.0
-        return {"policy_gradient_loss": mean(0), "value_loss": mean(1), "entropy_loss": mean(2), "sum_loss": mean(3), "approx_kl": mean(4),
+        mean_value, explained_var = value_log(buffer, idx_dev[(len(log) - 1) % len(idx_dev)]) if len(log) else (0.0, float("nan"))
+        return {"mean_value": mean_value, "explained_variance": explained_var,
+                "policy_gradient_loss": mean(0), "value_loss": mean(1), "entropy_loss": mean(2), "sum_loss": mean(3), "approx_kl": mean(4),
                 "grad_norm": mean(5), "learning_rate": lr, "lipschitz_para": lip, "difficulty": diff,
                 "optim_steps": self._steps_total - step_before, "early_stop": bool(stop.value), "log": log}
 

@@ -158,7 +158,7 @@ def test_update_against_the_reference_update(tag):
     nat.store_to(agent)
     assert out["optim_steps"] == int(gg["optim_step"]) and not out["early_stop"]
     assert abs(env.difficulty - float(gg["difficulty"])) < 1e-6
-    for name in ("policy_gradient_loss", "value_loss", "entropy_loss", "sum_loss", "approx_kl", "learning_rate", "lipschitz_para"):
+    for name in ("policy_gradient_loss", "value_loss", "entropy_loss", "sum_loss", "approx_kl", "learning_rate", "lipschitz_para", "mean_value", "explained_variance"):
         assert out[name] == pytest.approx(log[name], rel=2e-3, abs=2e-5), name
     sd = {k: v.cpu() for k, v in agent.state_dict().items()}
     cos = lambda keys: float(torch.nn.functional.cosine_similarity(torch.cat([(sd[k] - init[k]).flatten() for k in keys]),

@@ -44,7 +44,7 @@ def _run(golden_dir, tag, device, project):
     out = ppo_update(agent, opt, b, cfg, int(g["epoch"]), env=env, batch_idx=idx, project=project)
     assert out["optim_steps"] == int(g["optim_step"]) and not out["early_stop"]
     assert abs(env.difficulty - float(g["difficulty"])) < 1e-6
-    for name in ("policy_gradient_loss", "value_loss", "entropy_loss", "sum_loss", "approx_kl", "learning_rate", "lipschitz_para", "difficulty"):
+    for name in ("policy_gradient_loss", "value_loss", "entropy_loss", "sum_loss", "approx_kl", "learning_rate", "lipschitz_para", "difficulty", "mean_value", "explained_variance"):
         assert out[name] == pytest.approx(log[name], rel=2e-4, abs=2e-6), name
     worst = 0.0
     for k, v in agent.state_dict().items():
