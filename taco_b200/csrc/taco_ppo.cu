@@ -562,8 +562,7 @@ static int launch_gemm(TacoPPO* t, const CUtensorMap& a, const CUtensorMap& b, G
     p.kb_per_split = (kb_total + p.splits - 1) / p.splits;
     p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;       // no empty split
     p.stop = t->stop;
-    static const char* const dbg = getenv("TACO_PPO_DEBUG_SKIP");     // timing experiments only (wrong results): drop one of the output copies
-    if (dbg) {
+    if (const char* dbg = getenv("TACO_PPO_DEBUG_SKIP")) {            // timing experiments only (wrong results): drop one of the output copies
         if (strstr(dbg, "fm")) p.out_fm = nullptr;
         if (strstr(dbg, "bm")) p.out_bm = nullptr;
         if (strstr(dbg, "hfm")) p.lstm.h_fm = nullptr;
@@ -848,7 +847,7 @@ static int mlp_backward(TacoPPO* t, MlpNet& n, float* dx_out, cudaStream_t s) {
             GemmParams p;
             memset(&p, 0, sizeof(p));
             p.m = out; p.n = in; p.k = t->B; p.n_tile = pad16(in); p.splits = n.splits[l];
-            p.epi = EPI_F32; p.n_valid = pad16(in);
+            p.epi = EPI_F32; p.n_valid = pad16(in) < 32 ? pad16(in) : pad16(in);
             p.out_f32 = n.partial[l]; p.ldc = n.ld_p[l]; p.split_stride = (long long)out * n.ld_p[l];
             const int rc = launch_gemm(t, n.m_dz_fm[lz], n.m_x_fm[l], p, s);
             if (rc != TACO_OK) return rc;

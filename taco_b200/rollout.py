@@ -163,34 +163,17 @@ def collect_rollout(env, actor, buffer, value_fn, seed=0, tensor_cores=True, gro
     actor_tc = bool(tensor_cores and actor.tensor_cores_available)        # shapes the tcgen05 kernel rejects use the FP32 kernel
     if tensor_cores and not (actor_tc and (critic_tc or not native_critic)):
         _warn_fp32_fallback(actor_tc, critic_tc or not native_critic)
-    # Below ~one wave of tiles the actor / critic / step kernels are latency-bound launches that leave most SMs idle: the critic
-    # chain (the value of slot s needs only the state history step s-1 wrote; nothing before GAE needs the value) then runs on a
-    # side stream next to the actor -> step chain, as in GraphedRollout.  At large env counts every kernel fills the GPU: one stream.
-    side = None
-    if native_critic and buffer.num_envs <= 128 * 148 and not torch.cuda.is_current_stream_capturing():
-        side = getattr(buffer, "_critic_stream", None)
-        if side is None:
-            side = buffer._critic_stream = torch.cuda.Stream(device=buffer.device)
-    main = torch.cuda.current_stream(buffer.device)
     for s in range(H):
         obs, states = buffer.obs_ring[s], buffer.states_ring[s]
         out = buffer.rows(s)
-        if side is not None:
-            side.wait_stream(main)                                 # slot s is complete (attach / rewind, or step s-1)
-            with torch.cuda.stream(side):
-                value = value_fn.forward(states, tensor_cores=critic_tc, out=buffer.value_buf[s])
         actor.act(obs, env.step_count, seed=seed, env_offset=env.env_offset, tensor_cores=actor_tc, out=out)
-        if side is None:
-            value = value_fn.forward(states, tensor_cores=critic_tc, out=buffer.value_buf[s]) if native_critic else value_fn(obs, states)
+        if native_critic:
+            value = value_fn.forward(states, tensor_cores=critic_tc, out=buffer.value_buf[s])
+        else:
+            value = value_fn(obs, states)
         env.step(out[1])
         buffer.store(None, None, out[0], None, out[2], None, value, out[3], sigma, time_outs=True)
-    if side is not None:
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            last_value = value_fn.forward(buffer.states_ring[H], tensor_cores=critic_tc)
-        main.wait_stream(side)                                     # join: every value is written before GAE
-        last_value.record_stream(main)
-    elif native_critic:
+    if native_critic:
         last_value = value_fn.forward(buffer.states_ring[H], tensor_cores=critic_tc)
     else:
         last_value = value_fn(buffer.obs_ring[H], buffer.states_ring[H])
