@@ -304,6 +304,10 @@ int taco_ppo_debug_outputs(TacoPPO* ppo, float** mean_dev, float** value_dev);
 /* self-test of the GEMM kernel: D (m, n) fp32 = A (m, k) B (n, k)^T for bf16 row-major device matrices, n <= 256, k % 8 == 0 */
 int taco_gemm_selftest(int device, const void* a_bf16, const void* b_bf16, float* d_f32, int32_t m, int32_t n, int32_t k, int32_t splits,
                        void* stream);
+/* the same product from transposed operands At (k, m), Bt (k, n) (the kernel's MN-major operand mode, used by the weight-gradient
+ * GEMMs that read batch-major activations as they are); m % 8 == 0, n % 8 == 0 */
+int taco_gemm_selftest_mn(int device, const void* at_bf16, const void* bt_bf16, float* d_f32, int32_t m, int32_t n, int32_t k, int32_t splits,
+                          void* stream);
 
 /* -- rollout-buffer post-processing: PPOReplayBuffer.compute_returns_and_advantage
  * (IsaacGymEnvs/algorithms/buffer_asymmetry.py:93-132) and the time-out bootstrap PPO applies to the reward it stores

@@ -119,6 +119,7 @@ def lib():
         "taco_ppo_sigmas": (C.c_int, [vp, vp]),
         "taco_ppo_debug_outputs": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)]),
         "taco_gemm_selftest": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, vp]),
+        "taco_gemm_selftest_mn": (C.c_int, [C.c_int, vp, vp, vp, i32, i32, i32, i32, vp]),
         "taco_gae_advantages": (C.c_int, [C.c_int, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp]),
         "taco_gae_normalize": (C.c_int, [C.c_int, vp, C.c_int64, vp, vp]),
     }

@@ -1,22 +1,28 @@
 // General tcgen05 GEMM of the native PPO update (taco_ppo.cu):  D[M, N] = A[M, K] * B[N, K]^T, bf16 operands, fp32 accumulation
-// in tensor memory.  Both operands are row-major with K contiguous ("K-major") and reach shared memory through TMA tensor maps
-// (cp.async.bulk.tensor.2d, SWIZZLE_128B, out-of-bounds boxes zero-filled, so ragged M / N / K need no padding code).
+// in tensor memory.  Operands reach shared memory through TMA tensor maps (cp.async.bulk.tensor.2d, SWIZZLE_128B, out-of-bounds
+// boxes zero-filled, so ragged M / N / K need no padding code) in one of two forms:
+//   K-major    A as [M][K], B as [N][K] row-major (K contiguous): forward and dX GEMMs (K = features)
+//   MN-major   A as [K][M], B as [K][N] row-major (M / N contiguous): the weight-gradient GEMMs dW = dZ^T X (K = batch) read the
+//              batch-major gradients and activations exactly as the other GEMMs wrote them -- no transposed copies anywhere
 //
-//   tile       128 (M) x n_tile (N <= 256, multiple of 16) per work item; K in blocks of 64 (one 128-byte swizzle row), 16 per MMA
+//   tile       128 (M) x n_tile (N <= 256, multiple of 16) per work item; K in blocks of 64, 16 per MMA
 //   work item  (m_tile, k_split): split-K gives the K = batch GEMMs of the weight gradients (2 output tiles) enough CTAs; every
-//              split writes its own fp32 partial, which the gradient-norm kernel sums in a fixed order (bit-reproducible)
+//              split writes its own fp32 partial, which the assembly kernel sums in a fixed order (bit-reproducible)
 //   pipeline   persistent CTAs; warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..9 = epilogue (two per
 //              TMEM lane quarter, alternating 32-column chunks: the epilogue is latency-bound, so two warps per scheduler);
 //              4 smem stages (full / empty mbarriers), 2 accumulators of 256 TMEM columns (tmem_full / tmem_empty), so the
 //              epilogue of one work item overlaps the MMAs of the next
 //   epilogues  EPI_F32            out_f32[split][m][n] = acc (+ bias[n])
-//              EPI_BIAS_RELU_DUAL y = relu(acc + bias[n]) as bf16, written batch-major [m][n] AND feature-major [n][m]
-//              EPI_RELUBWD_DUAL   g = acc * (act[m][n] > 0) as bf16, both layouts (the ReLU backward of the layer below)
+//              EPI_BIAS_RELU      y = relu(acc + bias[n]) as bf16 [m][n]; one 32-bit word per (row, 32-column chunk) records which
+//                                 pre-activations were > 0
+//              EPI_RELUBWD        g = acc * (pre-activation > 0) as bf16 [m][n] (the ReLU backward of the layer below), from those
+//                                 mask words
 //              EPI_TANH_F32       out_f32[m][n] = tanh(acc + bias[n])     (actor mean, nets_asymmetry.py:32-39)
 //              EPI_LSTM           one LSTM time step from the gate pre-activations (nets_asymmetry.py:128-136), see LstmEpi
-// A thread of an epilogue warp owns one accumulator row (= TMEM lane).  A layout with "samples contiguous" is what the next
-// GEMM with K = batch needs as its K-major operand; "features contiguous" is what a GEMM with K = features needs: producing
-// both in the epilogue keeps every operand of every GEMM K-major without transpose passes.
+// A thread of an epilogue warp owns one accumulator row (= TMEM lane), so anything it reads or writes in a row-major tensor
+// directly costs one cache line per lane and instruction: the LSU, not DRAM, then bounds the kernel (measured: ~2.4 cycles per
+// line and SM).  The bf16 outputs therefore leave through a shared-memory staging tile and are stored with 4 lanes per row;
+// per-row inputs (ReLU mask) are one word per lane, lanes along the rows.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -37,20 +43,19 @@ constexpr int kStages = 4;
 constexpr int kGemmThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 column halves x 4 TMEM lane quarters)
 constexpr int kStageA = BM * BK * 2;          // 16 KB
 constexpr int kStageB = 256 * BK * 2;         // 32 KB (n_tile <= 256)
-constexpr int kGemmSmem = 1024 + kStages * (kStageA + kStageB) + 256 + 1024 + 2 * 2 * 32 * BM * 2;
+constexpr int kStageBm = BM * 64;             // output staging tile: 128 rows x 64 bytes (32 bf16), 16-byte pieces swizzled
+constexpr int kGemmSmem = 1024 + kStages * (kStageA + kStageB) + 256 + 1024 + 2 * 2 * kStageBm;
 constexpr int kAccCols = 256;
 
-enum : int { EPI_F32 = 0, EPI_BIAS_RELU_DUAL = 1, EPI_RELUBWD_DUAL = 2, EPI_TANH_F32 = 3, EPI_LSTM = 4 };
+enum : int { EPI_F32 = 0, EPI_BIAS_RELU = 1, EPI_RELUBWD = 2, EPI_TANH_F32 = 3, EPI_LSTM = 4 };
 
 struct LstmEpi {
     // gates = [i | f | g | o] pre-activations of H = 64 units each (torch nn.LSTM row blocks), bias already inside the GEMM
     const float* c_prev;              // [m][64] fp32 (null: zero)
     float* c_out;                     // [m][64] fp32
     __nv_bfloat16* gates_out;         // [m][256] bf16: sigmoid(i), sigmoid(f), tanh(g), sigmoid(o)   (saved for the backward pass)
-    __nv_bfloat16* h_bm;              // batch-major destination of h: row stride ld_h_bm elements (the next step's operand [h | x | 1 1])
+    __nv_bfloat16* h_bm;              // destination of h: row stride ld_h_bm elements (the next step's operand [h | x | 1 1])
     long long ld_h_bm;
-    __nv_bfloat16* h_fm;              // feature-major destination of h: row j at h_fm + j * ld_h_fm, sample m at + m
-    long long ld_h_fm;
 };
 
 struct GemmParams {
@@ -58,17 +63,30 @@ struct GemmParams {
     int n_tile;                       // UMMA N: multiple of 16, >= n, <= 256
     int splits, kb_per_split;         // split-K: work item (m_tile, split) covers k blocks [split * kb_per_split, ...)
     int a_row0, b_row0;               // row offsets into the tensor maps (views of larger buffers)
+    int mn_major;                     // 1: both operands are stored TRANSPOSED, A as [K][M] and B as [K][N] (M / N contiguous): the K = batch
+                                      // GEMMs of the weight gradients read the batch-major activations and gradients as they are.  The
+                                      // tensor maps then have 64 x 64 boxes (64 M- or N-elements x 64 k-rows, one 8 KB SWIZZLE_128B block
+                                      // per 64 columns) and the MMAs use MN-major shared-memory descriptors
     int epi;
     int n_valid;                      // columns written by the epilogue (<= n_tile)
     float* out_f32; long long ldc, split_stride;
     __nv_bfloat16* out_bm; long long ld_bm;
-    __nv_bfloat16* out_fm; long long ld_fm;
     const float* bias;
-    const __nv_bfloat16* act; long long ld_act;
+    const uint32_t* mask_in;          // EPI_RELUBWD: [ceil(n / 32)][ld_mask] words, bit j of word (c, m) = pre-activation (m, 32 c + j) > 0
+    uint32_t* mask_out;               // EPI_BIAS_RELU: the same array, written (may be null)
+    long long ld_mask;
     const int* stop;                  // device flag (may be null): non-zero = the update stopped early (KL), the launch is a no-op
     LstmEpi lstm;
 };
 
+// MN-major SWIZZLE_128B operand: 64 (M or N) x 64 (K) blocks of 8 KB; inside a block k-row r is the 128-byte line r (8-row atoms,
+// 1024 bytes apart = stride byte offset), the next 64 M / N elements are the next block (leading byte offset).  cute's canonical
+// layout Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.
+constexpr uint32_t kMnBlock = 64 * BK * 2;
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(kMnBlock >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
                  "l"(tm), "r"(bar), "r"(c0), "r"(c1)
@@ -98,13 +116,14 @@ __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t raw_u32 = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);      // offset arithmetic keeps the pointer in the shared state space (STS / LDS, not generic ST / LD)
     const uint32_t s_a = smem_u32(smem), s_b = s_a + kStages * kStageA;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kStageA + kStageB));
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages, bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
     float* s_bias = reinterpret_cast<float*>(smem + kStages * (kStageA + kStageB) + 256);           // [256]
-    uint16_t* s_stage = reinterpret_cast<uint16_t*>(smem + kStages * (kStageA + kStageB) + 256 + 1024);   // [half][2][32][128] bf16: feature-major copy-out
+    uint8_t* s_stage_bm = smem + kStages * (kStageA + kStageB) + 256 + 1024;                               // [half][2][128][64 B]: bf16 copy-out
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 1 && lane == 0) {
@@ -132,9 +151,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
                 if (elect_one_sync()) {
-                    mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes);
-                    tma_load_2d(s_a + stage * kStageA, &tmA, kb * BK, p.a_row0 + mt * BM, bar_full + 8 * stage);
-                    tma_load_2d(s_b + stage * kStageB, &tmB, kb * BK, p.b_row0, bar_full + 8 * stage);
+                    if (!p.mn_major) {
+                        mbar_arrive_expect_tx(bar_full + 8 * stage, stage_bytes);
+                        tma_load_2d(s_a + stage * kStageA, &tmA, kb * BK, p.a_row0 + mt * BM, bar_full + 8 * stage);
+                        tma_load_2d(s_b + stage * kStageB, &tmB, kb * BK, p.b_row0, bar_full + 8 * stage);
+                    } else {
+                        const int nb = (p.n_tile + 63) >> 6;
+                        mbar_arrive_expect_tx(bar_full + 8 * stage, (uint32_t)(2 + nb) * kMnBlock);
+                        for (int i = 0; i < 2; ++i) tma_load_2d(s_a + stage * kStageA + i * kMnBlock, &tmA, mt * BM + 64 * i, p.a_row0 + kb * BK, bar_full + 8 * stage);
+                        for (int i = 0; i < nb; ++i) tma_load_2d(s_b + stage * kStageB + i * kMnBlock, &tmB, 64 * i, p.b_row0 + kb * BK, bar_full + 8 * stage);
+                    }
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -143,7 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ===================== MMA issuer
         uint32_t stage = 0, phase = 0, buf = 0, acc_phase = 0;
-        const uint32_t idesc = umma_idesc_bf16(BM, p.n_tile);
+        const uint32_t idesc = umma_idesc_bf16(BM, p.n_tile) | (p.mn_major ? (1u << 15) | (1u << 16) : 0u);     // a_major / b_major = MN
         for (int w = blockIdx.x; w < total; w += gridDim.x) {
             const int sp = w / m_tiles;
             const int kb0 = sp * p.kb_per_split, kb1 = min(kb0 + p.kb_per_split, kb_total);
@@ -154,10 +180,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
                 if (elect_one_sync()) {
-                    const uint64_t adesc = umma_desc_sw128(s_a + stage * kStageA), bdesc = umma_desc_sw128(s_b + stage * kStageB);
                     const int ksteps = min(BK / 16, (p.k - kb * BK + 15) / 16);      // the zero-filled tail of K costs no MMAs
-                    for (int ks = 0; ks < ksteps; ++ks)
-                        umma_bf16(d_addr, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, (uint32_t)(kb != kb0 || ks != 0));
+                    if (!p.mn_major) {
+                        const uint64_t adesc = umma_desc_sw128(s_a + stage * kStageA), bdesc = umma_desc_sw128(s_b + stage * kStageB);
+                        for (int ks = 0; ks < ksteps; ++ks)          // 16 k = 32 bytes along the swizzled rows
+                            umma_bf16(d_addr, adesc + (uint64_t)(2 * ks), bdesc + (uint64_t)(2 * ks), idesc, (uint32_t)(kb != kb0 || ks != 0));
+                    } else {
+                        const uint64_t adesc = umma_desc_sw128_mn(s_a + stage * kStageA), bdesc = umma_desc_sw128_mn(s_b + stage * kStageB);
+                        for (int ks = 0; ks < ksteps; ++ks)          // 16 k = two 8-row atoms = 2048 bytes
+                            umma_bf16(d_addr, adesc + (uint64_t)(128 * ks), bdesc + (uint64_t)(128 * ks), idesc, (uint32_t)(kb != kb0 || ks != 0));
+                    }
                     umma_commit(bar_empty + 8 * stage);                 // stage free once these MMAs have read it
                     if (kb == kb1 - 1) umma_commit(bar_tfull + 8 * buf);
                 }
@@ -174,7 +206,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int r = (quad << 5) | lane;
         const int half = (warp - 2) >> 2;                                 // warps 2..5 take the even 32-column chunks, 6..9 the odd ones
         const int te = (((warp - 2) & 3) << 5) | lane;                    // 0..127: linear index inside the half's thread group
-        uint16_t* const s_stage_h = s_stage + half * (2 * 32 * BM);
+        uint8_t* const s_bm_h = s_stage_bm + half * (2 * kStageBm);
         uint32_t buf = 0, acc_phase = 0, sb = 0;
         // column-wise constants once per CTA (the bias of the layer)
         if (p.bias != nullptr)
@@ -225,74 +257,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         st_u4(g + 128, pg); st_u4(g + 136, pg + 4); st_u4(g + 192, po); st_u4(g + 200, po + 4);
                         if (L.h_bm) { st_u4(L.h_bm + m * L.ld_h_bm + j0, ph); st_u4(L.h_bm + m * L.ld_h_bm + j0 + 8, ph + 4); }
                     }
-                    if (L.h_fm) {                                         // feature-major copy of h through the staging tile (16 units x 128 samples)
-                        uint16_t* st = s_stage_h + sb * (32 * BM);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) st[j * BM + r] = (uint16_t)((j & 1) ? (ph[j >> 1] >> 16) : (ph[j >> 1] & 0xFFFFu));
-                        epi_barrier(half);
-#pragma unroll
-                        for (int q = 0; q < 2; ++q) {
-                            const int j = q * 8 + (te >> 4), seg = te & 15;
-                            const long long mm = (long long)mt * BM + seg * 8;
-                            if (mm < p.m)
-                                *reinterpret_cast<uint4*>(L.h_fm + (long long)(j0 + j) * L.ld_h_fm + mm) = *reinterpret_cast<const uint4*>(st + j * BM + seg * 8);
-                        }
-                        sb ^= 1u;
-                    }
                 }
-            } else if (p.epi == EPI_BIAS_RELU_DUAL || p.epi == EPI_RELUBWD_DUAL) {
+            } else if (p.epi == EPI_BIAS_RELU || p.epi == EPI_RELUBWD) {
+                // copy-out address of this thread: 4 lanes per row (a warp stores 8 rows x 64 contiguous bytes per instruction)
+                const bool full = (long long)(mt + 1) * BM <= p.m;
+                __nv_bfloat16* const bm_base = p.out_bm + ((long long)mt * BM + (te >> 2)) * p.ld_bm + 8 * (te & 3);
+                const uint32_t bm_rd = (uint32_t)((te >> 2) * 64 + (((te & 3) ^ ((te >> 3) & 3)) << 4));
+                int c0 = 32 * half;
+                uint32_t v[32];
+                if (c0 < p.n_valid) tmem_ld32(t_row + c0, v);
 #pragma unroll 1
-                for (int c0 = 32 * half; c0 < p.n_valid; c0 += 64) {
-                    uint32_t v[32];
-                    tmem_ld32(t_row + c0, v);
-                    uint32_t amask[16];
-                    if (p.epi == EPI_RELUBWD_DUAL) {                      // the activations whose sign is the ReLU mask: issued under the TMEM load
-                        const __nv_bfloat16* a = p.act + m * p.ld_act + c0;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 u = (row_ok && c0 + 8 * q < p.n_valid) ? *reinterpret_cast<const uint4*>(a + 8 * q) : make_uint4(0u, 0u, 0u, 0u);
-                            amask[4 * q] = u.x; amask[4 * q + 1] = u.y; amask[4 * q + 2] = u.z; amask[4 * q + 3] = u.w;
-                        }
-                    }
+                for (; c0 < p.n_valid; c0 += 64) {
+                    uint32_t mw = 0u;                                    // ReLU mask word of (row, chunk): one coalesced word per lane
+                    if (p.epi == EPI_RELUBWD && row_ok) mw = __ldg(p.mask_in + (long long)(c0 >> 5) * p.ld_mask + m);
                     tmem_ld_wait();
                     uint32_t pk[16];
-                    if (p.epi == EPI_BIAS_RELU_DUAL) {
+                    if (p.epi == EPI_BIAS_RELU) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
-                            pk[2 * q] = pack_bf16x2(fmaxf(__uint_as_float(v[4 * q]) + b4.x, 0.0f), fmaxf(__uint_as_float(v[4 * q + 1]) + b4.y, 0.0f));
-                            pk[2 * q + 1] = pack_bf16x2(fmaxf(__uint_as_float(v[4 * q + 2]) + b4.z, 0.0f), fmaxf(__uint_as_float(v[4 * q + 3]) + b4.w, 0.0f));
+                            const float z0 = __uint_as_float(v[4 * q]) + b4.x, z1 = __uint_as_float(v[4 * q + 1]) + b4.y;
+                            const float z2 = __uint_as_float(v[4 * q + 2]) + b4.z, z3 = __uint_as_float(v[4 * q + 3]) + b4.w;
+                            mw |= (z0 > 0.0f ? 1u : 0u) << (4 * q) | (z1 > 0.0f ? 2u : 0u) << (4 * q) | (z2 > 0.0f ? 4u : 0u) << (4 * q) | (z3 > 0.0f ? 8u : 0u) << (4 * q);
+                            pk[2 * q] = pack_bf16x2(fmaxf(z0, 0.0f), fmaxf(z1, 0.0f));
+                            pk[2 * q + 1] = pack_bf16x2(fmaxf(z2, 0.0f), fmaxf(z3, 0.0f));
                         }
+                        if (p.mask_out && row_ok) p.mask_out[(long long)(c0 >> 5) * p.ld_mask + m] = mw;
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            // bf16 > 0  <=>  sign clear and not zero (activations are post-ReLU: never negative, never NaN)
-                            const uint32_t a = amask[i];
-                            const bool lo = (a & 0x7FFFu) != 0u && !(a & 0x8000u), hi = (a & 0x7FFF0000u) != 0u && !(a & 0x80000000u);
-                            pk[i] = pack_bf16x2(lo ? __uint_as_float(v[2 * i]) : 0.0f, hi ? __uint_as_float(v[2 * i + 1]) : 0.0f);
-                        }
+                        for (int i = 0; i < 16; ++i)
+                            pk[i] = pack_bf16x2((mw >> (2 * i)) & 1u ? __uint_as_float(v[2 * i]) : 0.0f, (mw >> (2 * i + 1)) & 1u ? __uint_as_float(v[2 * i + 1]) : 0.0f);
                     }
+                    if (c0 + 64 < p.n_valid) tmem_ld32(t_row + c0 + 64, v);   // the next chunk's accumulator columns fly under the staging + copy-out
                     const int nv = min(32, p.n_valid - c0);               // multiple of 8
-                    if (p.out_bm && row_ok) {
-                        __nv_bfloat16* o = p.out_bm + m * p.ld_bm + c0;
+                    uint8_t* sbm = s_bm_h + sb * kStageBm;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)                           // own row into the staging tile (16-byte pieces XOR-swizzled: conflict-free)
+                        *reinterpret_cast<uint4*>(sbm + r * 64 + ((q ^ ((r >> 1) & 3)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    epi_barrier(half);
+                    uint4 ob[4];                                          // all shared-memory reads first, then the stores
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ob[q] = *reinterpret_cast<const uint4*>(sbm + q * (32 * 64) + bm_rd);
+                    if (full && nv == 32) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(bm_base + (long long)(q * 32) * p.ld_bm + c0) = ob[q];
+                    } else {
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            if (8 * q < nv) st_u4(o + 8 * q, pk + 4 * q);
+                            if ((long long)mt * BM + q * 32 + (te >> 2) < p.m && 8 * (te & 3) < nv)
+                                *reinterpret_cast<uint4*>(bm_base + (long long)(q * 32) * p.ld_bm + c0) = ob[q];
                     }
-                    if (p.out_fm) {                                       // feature-major copy through the staging tile (32 features x 128 samples)
-                        uint16_t* st = s_stage_h + sb * (32 * BM);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) st[j * BM + r] = (uint16_t)((j & 1) ? (pk[j >> 1] >> 16) : (pk[j >> 1] & 0xFFFFu));
-                        epi_barrier(half);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int j = q * 8 + (te >> 4), seg = te & 15;
-                            const long long mm = (long long)mt * BM + seg * 8;
-                            if (j < nv && mm < p.m)
-                                *reinterpret_cast<uint4*>(p.out_fm + (long long)(c0 + j) * p.ld_fm + mm) = *reinterpret_cast<const uint4*>(st + j * BM + seg * 8);
-                        }
-                        sb ^= 1u;
-                    }
+                    sb ^= 1u;
                 }
             } else {
                 for (int c0 = 32 * half; c0 < p.n_valid; c0 += 64) {

@@ -89,56 +89,39 @@ struct Hyper {
     int use_lipschitz, world;
 };
 
-// minibatch gather: rows idx[i] of the rollout tensors -> bf16 operands (both layouts) + compact fp32 side arrays
+// minibatch gather: rows idx[i] of the rollout tensors -> bf16 operands (batch-major) + compact fp32 side arrays
 struct GatherParams {
     const float* obs; int obs_dim;                  // [N][obs_dim]
     const float* states; int seq, state_dim;        // [N][seq][state_dim]
     const float* act; const float* logp; const float* adv; const float* ret;   // [N][A], [N], [N], [N]
     const long long* idx; int B, act_dim;
-    bf16* x0_bm; int ld_x0; bf16* x0_fm;            // [B][ld_x0], [pad8(obs_dim)][B]
-    bf16* u_bm; bf16* u_fm; int ld_u;               // [seq*B][ld_u], [ld_u][seq*B]: columns [h(64) | x | 1 1 | 0]
+    bf16* x0_bm; int ld_x0;                         // [B][ld_x0]
+    bf16* u_bm; int ld_u;                           // [seq*B][ld_u]: columns [h(64) | x | 1 1 | 0]
     float* g_act; float* g_logp; float* g_adv; float* g_ret;
     const int* stop;
 };
 // one operand matrix for the 32 samples of a CTA: features [0, n_src) come from the sample's source row, [n_src, n_src + n_one) are
-// the constant 1, the rest up to n_out is 0; written batch-major (rows of the samples) and feature-major (runs of 32 samples), both
-// in 64-byte segments, through a shared-memory tile
-__device__ __forceinline__ void gather_matrix(float (*tile)[33], const float* src, long long src_stride, const long long* rows, int n_valid,
-                                              int n_src, int n_one, int n_out, bf16* bm, long long ld_bm, bf16* fm, long long ld_fm) {
-    for (int f0 = 0; f0 < n_out; f0 += 64) {
-        const int nf = min(64, n_out - f0);
-        __syncthreads();
-        for (int e = threadIdx.x; e < 32 * nf; e += blockDim.x) {
-            const int sidx = e / nf, j = e % nf, f = f0 + j;
-            float v = 0.0f;
-            if (sidx < n_valid) v = f < n_src ? __ldg(src + rows[sidx] * src_stride + f) : (f < n_src + n_one ? 1.0f : 0.0f);
-            tile[j][sidx] = v;
-        }
-        __syncthreads();
-        for (int e = threadIdx.x; e < 32 * nf; e += blockDim.x) {
-            const int sidx = e / nf, j = e % nf;
-            if (sidx < n_valid) bm[(long long)sidx * ld_bm + f0 + j] = __float2bfloat16_rn(tile[j][sidx]);
-        }
-        for (int e = threadIdx.x; e < 32 * nf; e += blockDim.x) {
-            const int j = e >> 5, sidx = e & 31;
-            if (sidx < n_valid) fm[(long long)(f0 + j) * ld_fm + sidx] = __float2bfloat16_rn(tile[j][sidx]);
-        }
+// the constant 1, the rest up to n_out is 0
+__device__ __forceinline__ void gather_matrix(const float* src, long long src_stride, const long long* rows, int n_valid,
+                                              int n_src, int n_one, int n_out, bf16* bm, long long ld_bm) {
+    for (int e = threadIdx.x; e < n_valid * n_out; e += blockDim.x) {
+        const int sidx = e / n_out, f = e % n_out;
+        const float v = f < n_src ? __ldg(src + rows[sidx] * src_stride + f) : (f < n_src + n_one ? 1.0f : 0.0f);
+        bm[(long long)sidx * ld_bm + f] = __float2bfloat16_rn(v);
     }
 }
 __global__ void __launch_bounds__(256) gather_kernel(const GatherParams p) {
     if (p.stop && *p.stop) return;
-    __shared__ float tile[64][33];
     __shared__ long long rows[32];
     const int i0 = blockIdx.x * 32;
     const int nv = min(32, p.B - i0);
     if (threadIdx.x < 32) rows[threadIdx.x] = threadIdx.x < nv ? p.idx[i0 + threadIdx.x] : 0;
     __syncthreads();
-    gather_matrix(tile, p.obs, p.obs_dim, rows, nv, p.obs_dim, 0, (p.obs_dim + 7) & ~7, p.x0_bm + (long long)i0 * p.ld_x0, p.ld_x0, p.x0_fm + i0, p.B);
-    const long long SB = (long long)p.seq * p.B;
+    gather_matrix(p.obs, p.obs_dim, rows, nv, p.obs_dim, 0, (p.obs_dim + 7) & ~7, p.x0_bm + (long long)i0 * p.ld_x0, p.ld_x0);
     // U_t = [h_{t-1} (64, written by the previous LSTM step; h_0 = 0 stays as allocated) | x_t | 1 1 | 0]: two constant-1 inputs carry the bias
     for (int t = 0; t < p.seq; ++t)
-        gather_matrix(tile, p.states + (long long)t * p.state_dim, (long long)p.seq * p.state_dim, rows, nv, p.state_dim, 2, p.ld_u - kH,
-                      p.u_bm + ((long long)t * p.B + i0) * p.ld_u + kH, p.ld_u, p.u_fm + (long long)kH * SB + (long long)t * p.B + i0, SB);
+        gather_matrix(p.states + (long long)t * p.state_dim, (long long)p.seq * p.state_dim, rows, nv, p.state_dim, 2, p.ld_u - kH,
+                      p.u_bm + ((long long)t * p.B + i0) * p.ld_u + kH, p.ld_u);
     for (int e = threadIdx.x; e < nv * (p.act_dim + 3); e += blockDim.x) {
         const int sidx = e / (p.act_dim + 3), c = e % (p.act_dim + 3);
         const long long r = rows[sidx];
@@ -156,8 +139,8 @@ struct LossParams {
     const float* log_std;                           // [A] (master parameter)
     int B, act_dim;
     Hyper h;
-    bf16* dz_bm; bf16* dz_fm;                       // actor output-layer pre-activation gradient: [B][16], [16][B]
-    bf16* dv_bm; bf16* dv_fm;                       // critic value gradient: [B][16], [16][B] (column / row 0)
+    bf16* dz_bm;                                    // actor output-layer pre-activation gradient: [B][16]
+    bf16* dv_bm;                                    // critic value gradient: [B][16] (column 0)
     double* acc;                                    // kNumStat accumulators
     const int* stop;
 };
@@ -197,10 +180,8 @@ __global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
             }
             const bf16 b = __float2bfloat16_rn(g);
             p.dz_bm[(long long)i * 16 + k] = b;
-            p.dz_fm[(long long)k * p.B + i] = b;
             const bf16 bv = __float2bfloat16_rn(k == 0 ? p.h.vf_coef * 2.0f * dv * invB : 0.0f);
             p.dv_bm[(long long)i * 16 + k] = bv;
-            p.dv_fm[(long long)k * p.B + i] = bv;
         }
     }
     __shared__ float red[7][8];
@@ -251,73 +232,65 @@ __global__ void decide_kernel(const DecideParams p) {
     for (int k = 0; k < 8; ++k) p.acc[k] = 0.0;
 }
 
-// LSTM backward, point-wise part of one time step (the gate math of nn.LSTM): one thread per (sample, unit)
+// LSTM backward, point-wise part of one time step (the gate math of nn.LSTM): one thread per (sample, unit), lanes along the units
 struct LstmBwdParams {
     const float* dh; float* dc;                     // [B][64]: dL/dh_t (total), dL/dc_t carried from step t+1 (in) -> dL/dc_{t-1} (out)
     const bf16* gates; const float* c_prev; const float* c_cur;     // [B][256] activated gates of step t, c_{t-1} (null: 0), c_t
-    bf16* dg_bm; bf16* dg_fm; long long ld_fm; long long fm_col0;   // [B][256], [256][seq*B] at column fm_col0
+    bf16* dg_bm;                                    // [B][256] gate pre-activation gradients of step t
     int B; int first;                               // first = this is the last time step (dc_in = 0)
     const int* stop;
 };
 __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdParams p) {
     if (p.stop && *p.stop) return;
-    // a CTA owns 32 samples x 64 units.  Phase 1: lanes along the units (the batch-major tensors are read / written in
-    // contiguous rows); phase 2: lanes along the samples (64-byte runs of the feature-major gate-gradient rows), through smem.
-    __shared__ float tile[4 * kH][33];
-    const int i0 = blockIdx.x * 32;
-    const int j = threadIdx.x & (kH - 1), sub = threadIdx.x >> 6;
-    for (int s = sub; s < 32; s += 4) {
-        const long long i = i0 + s;
-        if (i >= p.B) break;
-        const bf16* g = p.gates + i * kG;
-        const float gi = __bfloat162float(g[j]), gf = __bfloat162float(g[kH + j]), gg = __bfloat162float(g[2 * kH + j]), go = __bfloat162float(g[3 * kH + j]);
-        const float c = p.c_cur[i * kH + j], cp = p.c_prev ? p.c_prev[i * kH + j] : 0.0f;
-        const float tc = tanhf(c);
-        const float dh = p.dh[i * kH + j];
-        const float dc = (p.first ? 0.0f : p.dc[i * kH + j]) + dh * go * (1.0f - tc * tc);
-        const float d4[4] = {dc * gg * gi * (1.0f - gi), dc * cp * gf * (1.0f - gf), dc * gi * (1.0f - gg * gg), dh * tc * go * (1.0f - go)};
-        p.dc[i * kH + j] = dc * gf;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            p.dg_bm[i * kG + q * kH + j] = __float2bfloat16_rn(d4[q]);
-            tile[q * kH + j][s] = d4[q];
-        }
-    }
-    __syncthreads();
-    const int sl = threadIdx.x & 31, rg = threadIdx.x >> 5;
-    if (i0 + sl < p.B)
-        for (int r = rg; r < 4 * kH; r += 8) p.dg_fm[(long long)r * p.ld_fm + p.fm_col0 + i0 + sl] = __float2bfloat16_rn(tile[r][sl]);
+    const int j = threadIdx.x & (kH - 1);
+    const long long i = (long long)blockIdx.x * 4 + (threadIdx.x >> 6);
+    if (i >= p.B) return;
+    const bf16* g = p.gates + i * kG;
+    const float gi = __bfloat162float(g[j]), gf = __bfloat162float(g[kH + j]), gg = __bfloat162float(g[2 * kH + j]), go = __bfloat162float(g[3 * kH + j]);
+    const float c = p.c_cur[i * kH + j], cp = p.c_prev ? p.c_prev[i * kH + j] : 0.0f;
+    const float tc = tanhf(c);
+    const float dh = p.dh[i * kH + j];
+    const float dc = (p.first ? 0.0f : p.dc[i * kH + j]) + dh * go * (1.0f - tc * tc);
+    p.dc[i * kH + j] = dc * gf;
+    bf16* d = p.dg_bm + i * kG + j;
+    d[0] = __float2bfloat16_rn(dc * gg * gi * (1.0f - gi));
+    d[kH] = __float2bfloat16_rn(dc * cp * gf * (1.0f - gf));
+    d[2 * kH] = __float2bfloat16_rn(dc * gi * (1.0f - gg * gg));
+    d[3 * kH] = __float2bfloat16_rn(dh * tc * go * (1.0f - go));
 }
 
-// row sums of feature-major bf16 matrices = bias gradients; one warp per row
-struct RowSumSeg { const bf16* src; long long ld; int rows; long long count; float* dst; };
-struct RowSumParams { RowSumSeg seg[12]; int n_seg; const int* stop; };
-__global__ void __launch_bounds__(256) rowsum_kernel(const RowSumParams p) {
+// column sums of batch-major bf16 matrices = bias gradients.  A CTA sums kColRows rows of one matrix (lanes along the columns, bf16
+// pairs) and writes one partial row; grad_assemble_kernel adds the partial rows in a fixed order (bit-reproducible).
+constexpr int kColRows = 512, kColLd = 256;
+struct ColSumSeg { const bf16* src; int ld; };      // [B][ld], ld a multiple of 16, <= 256
+struct ColSumParams { ColSumSeg seg[2 * (kMaxHiddenL + 1)]; int n_seg; int B; float* partial; const int* stop; };   // partial: [seg][chunk][kColLd]
+__global__ void __launch_bounds__(256) colsum_kernel(const ColSumParams p) {
     if (p.stop && *p.stop) return;
-    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    for (int s = 0; s < p.n_seg; ++s) {
-        if (row < p.seg[s].rows) {
-            const bf16* src = p.seg[s].src + (long long)row * p.seg[s].ld;
-            float acc = 0.f;
-            const long long n8 = p.seg[s].count >> 3;
-            for (long long k = lane; k < n8; k += 32) {
-                const uint4 u = *reinterpret_cast<const uint4*>(src + 8 * k);
-                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc += __uint_as_float(w4[e] << 16) + __uint_as_float(w4[e] & 0xFFFF0000u);
-            }
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) p.seg[s].dst[row] = acc;
-            return;
+    __shared__ float2 part[256];
+    const ColSumSeg sg = p.seg[blockIdx.y];
+    const int pairs = sg.ld >> 1;                    // 8 .. 128 column pairs
+    const int lanes = 256 / pairs;                   // row lanes
+    const int cp = threadIdx.x % pairs, rl = threadIdx.x / pairs;
+    const int r0 = blockIdx.x * kColRows, r1 = min(r0 + kColRows, p.B);
+    float2 acc = make_float2(0.f, 0.f);
+    if (rl < lanes)
+        for (int r = r0 + rl; r < r1; r += lanes) {
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(sg.src + (long long)r * sg.ld + 2 * cp);
+            acc.x += __uint_as_float(u << 16); acc.y += __uint_as_float(u & 0xFFFF0000u);
         }
-        row -= p.seg[s].rows;
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < pairs) {
+        float2 t = make_float2(0.f, 0.f);
+        for (int l = 0; l < lanes; ++l) { t.x += part[l * pairs + threadIdx.x].x; t.y += part[l * pairs + threadIdx.x].y; }
+        float* dst = p.partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * kColLd + 2 * threadIdx.x;
+        dst[0] = t.x; dst[1] = t.y;
     }
 }
 
 // gradient assembly: flat_grad[dst + r * cols + c] = sum over splits of partial[s][r][col0 + c]; accumulates the global norm^2
 struct GradSeg { const float* partial; int splits; long long split_stride; int ld, col0, rows, cols; long long dst; };
-struct GradParams { GradSeg seg[20]; int n_seg; float* grad; double* acc; const int* stop; };
+struct GradParams { GradSeg seg[32]; int n_seg; float* grad; double* acc; const int* stop; };
 __global__ void __launch_bounds__(256) grad_assemble_kernel(const GradParams p) {
     if (p.stop && *p.stop) return;
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -511,12 +484,13 @@ struct MlpNet {
     bf16* wb[kMaxHiddenL + 1]; int ld_w[kMaxHiddenL + 1];          // [out_pad16][pad8(in)]
     bf16* wt[kMaxHiddenL + 1]; int ld_t[kMaxHiddenL + 1];          // [in][pad8(out) (>= 16)]
     bf16* x_bm[kMaxHiddenL + 1]; int ld_x[kMaxHiddenL + 1];        // activations X_0 .. X_{L-1}: [B][pad8(s_l)]
-    bf16* x_fm[kMaxHiddenL + 1];                                   // [pad8(s_l)][B]
-    bf16* dz_bm[kMaxHiddenL + 2]; bf16* dz_fm[kMaxHiddenL + 2];    // dZ_1 .. dZ_L (index l): [B][ld], [rows][B]
+    uint32_t* relu_mask[kMaxHiddenL + 1];                          // l >= 1: [ceil(s_l / 32)][B] words, bit j = pre-activation (sample, 32 c + j) > 0
+    bf16* dz_bm[kMaxHiddenL + 2];                                  // dZ_1 .. dZ_L (index l): [B][ld]
     int ld_dz[kMaxHiddenL + 2];
     float* partial[kMaxHiddenL + 1]; int splits[kMaxHiddenL + 1]; int ld_p[kMaxHiddenL + 1];
-    CUtensorMap m_x_bm[kMaxHiddenL + 1], m_x_fm[kMaxHiddenL + 1], m_w[kMaxHiddenL + 1], m_wt[kMaxHiddenL + 1];
-    CUtensorMap m_dz_bm[kMaxHiddenL + 2], m_dz_fm[kMaxHiddenL + 2];
+    // K-major maps (forward / dX GEMMs) and MN-major maps of the same batch-major tensors (dW = dZ^T X reads both transposed)
+    CUtensorMap m_x_bm[kMaxHiddenL + 1], m_x_mn[kMaxHiddenL + 1], m_w[kMaxHiddenL + 1], m_wt[kMaxHiddenL + 1];
+    CUtensorMap m_dz_bm[kMaxHiddenL + 2], m_dz_mn[kMaxHiddenL + 2];
 };
 
 struct TacoPPO {
@@ -528,10 +502,10 @@ struct TacoPPO {
     float *prm = nullptr, *grad = nullptr, *adam_m = nullptr, *adam_v = nullptr;
     MlpNet actor, critic;
     // LSTM
-    bf16 *wcat = nullptr, *whh_t = nullptr, *u_bm = nullptr, *u_fm = nullptr, *gates = nullptr, *dg_bm = nullptr, *dg_fm = nullptr;
-    float *c_state = nullptr, *dh = nullptr, *dc = nullptr, *lstm_partial = nullptr;
+    bf16 *wcat = nullptr, *whh_t = nullptr, *u_bm = nullptr, *gates = nullptr, *dg_bm = nullptr;     // dg_bm: [seq*B][256], all time steps
+    float *c_state = nullptr, *dh = nullptr, *dc = nullptr, *lstm_partial = nullptr, *colsum_partial = nullptr;
     int lstm_splits = 1;
-    CUtensorMap m_u_bm, m_u_fm, m_wcat, m_whh_t, m_dg_bm, m_dg_fm;
+    CUtensorMap m_u_bm, m_u_mn, m_wcat, m_whh_t, m_dg_bm, m_dg_mn;
     // heads / side arrays
     float *mean = nullptr, *value = nullptr, *g_act = nullptr, *g_logp = nullptr, *g_adv = nullptr, *g_ret = nullptr;
     // bookkeeping
@@ -562,11 +536,6 @@ static int launch_gemm(TacoPPO* t, const CUtensorMap& a, const CUtensorMap& b, G
     p.kb_per_split = (kb_total + p.splits - 1) / p.splits;
     p.splits = (kb_total + p.kb_per_split - 1) / p.kb_per_split;       // no empty split
     p.stop = t->stop;
-    if (const char* dbg = getenv("TACO_PPO_DEBUG_SKIP")) {            // timing experiments only (wrong results): drop one of the output copies
-        if (strstr(dbg, "fm")) p.out_fm = nullptr;
-        if (strstr(dbg, "bm")) p.out_bm = nullptr;
-        if (strstr(dbg, "hfm")) p.lstm.h_fm = nullptr;
-    }
     const int total = ((p.m + BM - 1) / BM) * p.splits;
     const int grid = total < t->num_sms ? total : t->num_sms;
     gemm_tc_kernel<<<grid, kGemmThreads, kGemmSmem, s>>>(a, b, p); TACO_LAUNCHED();
@@ -593,20 +562,20 @@ static int setup_net(TacoPPO* t, MlpNet& n, long long& off, bool actor) {
         if (dev_alloc(t, &n.wt[l], (size_t)pad8(in) * n.ld_t[l]) != cudaSuccess) return TACO_E_NOMEM;
         n.ld_x[l] = pad8(in);
         if (dev_alloc(t, &n.x_bm[l], (size_t)B * n.ld_x[l]) != cudaSuccess) return TACO_E_NOMEM;
-        if (dev_alloc(t, &n.x_fm[l], (size_t)pad8(in) * B) != cudaSuccess) return TACO_E_NOMEM;
+        n.relu_mask[l] = nullptr;
+        if (l > 0 && dev_alloc(t, &n.relu_mask[l], (size_t)((in + 31) / 32) * B) != cudaSuccess) return TACO_E_NOMEM;
         const int lz = l + 1;
         n.ld_dz[lz] = pad16(out);
         if (dev_alloc(t, &n.dz_bm[lz], (size_t)B * n.ld_dz[lz]) != cudaSuccess) return TACO_E_NOMEM;
-        if (dev_alloc(t, &n.dz_fm[lz], (size_t)pad16(out) * B) != cudaSuccess) return TACO_E_NOMEM;
         n.splits[l] = splits_for(out, B, t->num_sms);
         n.ld_p[l] = pad16(in);
         if (dev_alloc(t, &n.partial[l], (size_t)n.splits[l] * out * n.ld_p[l]) != cudaSuccess) return TACO_E_NOMEM;
         bool ok = make_map(&n.m_x_bm[l], n.x_bm[l], B, in, n.ld_x[l], BM);
-        ok = ok && make_map(&n.m_x_fm[l], n.x_fm[l], in, B, B, pad16(in));                   // B operand of the dW GEMM
+        ok = ok && make_map(&n.m_x_mn[l], n.x_bm[l], B, n.ld_x[l], n.ld_x[l], BK);           // B operand of the dW GEMM (MN-major: 64 x 64 boxes)
         ok = ok && make_map(&n.m_w[l], n.wb[l], out, in, n.ld_w[l], pad16(out));             // B operand of the forward GEMM
         ok = ok && make_map(&n.m_wt[l], n.wt[l], in, pad8(out) < 16 ? 16 : out, n.ld_t[l], pad16(in));   // B operand of the dX GEMM
         ok = ok && make_map(&n.m_dz_bm[lz], n.dz_bm[lz], B, n.ld_dz[lz], n.ld_dz[lz], BM);   // A operand of the dX GEMM
-        ok = ok && make_map(&n.m_dz_fm[lz], n.dz_fm[lz], out, B, B, BM);                     // A operand of the dW GEMM
+        ok = ok && make_map(&n.m_dz_mn[lz], n.dz_bm[lz], B, n.ld_dz[lz], n.ld_dz[lz], BK);   // A operand of the dW GEMM (MN-major)
         if (!ok) return ppo_fail(TACO_E_CUDA, "cuTensorMapEncodeTiled failed");
     }
     (void)actor;
@@ -672,10 +641,9 @@ int taco_ppo_create(int device, const TacoPPOCfg* cfg, TacoPPO** out) {
     if (ce == cudaSuccess) ce = dev_alloc(t, &t->wcat, (size_t)kG * t->ld_u);
     if (ce == cudaSuccess) ce = dev_alloc(t, &t->whh_t, (size_t)kH * kG);
     if (ce == cudaSuccess) ce = dev_alloc(t, &t->u_bm, (size_t)SB * t->ld_u);
-    if (ce == cudaSuccess) ce = dev_alloc(t, &t->u_fm, (size_t)t->ld_u * SB);
     if (ce == cudaSuccess) ce = dev_alloc(t, &t->gates, (size_t)SB * kG);
-    if (ce == cudaSuccess) ce = dev_alloc(t, &t->dg_bm, (size_t)B * kG);
-    if (ce == cudaSuccess) ce = dev_alloc(t, &t->dg_fm, (size_t)kG * SB);
+    if (ce == cudaSuccess) ce = dev_alloc(t, &t->dg_bm, (size_t)SB * kG);
+    if (ce == cudaSuccess) ce = dev_alloc(t, &t->colsum_partial, (size_t)2 * (kMaxHiddenL + 1) * ((B + kColRows - 1) / kColRows) * kColLd);
     if (ce == cudaSuccess) ce = dev_alloc(t, &t->c_state, (size_t)SB * kH);
     if (ce == cudaSuccess) ce = dev_alloc(t, &t->dh, (size_t)B * kH);
     if (ce == cudaSuccess) ce = dev_alloc(t, &t->dc, (size_t)B * kH);
@@ -702,11 +670,11 @@ int taco_ppo_create(int device, const TacoPPOCfg* cfg, TacoPPO** out) {
     }
     if (ce != cudaSuccess) return bail(ce == cudaErrorMemoryAllocation ? TACO_E_NOMEM : TACO_E_CUDA, "taco_ppo_create: device allocation failed");
     bool ok = make_map(&t->m_u_bm, t->u_bm, SB, t->ld_u, t->ld_u, BM);
-    ok = ok && make_map(&t->m_u_fm, t->u_fm, t->ld_u, SB, SB, pad16(t->ld_u));
+    ok = ok && make_map(&t->m_u_mn, t->u_bm, SB, t->ld_u, t->ld_u, BK);
     ok = ok && make_map(&t->m_wcat, t->wcat, kG, t->ld_u, t->ld_u, kG);
     ok = ok && make_map(&t->m_whh_t, t->whh_t, kH, kG, kG, kH);
-    ok = ok && make_map(&t->m_dg_bm, t->dg_bm, B, kG, kG, BM);
-    ok = ok && make_map(&t->m_dg_fm, t->dg_fm, kG, SB, SB, BM);
+    ok = ok && make_map(&t->m_dg_bm, t->dg_bm, SB, kG, kG, BM);
+    ok = ok && make_map(&t->m_dg_mn, t->dg_bm, SB, kG, kG, BK);
     if (!ok) return bail(TACO_E_CUDA, "taco_ppo_create: cuTensorMapEncodeTiled failed");
     if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem) != cudaSuccess)
         return bail(TACO_E_CUDA, "taco_ppo_create: cudaFuncSetAttribute failed");
@@ -826,8 +794,9 @@ static int mlp_forward(TacoPPO* t, MlpNet& n, bool actor, cudaStream_t s) {
         p.m = t->B; p.n = n.s[l + 1]; p.k = n.s[l]; p.n_tile = pad16(n.s[l + 1]); p.splits = 1;
         p.bias = t->prm + n.b_off[l];
         if (l + 1 < n.L) {
-            p.epi = EPI_BIAS_RELU_DUAL; p.n_valid = pad8(n.s[l + 1]);
-            p.out_bm = n.x_bm[l + 1]; p.ld_bm = n.ld_x[l + 1]; p.out_fm = n.x_fm[l + 1]; p.ld_fm = t->B;
+            p.epi = EPI_BIAS_RELU; p.n_valid = pad8(n.s[l + 1]);
+            p.out_bm = n.x_bm[l + 1]; p.ld_bm = n.ld_x[l + 1];
+            p.mask_out = n.relu_mask[l + 1]; p.ld_mask = t->B;
         } else if (actor) {
             p.epi = EPI_TANH_F32; p.n_valid = t->A; p.out_f32 = t->mean; p.ldc = t->A;
         } else {
@@ -847,9 +816,10 @@ static int mlp_backward(TacoPPO* t, MlpNet& n, float* dx_out, cudaStream_t s) {
             GemmParams p;
             memset(&p, 0, sizeof(p));
             p.m = out; p.n = in; p.k = t->B; p.n_tile = pad16(in); p.splits = n.splits[l];
-            p.epi = EPI_F32; p.n_valid = pad16(in) < 32 ? pad16(in) : pad16(in);
+            p.epi = EPI_F32; p.n_valid = pad16(in);
             p.out_f32 = n.partial[l]; p.ldc = n.ld_p[l]; p.split_stride = (long long)out * n.ld_p[l];
-            const int rc = launch_gemm(t, n.m_dz_fm[lz], n.m_x_fm[l], p, s);
+            p.mn_major = 1;
+            const int rc = launch_gemm(t, n.m_dz_mn[lz], n.m_x_mn[l], p, s);
             if (rc != TACO_OK) return rc;
         }
         if (l > 0 || dx_out) {   // dX_{l-1} = dZ W_l: M = batch, N = in, K = out
@@ -857,9 +827,9 @@ static int mlp_backward(TacoPPO* t, MlpNet& n, float* dx_out, cudaStream_t s) {
             memset(&p, 0, sizeof(p));
             p.m = t->B; p.n = in; p.k = n.ld_dz[lz] < n.ld_t[l] ? n.ld_dz[lz] : n.ld_t[l]; p.n_tile = pad16(in); p.splits = 1;
             if (l > 0) {
-                p.epi = EPI_RELUBWD_DUAL; p.n_valid = pad8(in);
-                p.act = n.x_bm[l]; p.ld_act = n.ld_x[l];
-                p.out_bm = n.dz_bm[l]; p.ld_bm = n.ld_dz[l]; p.out_fm = n.dz_fm[l]; p.ld_fm = t->B;
+                p.epi = EPI_RELUBWD; p.n_valid = pad8(in);
+                p.mask_in = n.relu_mask[l]; p.ld_mask = t->B;
+                p.out_bm = n.dz_bm[l]; p.ld_bm = n.ld_dz[l];
             } else {
                 p.epi = EPI_F32; p.n_valid = in; p.out_f32 = dx_out; p.ldc = in;
             }
@@ -881,8 +851,8 @@ int taco_ppo_forward_loss(TacoPPO* t, const TacoPPOHyper* hyper, const float* ob
     memset(&g, 0, sizeof(g));
     g.obs = obs; g.obs_dim = t->cfg.obs_dim; g.states = states; g.seq = t->seq; g.state_dim = t->sd;
     g.act = act; g.logp = old_logp; g.adv = adv; g.ret = ret; g.idx = (const long long*)idx_dev; g.B = B; g.act_dim = t->A;
-    g.x0_bm = t->actor.x_bm[0]; g.ld_x0 = t->actor.ld_x[0]; g.x0_fm = t->actor.x_fm[0];
-    g.u_bm = t->u_bm; g.u_fm = t->u_fm; g.ld_u = t->ld_u;
+    g.x0_bm = t->actor.x_bm[0]; g.ld_x0 = t->actor.ld_x[0];
+    g.u_bm = t->u_bm; g.ld_u = t->ld_u;
     g.g_act = t->g_act; g.g_logp = t->g_logp; g.g_adv = t->g_adv; g.g_ret = t->g_ret; g.stop = t->stop;
     gather_kernel<<<(B + 31) / 32, 256, 0, s>>>(g); TACO_LAUNCHED();
     int rc = TACO_OK;
@@ -897,10 +867,8 @@ int taco_ppo_forward_loss(TacoPPO* t, const TacoPPOHyper* hyper, const float* ob
         p.lstm.gates_out = t->gates + (size_t)k * B * kG;
         if (k + 1 < t->seq) {
             p.lstm.h_bm = t->u_bm + (size_t)(k + 1) * B * t->ld_u; p.lstm.ld_h_bm = t->ld_u;
-            p.lstm.h_fm = t->u_fm + (size_t)(k + 1) * B; p.lstm.ld_h_fm = (long long)t->seq * B;
         } else {
             p.lstm.h_bm = t->critic.x_bm[0]; p.lstm.ld_h_bm = t->critic.ld_x[0];
-            p.lstm.h_fm = t->critic.x_fm[0]; p.lstm.ld_h_fm = B;
         }
         rc = launch_gemm(t, t->m_u_bm, t->m_wcat, p, s);
         if (rc != TACO_OK) return rc;
@@ -915,8 +883,8 @@ int taco_ppo_forward_loss(TacoPPO* t, const TacoPPOHyper* hyper, const float* ob
     memset(&L, 0, sizeof(L));
     L.mean = t->mean; L.value = t->value; L.act = t->g_act; L.old_logp = t->g_logp; L.adv = t->g_adv; L.ret = t->g_ret;
     L.log_std = t->prm + t->off_log_std; L.B = B; L.act_dim = t->A; L.h = to_hyper(hyper);
-    L.dz_bm = t->actor.dz_bm[t->actor.L]; L.dz_fm = t->actor.dz_fm[t->actor.L];
-    L.dv_bm = t->critic.dz_bm[t->critic.L]; L.dv_fm = t->critic.dz_fm[t->critic.L];
+    L.dz_bm = t->actor.dz_bm[t->actor.L];
+    L.dv_bm = t->critic.dz_bm[t->critic.L];
     L.acc = t->acc; L.stop = t->stop;
     loss_kernel<<<(B + 255) / 256, 256, 0, s>>>(L); TACO_LAUNCHED();
     PPO_CUDA(cudaGetLastError());
@@ -961,39 +929,39 @@ int taco_ppo_backward(TacoPPO* t, void* stream) {
         memset(&b, 0, sizeof(b));
         b.dh = t->dh; b.dc = t->dc; b.gates = t->gates + (size_t)k * B * kG;
         b.c_prev = k > 0 ? t->c_state + (size_t)(k - 1) * B * kH : nullptr; b.c_cur = t->c_state + (size_t)k * B * kH;
-        b.dg_bm = t->dg_bm; b.dg_fm = t->dg_fm; b.ld_fm = SB; b.fm_col0 = (long long)k * B; b.B = B; b.first = (k == t->seq - 1); b.stop = t->stop;
-        lstm_bwd_kernel<<<(B + 31) / 32, 256, 0, s>>>(b); TACO_LAUNCHED();
-        if (k > 0) {   // dh_{t-1} = dgates W_hh: M = batch, N = 64, K = 256
+        b.dg_bm = t->dg_bm + (size_t)k * B * kG; b.B = B; b.first = (k == t->seq - 1); b.stop = t->stop;
+        lstm_bwd_kernel<<<(B + 3) / 4, 256, 0, s>>>(b); TACO_LAUNCHED();
+        if (k > 0) {   // dh_{t-1} = dgates_t W_hh: M = batch, N = 64, K = 256
             GemmParams p;
             memset(&p, 0, sizeof(p));
-            p.m = B; p.n = kH; p.k = kG; p.n_tile = kH; p.splits = 1; p.epi = EPI_F32; p.n_valid = kH; p.out_f32 = t->dh; p.ldc = kH;
+            p.m = B; p.n = kH; p.k = kG; p.n_tile = kH; p.splits = 1; p.a_row0 = k * B; p.epi = EPI_F32; p.n_valid = kH; p.out_f32 = t->dh; p.ldc = kH;
             rc = launch_gemm(t, t->m_dg_bm, t->m_whh_t, p, s);
             if (rc != TACO_OK) return rc;
         }
     }
-    {   // dWcat = dgates^T [h | x | 1 1] over all time steps: M = 256, N = ld_u, K = seq * batch
+    {   // dWcat = dgates^T [h | x | 1 1] over all time steps: M = 256, N = ld_u, K = seq * batch (both operands read transposed)
         GemmParams p;
         memset(&p, 0, sizeof(p));
         p.m = kG; p.n = t->ld_u; p.k = (int)SB; p.n_tile = pad16(t->ld_u); p.splits = t->lstm_splits; p.epi = EPI_F32; p.n_valid = pad16(t->ld_u);
         p.out_f32 = t->lstm_partial; p.ldc = t->ld_u; p.split_stride = (long long)kG * t->ld_u;
         if (p.n_valid > t->ld_u) p.n_valid = t->ld_u;
-        rc = launch_gemm(t, t->m_dg_fm, t->m_u_fm, p, s);
+        p.mn_major = 1;
+        rc = launch_gemm(t, t->m_dg_mn, t->m_u_mn, p, s);
         if (rc != TACO_OK) return rc;
     }
-    // bias gradients = row sums of the feature-major dZ
-    RowSumParams rs;
-    memset(&rs, 0, sizeof(rs));
-    int rows_total = 0;
+    // bias gradients = column sums of the batch-major dZ: partial rows here, summed by the assembly kernel below
+    ColSumParams cs;
+    memset(&cs, 0, sizeof(cs));
+    const int col_chunks = (B + kColRows - 1) / kColRows;
     for (int k = 0; k < 2; ++k) {
         MlpNet& n = k == 0 ? t->actor : t->critic;
         for (int l = 0; l < n.L; ++l) {
-            RowSumSeg& S = rs.seg[rs.n_seg++];
-            S.src = n.dz_fm[l + 1]; S.ld = B; S.rows = n.s[l + 1]; S.count = B; S.dst = t->grad + n.b_off[l];
-            rows_total += S.rows;
+            ColSumSeg& S = cs.seg[cs.n_seg++];
+            S.src = n.dz_bm[l + 1]; S.ld = n.ld_dz[l + 1];
         }
     }
-    rs.stop = t->stop;
-    rowsum_kernel<<<(rows_total + 7) / 8, 256, 0, s>>>(rs); TACO_LAUNCHED();
+    cs.B = B; cs.partial = t->colsum_partial; cs.stop = t->stop;
+    colsum_kernel<<<dim3(col_chunks, cs.n_seg), 256, 0, s>>>(cs); TACO_LAUNCHED();
     // weight gradients from the split-K partials
     GradParams gp;
     memset(&gp, 0, sizeof(gp));
@@ -1012,6 +980,7 @@ int taco_ppo_backward(TacoPPO* t, void* stream) {
             const int per = (kb_total + sp - 1) / sp;
             sp = (kb_total + per - 1) / per;
             add(n.partial[l], sp, (long long)n.s[l + 1] * n.ld_p[l], n.ld_p[l], 0, n.s[l + 1], n.s[l], n.w_off[l]);
+            add(t->colsum_partial + (long long)(k * t->actor.L + l) * col_chunks * kColLd, col_chunks, kColLd, kColLd, 0, 1, n.s[l + 1], n.b_off[l]);
         }
     }
     {
@@ -1109,13 +1078,15 @@ int taco_ppo_debug_outputs(TacoPPO* t, float** mean_dev, float** value_dev) {
 
 // test hook: D[M][N] (fp32, ld = N) = A[M][K] B[N][K]^T for bf16 row-major device matrices (ld = K, K multiple of 8) through
 // gemm_tc_kernel with `splits` split-K partials summed on the host side of the call
-int taco_gemm_selftest(int device, const void* a_bf16, const void* b_bf16, float* d_f32, int32_t m, int32_t n, int32_t k, int32_t splits, void* stream) {
+static int gemm_selftest_impl(int device, const void* a_bf16, const void* b_bf16, float* d_f32, int32_t m, int32_t n, int32_t k, int32_t splits, bool mn, void* stream) {
     if (!a_bf16 || !b_bf16 || !d_f32 || m < 1 || n < 1 || n > 256 || k < 8 || (k & 7)) return ppo_fail(TACO_E_INVALID, "taco_gemm_selftest: bad argument");
     DevGuard guard(device);
     cudaStream_t s = (cudaStream_t)stream;
     if (!encode_fn()) return ppo_fail(TACO_E_CUDA, "cuTensorMapEncodeTiled unavailable");
     CUtensorMap ma, mb;
-    if (!make_map(&ma, (const bf16*)a_bf16, m, k, k, BM) || !make_map(&mb, (const bf16*)b_bf16, n, k, k, pad16(n))) return ppo_fail(TACO_E_CUDA, "tensor map");
+    const bool ok = mn ? make_map(&ma, (const bf16*)a_bf16, k, m, m, BK) && make_map(&mb, (const bf16*)b_bf16, k, n, n, BK)
+                       : make_map(&ma, (const bf16*)a_bf16, m, k, k, BM) && make_map(&mb, (const bf16*)b_bf16, n, k, k, pad16(n));
+    if (!ok) return ppo_fail(TACO_E_CUDA, "tensor map");
     PPO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     const int kb_total = (k + BK - 1) / BK;
     int sp = splits < 1 ? 1 : (splits > kb_total ? kb_total : splits);
@@ -1125,7 +1096,7 @@ int taco_gemm_selftest(int device, const void* a_bf16, const void* b_bf16, float
     PPO_CUDA(cudaMalloc(&part, (size_t)sp * m * n * sizeof(float)));
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    p.m = m; p.n = n; p.k = k; p.n_tile = pad16(n); p.splits = sp; p.kb_per_split = per; p.epi = EPI_F32; p.n_valid = n;
+    p.m = m; p.n = n; p.k = k; p.n_tile = pad16(n); p.splits = sp; p.kb_per_split = per; p.epi = EPI_F32; p.n_valid = n; p.mn_major = mn ? 1 : 0;
     p.out_f32 = part; p.ldc = n; p.split_stride = (long long)m * n;
     cudaDeviceProp prop;
     PPO_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -1141,6 +1112,16 @@ int taco_gemm_selftest(int device, const void* a_bf16, const void* b_bf16, float
     cudaFree(part);
     if (e != cudaSuccess) return ppo_fail(TACO_E_CUDA, std::string("taco_gemm_selftest: ") + cudaGetErrorString(e));
     return TACO_OK;
+}
+
+// D[m][n] = A[m][k] B[n][k]^T with both operands K-major (k contiguous)
+int taco_gemm_selftest(int device, const void* a_bf16, const void* b_bf16, float* d_f32, int32_t m, int32_t n, int32_t k, int32_t splits, void* stream) {
+    return gemm_selftest_impl(device, a_bf16, b_bf16, d_f32, m, n, k, splits, false, stream);
+}
+// the same product from TRANSPOSED operands: at[k][m], bt[k][n] (m, n multiples of 8)
+int taco_gemm_selftest_mn(int device, const void* at_bf16, const void* bt_bf16, float* d_f32, int32_t m, int32_t n, int32_t k, int32_t splits, void* stream) {
+    if ((m & 7) || (n & 7)) return ppo_fail(TACO_E_INVALID, "taco_gemm_selftest_mn: m and n must be multiples of 8");
+    return gemm_selftest_impl(device, at_bf16, bt_bf16, d_f32, m, n, k, splits, true, stream);
 }
 
 }  // extern "C"

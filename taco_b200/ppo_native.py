@@ -214,12 +214,16 @@ def ppo_update_native(native, buffer, cfg, epoch, env=None, batch_idx=None, grou
     return native.update(buffer, cfg, epoch, env=env, batch_idx=batch_idx, group=group)
 
 
-def gemm_selftest(a_bf16, b_bf16, splits=1):
-    """D = A B^T through the tcgen05 GEMM kernel of the native update (bf16 CUDA tensors (m, k), (n, k)); returns fp32 (m, n)."""
-    m, k = a_bf16.shape
-    n = b_bf16.shape[0]
+def gemm_selftest(a_bf16, b_bf16, splits=1, transposed=False):
+    """D = A B^T through the tcgen05 GEMM kernel of the native update; returns fp32 (m, n).  ``transposed=False``: bf16 CUDA tensors A (m, k),
+    B (n, k) (K-major operands); ``transposed=True``: the operands are given as At (k, m), Bt (k, n) (the kernel's MN-major mode)."""
+    if transposed:
+        (k, m), n = a_bf16.shape, b_bf16.shape[1]
+    else:
+        (m, k), n = a_bf16.shape, b_bf16.shape[0]
     d = torch.empty(m, n, dtype=torch.float32, device=a_bf16.device)
     dev = a_bf16.device.index or 0
-    _capi.check(_capi.lib().taco_gemm_selftest(dev, C.c_void_p(a_bf16.data_ptr()), C.c_void_p(b_bf16.data_ptr()), C.c_void_p(d.data_ptr()), m, n, k,
-                                               int(splits), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "taco_gemm_selftest")
+    fn = _capi.lib().taco_gemm_selftest_mn if transposed else _capi.lib().taco_gemm_selftest
+    _capi.check(fn(dev, C.c_void_p(a_bf16.data_ptr()), C.c_void_p(b_bf16.data_ptr()), C.c_void_p(d.data_ptr()), m, n, k,
+                   int(splits), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "taco_gemm_selftest")
     return d

@@ -67,6 +67,20 @@ def test_gemm_kernel_against_matmul(m, n, k, splits):
     assert float((d - ref).abs().max() / ref.abs().max()) <= 2e-6
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,n,k,splits", [(256, 256, 4096, 8), (256, 32, 8192, 16), (64, 96, 5120, 20), (256, 64, 65536, 74), (48, 256, 640, 3),
+                                          (128, 16, 64, 1), (16, 8, 136, 1), (296, 72, 1000, 5)])
+def test_gemm_kernel_transposed_operands(m, n, k, splits):
+    """The MN-major operand mode (weight gradients dW = dZ^T X straight from the batch-major tensors)."""
+    from taco_b200.ppo_native import gemm_selftest
+    g = torch.Generator(device="cuda").manual_seed(m + n + k)
+    at = (torch.randn(k, m, device="cuda", generator=g) * 0.5).bfloat16()
+    bt = (torch.randn(k, n, device="cuda", generator=g) * 0.5).bfloat16()
+    d = gemm_selftest(at, bt, splits, transposed=True)
+    ref = at.float().T @ bt.float()
+    assert float((d - ref).abs().max() / ref.abs().max()) <= 2e-6
+
+
 def _hyper(cfg, lr, lip):
     from taco_b200 import _capi
     return _capi.TacoPPOHyper(lr=lr, clip=cfg.clip, target_kl=cfg.target_kl, max_grad=cfg.max_grad, pi_coef=cfg.pi_coef, vf_coef=cfg.vf_coef,
