@@ -10,7 +10,7 @@
 //              split writes its own fp32 partial, which the assembly kernel sums in a fixed order (bit-reproducible)
 //   pipeline   persistent CTAs; warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..9 = epilogue (two per
 //              TMEM lane quarter, alternating 32-column chunks: the epilogue is latency-bound, so two warps per scheduler);
-//              4 smem stages (full / empty mbarriers), 2 accumulators of 256 TMEM columns (tmem_full / tmem_empty), so the
+//              3 smem stages (full / empty mbarriers), 2 accumulators of 256 TMEM columns (tmem_full / tmem_empty), so the
 //              epilogue of one work item overlaps the MMAs of the next
 //   epilogues  EPI_F32            out_f32[split][m][n] = acc (+ bias[n])
 //              EPI_BIAS_RELU      y = relu(acc + bias[n]) as bf16 [m][n]; one 32-bit word per (row, 32-column chunk) records which
@@ -21,8 +21,10 @@
 //              EPI_LSTM           one LSTM time step from the gate pre-activations (nets_asymmetry.py:128-136), see LstmEpi
 // A thread of an epilogue warp owns one accumulator row (= TMEM lane), so anything it reads or writes in a row-major tensor
 // directly costs one cache line per lane and instruction: the LSU, not DRAM, then bounds the kernel (measured: ~2.4 cycles per
-// line and SM).  The bf16 outputs therefore leave through a shared-memory staging tile and are stored with 4 lanes per row;
-// per-row inputs (ReLU mask) are one word per lane, lanes along the rows.
+// line and SM).  Outputs therefore leave through a shared-memory staging tile of 128 rows x 128 bytes in the SWIZZLE_128B
+// pattern: a thread writes its row with conflict-free 16-byte stores and one elected thread hands the tile to the TMA store
+// engine (cp.async.bulk.tensor, clipped at the tensor's edges), which keeps the copy-out off the LSU altogether.  Row-major
+// INPUTS of the LSTM step cross with lanes along the row's bytes; the ReLU mask is one word per lane, lanes along the rows.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -39,11 +41,11 @@ namespace gemm {
 using namespace taco::actor;
 
 constexpr int BM = 128, BK = 64;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kGemmThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 column halves x 4 TMEM lane quarters)
 constexpr int kStageA = BM * BK * 2;          // 16 KB
 constexpr int kStageB = 256 * BK * 2;         // 32 KB (n_tile <= 256)
-constexpr int kStageBm = BM * 64;             // output staging tile: 128 rows x 64 bytes (32 bf16), 16-byte pieces swizzled
+constexpr int kStageBm = BM * 128;            // epilogue staging tile: 128 rows x up to 128 bytes, 16-byte pieces XOR-swizzled
 constexpr int kGemmSmem = 1024 + kStages * (kStageA + kStageB) + 256 + 1024 + 2 * 2 * kStageBm;
 constexpr int kAccCols = 256;
 
@@ -53,7 +55,8 @@ struct LstmEpi {
     // gates = [i | f | g | o] pre-activations of H = 64 units each (torch nn.LSTM row blocks), bias already inside the GEMM
     const float* c_prev;              // [m][64] fp32 (null: zero)
     float* c_out;                     // [m][64] fp32
-    __nv_bfloat16* gates_out;         // [m][256] bf16: sigmoid(i), sigmoid(f), tanh(g), sigmoid(o)   (saved for the backward pass)
+    __nv_bfloat16* gates_out;         // [m][4 chunks][4 gates][16 units] bf16: sigmoid(i), sigmoid(f), tanh(g), sigmoid(o) of units 16 c .. 16 c + 15
+                                      // (saved for the backward pass; a chunk's 128 bytes are what one epilogue round produces per row)
     __nv_bfloat16* h_bm;              // destination of h: row stride ld_h_bm elements (the next step's operand [h | x | 1 1])
     long long ld_h_bm;
 };
@@ -70,7 +73,8 @@ struct GemmParams {
     int epi;
     int n_valid;                      // columns written by the epilogue (<= n_tile)
     float* out_f32; long long ldc, split_stride;
-    __nv_bfloat16* out_bm; long long ld_bm;
+    int tma_store;                    // the output leaves through the third tensor map (tmC): bf16 [m][n] (EPI_BIAS_RELU / EPI_RELUBWD, boxes of
+                                      // 64 columns x 128 rows) or, with EPI_F32, fp32 [splits * m][n] (32 columns x 128 rows; needs m % 128 == 0)
     const float* bias;
     const uint32_t* mask_in;          // EPI_RELUBWD: [ceil(n / 32)][ld_mask] words, bit j of word (c, m) = pre-activation (m, 32 c + j) > 0
     uint32_t* mask_out;               // EPI_BIAS_RELU: the same array, written (may be null)
@@ -92,6 +96,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
                  "l"(tm), "r"(bar), "r"(c0), "r"(c1)
                  : "memory");
 }
+// staging tile (shared memory, SWIZZLE_128B, 128 rows x 128 bytes) -> global tensor at (column c0, row c1), clipped at the tensor's edges
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src_smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// programmatic dependent launch: a kernel launched with the stream-serialization attribute may start while its predecessor in the
+// stream is still running; nothing the predecessor wrote may be read (and nothing it reads overwritten) before pdl_wait()
+// returns = predecessor complete and flushed.  pdl_launch_dependents() lets the successor's CTAs be scheduled from here on.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -114,16 +133,16 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f,
 __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_u32 = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + (((raw_u32 + 1023u) & ~1023u) - raw_u32);      // offset arithmetic keeps the pointer in the shared state space (STS / LDS, not generic ST / LD)
     const uint32_t s_a = smem_u32(smem), s_b = s_a + kStages * kStageA;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kStageA + kStageB));
+    uint8_t* s_stage_bm = smem + kStages * (kStageA + kStageB);                                            // [half][2][128][128 B], 1024-aligned: epilogue staging
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage_bm + 2 * 2 * kStageBm);
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages, bar_tfull = bar_empty + 8 * kStages, bar_tempty = bar_tfull + 16;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-    float* s_bias = reinterpret_cast<float*>(smem + kStages * (kStageA + kStageB) + 256);           // [256]
-    uint8_t* s_stage_bm = smem + kStages * (kStageA + kStageB) + 256 + 1024;                               // [half][2][128][64 B]: bf16 copy-out
+    float* s_bias = reinterpret_cast<float*>(s_stage_bm + 2 * 2 * kStageBm + 256);                         // [256]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 1 && lane == 0) {
@@ -136,6 +155,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem0 = *s_tmem;
+    // everything above is on-chip set-up and may overlap the tail of the previous kernel in the stream
+    pdl_launch_dependents();
+    pdl_wait();
 
     const int m_tiles = (p.m + BM - 1) / BM;
     const int total = (p.stop != nullptr && __ldg(p.stop) != 0) ? 0 : m_tiles * p.splits;
@@ -220,19 +242,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const uint32_t t_row = tmem0 + ((uint32_t)(quad << 5) << 16) + buf * kAccCols;
             if (p.epi == EPI_LSTM) {
+                // Per 16-unit chunk a row reads 64 B of c_{t-1} and writes 64 B of c_t, 32 B of h_t and 128 B of gates.  All of it
+                // crosses global memory with lanes along the row's bytes (3 staging rounds: c in; c + h out; gates out).
                 const LstmEpi& L = p.lstm;
+                const bool full = (long long)(mt + 1) * BM <= p.m;
+                const long long m0 = (long long)mt * BM;
+                const int row4 = te >> 2, pc4 = te & 3;                   // 4 lanes per row (64-byte runs): rows row4 + 32 q
+                const int row8 = te >> 3, pc8 = te & 7;                   // 8 lanes per row (128-byte runs): rows row8 + 16 q
+                const int row2 = te >> 1, pc2 = te & 1;                   // 2 lanes per row (32-byte runs): rows row2 + 64 q
+                const uint32_t own = (uint32_t)(r * 128), key = (uint32_t)(r & 7);
 #pragma unroll 1
                 for (int j0 = 32 * half; j0 < 32 * half + 32; j0 += 16) {
                     uint32_t vi[16], vf[16], vg[16], vo[16];
                     tmem_ld16(t_row + j0, vi); tmem_ld16(t_row + 64 + j0, vf); tmem_ld16(t_row + 128 + j0, vg); tmem_ld16(t_row + 192 + j0, vo);
                     float cp[16];
+                    if (L.c_prev) {                                       // round 1: c_{t-1}, 4 lanes per row -> staging -> own row
+                        uint8_t* sa = s_bm_h + sb * kStageBm;
+                        uint4 in[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const float4 c4 = (L.c_prev && row_ok) ? *reinterpret_cast<const float4*>(L.c_prev + m * 64 + j0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        cp[4 * q] = c4.x; cp[4 * q + 1] = c4.y; cp[4 * q + 2] = c4.z; cp[4 * q + 3] = c4.w;
+                        for (int q = 0; q < 4; ++q) {
+                            const int row = row4 + 32 * q;
+                            in[q] = (full || m0 + row < p.m) ? __ldg(reinterpret_cast<const uint4*>(L.c_prev + (m0 + row) * 64 + j0 + 4 * pc4)) : make_uint4(0u, 0u, 0u, 0u);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int row = row4 + 32 * q;
+                            *reinterpret_cast<uint4*>(sa + row * 128 + ((pc4 ^ (row & 7)) << 4)) = in[q];
+                        }
+                        epi_barrier(half);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 c4 = *reinterpret_cast<const float4*>(sa + own + ((q ^ key) << 4));
+                            cp[4 * q] = c4.x; cp[4 * q + 1] = c4.y; cp[4 * q + 2] = c4.z; cp[4 * q + 3] = c4.w;
+                        }
+                        sb ^= 1u;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) cp[j] = 0.0f;
                     }
                     tmem_ld_wait();
-                    uint32_t pi[8], pf[8], pg[8], po[8], ph[8];
+                    uint32_t pg4[4][8], ph[8];                            // packed gates i, f, g, o and h
                     float cc[16];
 #pragma unroll
                     for (int j = 0; j < 16; j += 2) {
@@ -244,69 +293,118 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             cc[j + e] = gf[e] * cp[j + e] + gi[e] * gg[e];
                             hh[e] = go[e] * tanh_fast(cc[j + e]);
                         }
-                        pi[j >> 1] = pack_bf16x2(gi[0], gi[1]); pf[j >> 1] = pack_bf16x2(gf[0], gf[1]);
-                        pg[j >> 1] = pack_bf16x2(gg[0], gg[1]); po[j >> 1] = pack_bf16x2(go[0], go[1]);
+                        pg4[0][j >> 1] = pack_bf16x2(gi[0], gi[1]); pg4[1][j >> 1] = pack_bf16x2(gf[0], gf[1]);
+                        pg4[2][j >> 1] = pack_bf16x2(gg[0], gg[1]); pg4[3][j >> 1] = pack_bf16x2(go[0], go[1]);
                         ph[j >> 1] = pack_bf16x2(hh[0], hh[1]);
                     }
-                    if (row_ok) {
+                    {                                                     // round 2: c_t (pieces 0..3) and h_t (pieces 4, 5) of the own row -> staging
+                        uint8_t* sa = s_bm_h + sb * kStageBm;
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<float4*>(L.c_out + m * 64 + j0 + 4 * q) = make_float4(cc[4 * q], cc[4 * q + 1], cc[4 * q + 2], cc[4 * q + 3]);
-                        __nv_bfloat16* g = L.gates_out + m * 256 + j0;
-                        st_u4(g, pi); st_u4(g + 8, pi + 4); st_u4(g + 64, pf); st_u4(g + 72, pf + 4);
-                        st_u4(g + 128, pg); st_u4(g + 136, pg + 4); st_u4(g + 192, po); st_u4(g + 200, po + 4);
-                        if (L.h_bm) { st_u4(L.h_bm + m * L.ld_h_bm + j0, ph); st_u4(L.h_bm + m * L.ld_h_bm + j0 + 8, ph + 4); }
+                            *reinterpret_cast<float4*>(sa + own + ((q ^ key) << 4)) = make_float4(cc[4 * q], cc[4 * q + 1], cc[4 * q + 2], cc[4 * q + 3]);
+                        *reinterpret_cast<uint4*>(sa + own + ((4u ^ key) << 4)) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                        *reinterpret_cast<uint4*>(sa + own + ((5u ^ key) << 4)) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+                        epi_barrier(half);
+                        uint4 oc[4], oh[2];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) { const int row = row4 + 32 * q; oc[q] = *reinterpret_cast<const uint4*>(sa + row * 128 + ((pc4 ^ (row & 7)) << 4)); }
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) { const int row = row2 + 64 * q; oh[q] = *reinterpret_cast<const uint4*>(sa + row * 128 + (((4 + pc2) ^ (row & 7)) << 4)); }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int row = row4 + 32 * q;
+                            if (full || m0 + row < p.m) *reinterpret_cast<uint4*>(L.c_out + (m0 + row) * 64 + j0 + 4 * pc4) = oc[q];
+                        }
+                        if (L.h_bm) {
+#pragma unroll
+                            for (int q = 0; q < 2; ++q) {
+                                const int row = row2 + 64 * q;
+                                if (full || m0 + row < p.m) *reinterpret_cast<uint4*>(L.h_bm + (m0 + row) * L.ld_h_bm + j0 + 8 * pc2) = oh[q];
+                            }
+                        }
+                        sb ^= 1u;
+                    }
+                    {                                                     // round 3: the chunk's 4 x 16 gates = 128 bytes of the own row -> staging
+                        uint8_t* sa = s_bm_h + sb * kStageBm;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<uint4*>(sa + own + (((uint32_t)q ^ key) << 4)) = make_uint4(pg4[q >> 1][4 * (q & 1)], pg4[q >> 1][4 * (q & 1) + 1], pg4[q >> 1][4 * (q & 1) + 2], pg4[q >> 1][4 * (q & 1) + 3]);
+                        epi_barrier(half);
+                        uint4 og[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) { const int row = row8 + 16 * q; og[q] = *reinterpret_cast<const uint4*>(sa + row * 128 + ((pc8 ^ (row & 7)) << 4)); }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int row = row8 + 16 * q;
+                            if (full || m0 + row < p.m) *reinterpret_cast<uint4*>(L.gates_out + (m0 + row) * 256 + (j0 >> 4) * 64 + 8 * pc8) = og[q];
+                        }
+                        sb ^= 1u;
                     }
                 }
             } else if (p.epi == EPI_BIAS_RELU || p.epi == EPI_RELUBWD) {
-                // copy-out address of this thread: 4 lanes per row (a warp stores 8 rows x 64 contiguous bytes per instruction)
-                const bool full = (long long)(mt + 1) * BM <= p.m;
-                __nv_bfloat16* const bm_base = p.out_bm + ((long long)mt * BM + (te >> 2)) * p.ld_bm + 8 * (te & 3);
-                const uint32_t bm_rd = (uint32_t)((te >> 2) * 64 + (((te & 3) ^ ((te >> 3) & 3)) << 4));
+                // 64 columns (128 bytes of bf16 per row) per round; the two halves take alternating rounds
+                const uint32_t own = (uint32_t)(r * 128), key = (uint32_t)(r & 7);
+                int c0 = 64 * half;
+                uint32_t v[32];
+                if (c0 < p.n_valid) tmem_ld32(t_row + c0, v);
+#pragma unroll 1
+                for (; c0 < p.n_valid; c0 += 128) {
+                    uint8_t* sa = s_bm_h + sb * kStageBm;
+                    if (te == 0) tma_store_wait_read();                   // the store issued from this buffer two rounds ago has drained it
+#pragma unroll 1
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int cc = c0 + 32 * h2;
+                        if (cc >= p.n_valid) break;                       // (n_valid is a multiple of 8; columns past it in a stored box are clipped or zero)
+                        uint32_t mw = 0u;                                // ReLU mask word of (row, 32 columns): one coalesced word per lane
+                        if (p.epi == EPI_RELUBWD && row_ok) mw = __ldg(p.mask_in + (long long)(cc >> 5) * p.ld_mask + m);
+                        tmem_ld_wait();
+                        uint32_t pk[16];
+                        if (p.epi == EPI_BIAS_RELU) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cc + 4 * q);
+                                const float z0 = __uint_as_float(v[4 * q]) + b4.x, z1 = __uint_as_float(v[4 * q + 1]) + b4.y;
+                                const float z2 = __uint_as_float(v[4 * q + 2]) + b4.z, z3 = __uint_as_float(v[4 * q + 3]) + b4.w;
+                                mw |= (z0 > 0.0f ? 1u : 0u) << (4 * q) | (z1 > 0.0f ? 2u : 0u) << (4 * q) | (z2 > 0.0f ? 4u : 0u) << (4 * q) | (z3 > 0.0f ? 8u : 0u) << (4 * q);
+                                pk[2 * q] = pack_bf16x2(fmaxf(z0, 0.0f), fmaxf(z1, 0.0f));
+                                pk[2 * q + 1] = pack_bf16x2(fmaxf(z2, 0.0f), fmaxf(z3, 0.0f));
+                            }
+                            if (p.mask_out && row_ok) p.mask_out[(long long)(cc >> 5) * p.ld_mask + m] = mw;
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                pk[i] = pack_bf16x2((mw >> (2 * i)) & 1u ? __uint_as_float(v[2 * i]) : 0.0f, (mw >> (2 * i + 1)) & 1u ? __uint_as_float(v[2 * i + 1]) : 0.0f);
+                        }
+                        // the next 32 accumulator columns fly under the staging stores
+                        const int cn = h2 == 0 ? cc + 32 : c0 + 128;
+                        if (cn < p.n_valid) tmem_ld32(t_row + cn, v);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)                       // own row, pieces 4 h2 .. 4 h2 + 3 (XOR-swizzled: conflict-free, and the TMA's SWIZZLE_128B)
+                            *reinterpret_cast<uint4*>(sa + own + (((uint32_t)(4 * h2 + q) ^ key) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    }
+                    fence_async_smem();
+                    epi_barrier(half);
+                    if (te == 0) tma_store_2d(&tmC, smem_u32(sa), c0, mt * BM);
+                    sb ^= 1u;
+                }
+            } else if (p.epi == EPI_F32 && p.tma_store) {
+                // fp32 tile (split-K partial of a weight gradient): 32 columns = 128 bytes per row and round
+                const uint32_t own = (uint32_t)(r * 128), key = (uint32_t)(r & 7);
                 int c0 = 32 * half;
                 uint32_t v[32];
                 if (c0 < p.n_valid) tmem_ld32(t_row + c0, v);
 #pragma unroll 1
                 for (; c0 < p.n_valid; c0 += 64) {
-                    uint32_t mw = 0u;                                    // ReLU mask word of (row, chunk): one coalesced word per lane
-                    if (p.epi == EPI_RELUBWD && row_ok) mw = __ldg(p.mask_in + (long long)(c0 >> 5) * p.ld_mask + m);
+                    uint8_t* sa = s_bm_h + sb * kStageBm;
+                    if (te == 0) tma_store_wait_read();
                     tmem_ld_wait();
-                    uint32_t pk[16];
-                    if (p.epi == EPI_BIAS_RELU) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
-                            const float z0 = __uint_as_float(v[4 * q]) + b4.x, z1 = __uint_as_float(v[4 * q + 1]) + b4.y;
-                            const float z2 = __uint_as_float(v[4 * q + 2]) + b4.z, z3 = __uint_as_float(v[4 * q + 3]) + b4.w;
-                            mw |= (z0 > 0.0f ? 1u : 0u) << (4 * q) | (z1 > 0.0f ? 2u : 0u) << (4 * q) | (z2 > 0.0f ? 4u : 0u) << (4 * q) | (z3 > 0.0f ? 8u : 0u) << (4 * q);
-                            pk[2 * q] = pack_bf16x2(fmaxf(z0, 0.0f), fmaxf(z1, 0.0f));
-                            pk[2 * q + 1] = pack_bf16x2(fmaxf(z2, 0.0f), fmaxf(z3, 0.0f));
-                        }
-                        if (p.mask_out && row_ok) p.mask_out[(long long)(c0 >> 5) * p.ld_mask + m] = mw;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            pk[i] = pack_bf16x2((mw >> (2 * i)) & 1u ? __uint_as_float(v[2 * i]) : 0.0f, (mw >> (2 * i + 1)) & 1u ? __uint_as_float(v[2 * i + 1]) : 0.0f);
-                    }
-                    if (c0 + 64 < p.n_valid) tmem_ld32(t_row + c0 + 64, v);   // the next chunk's accumulator columns fly under the staging + copy-out
-                    const int nv = min(32, p.n_valid - c0);               // multiple of 8
-                    uint8_t* sbm = s_bm_h + sb * kStageBm;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)                           // own row into the staging tile (16-byte pieces XOR-swizzled: conflict-free)
-                        *reinterpret_cast<uint4*>(sbm + r * 64 + ((q ^ ((r >> 1) & 3)) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<uint4*>(sa + own + (((uint32_t)q ^ key) << 4)) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    if (c0 + 64 < p.n_valid) tmem_ld32(t_row + c0 + 64, v);
+                    fence_async_smem();
                     epi_barrier(half);
-                    uint4 ob[4];                                          // all shared-memory reads first, then the stores
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) ob[q] = *reinterpret_cast<const uint4*>(sbm + q * (32 * 64) + bm_rd);
-                    if (full && nv == 32) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(bm_base + (long long)(q * 32) * p.ld_bm + c0) = ob[q];
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if ((long long)mt * BM + q * 32 + (te >> 2) < p.m && 8 * (te & 3) < nv)
-                                *reinterpret_cast<uint4*>(bm_base + (long long)(q * 32) * p.ld_bm + c0) = ob[q];
-                    }
+                    if (te == 0) tma_store_2d(&tmC, smem_u32(sa), c0, sp * p.m + mt * BM);
                     sb ^= 1u;
                 }
             } else {
@@ -345,6 +443,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             buf ^= 1u;
             if (buf == 0) acc_phase ^= 1u;
         }
+        if (te == 0) tma_store_wait_all();                                // the staging tiles must outlive the bulk stores reading them
     }
     tc_fence_before();
     __syncthreads();

@@ -83,6 +83,18 @@ static bool make_map(CUtensorMap* tm, const bf16* ptr, long long rows, long long
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// fp32 [rows][cols] output of the split-K GEMMs, stored tile by tile (32 columns x 128 rows) by the TMA store engine
+static bool make_map_f32(CUtensorMap* tm, const float* ptr, long long rows, long long cols, long long ld) {
+    EncodeTiledFn f = encode_fn();
+    if (!f) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    return f(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ---------------------------------------------------------------------------------------------- small kernels
 struct Hyper {
     float lr, clip, target_kl, max_grad, pi_coef, vf_coef, ent_coef, lipschitz;
@@ -111,6 +123,8 @@ __device__ __forceinline__ void gather_matrix(const float* src, long long src_st
     }
 }
 __global__ void __launch_bounds__(256) gather_kernel(const GatherParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (p.stop && *p.stop) return;
     __shared__ long long rows[32];
     const int i0 = blockIdx.x * 32;
@@ -145,6 +159,8 @@ struct LossParams {
     const int* stop;
 };
 __global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (p.stop && *p.stop) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float s_sur = 0.f, s_val = 0.f, s_kl = 0.f, dls[4] = {0.f, 0.f, 0.f, 0.f};
@@ -209,6 +225,8 @@ struct DecideParams {
     float* grad_log_std;                           // flat gradient slot of log_std
 };
 __global__ void decide_kernel(const DecideParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (*p.stop) return;
     const double w = (double)p.h.world, n = (double)p.B * w;           // under data parallelism acc holds the all-reduced sums
@@ -235,18 +253,20 @@ __global__ void decide_kernel(const DecideParams p) {
 // LSTM backward, point-wise part of one time step (the gate math of nn.LSTM): one thread per (sample, unit), lanes along the units
 struct LstmBwdParams {
     const float* dh; float* dc;                     // [B][64]: dL/dh_t (total), dL/dc_t carried from step t+1 (in) -> dL/dc_{t-1} (out)
-    const bf16* gates; const float* c_prev; const float* c_cur;     // [B][256] activated gates of step t, c_{t-1} (null: 0), c_t
+    const bf16* gates; const float* c_prev; const float* c_cur;     // [B][256] activated gates of step t (chunked layout), c_{t-1} (null: 0), c_t
     bf16* dg_bm;                                    // [B][256] gate pre-activation gradients of step t
     int B; int first;                               // first = this is the last time step (dc_in = 0)
     const int* stop;
 };
 __global__ void __launch_bounds__(256) lstm_bwd_kernel(const LstmBwdParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (p.stop && *p.stop) return;
     const int j = threadIdx.x & (kH - 1);
     const long long i = (long long)blockIdx.x * 4 + (threadIdx.x >> 6);
     if (i >= p.B) return;
-    const bf16* g = p.gates + i * kG;
-    const float gi = __bfloat162float(g[j]), gf = __bfloat162float(g[kH + j]), gg = __bfloat162float(g[2 * kH + j]), go = __bfloat162float(g[3 * kH + j]);
+    const bf16* g = p.gates + i * kG + (j >> 4) * 64 + (j & 15);     // [4 chunks][4 gates][16 units] (gemm_tc.cuh LstmEpi::gates_out)
+    const float gi = __bfloat162float(g[0]), gf = __bfloat162float(g[16]), gg = __bfloat162float(g[32]), go = __bfloat162float(g[48]);
     const float c = p.c_cur[i * kH + j], cp = p.c_prev ? p.c_prev[i * kH + j] : 0.0f;
     const float tc = tanhf(c);
     const float dh = p.dh[i * kH + j];
@@ -265,6 +285,8 @@ constexpr int kColRows = 512, kColLd = 256;
 struct ColSumSeg { const bf16* src; int ld; };      // [B][ld], ld a multiple of 16, <= 256
 struct ColSumParams { ColSumSeg seg[2 * (kMaxHiddenL + 1)]; int n_seg; int B; float* partial; const int* stop; };   // partial: [seg][chunk][kColLd]
 __global__ void __launch_bounds__(256) colsum_kernel(const ColSumParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (p.stop && *p.stop) return;
     __shared__ float2 part[256];
     const ColSumSeg sg = p.seg[blockIdx.y];
@@ -292,6 +314,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColSumParams p) {
 struct GradSeg { const float* partial; int splits; long long split_stride; int ld, col0, rows, cols; long long dst; };
 struct GradParams { GradSeg seg[32]; int n_seg; float* grad; double* acc; const int* stop; };
 __global__ void __launch_bounds__(256) grad_assemble_kernel(const GradParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (p.stop && *p.stop) return;
     long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (int s = 0; s < p.n_seg; ++s) {
@@ -309,6 +333,8 @@ __global__ void __launch_bounds__(256) grad_assemble_kernel(const GradParams p) 
     }
 }
 __global__ void __launch_bounds__(256) grad_norm_kernel(const float* grad, long long n, float inv_world, double* acc, const int* stop) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (stop && *stop) return;
     double s = 0.0;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
@@ -329,6 +355,8 @@ __global__ void __launch_bounds__(256) grad_norm_kernel(const float* grad, long 
 // clip_grad_norm_ (:244) + torch.optim.Adam (betas 0.9 / 0.999, eps 1e-5, :117): element-wise over the flat parameter vector
 __global__ void __launch_bounds__(256) adam_kernel(float* prm, float* m, float* v, const float* grad, long long n, Hyper h, int* step, double* acc,
                                                    float* log, const int* n_logged, int max_log, const int* stop) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (stop && *stop) return;
     const double norm = sqrt(acc[8]);
     const float coef = fminf((float)((double)h.max_grad / (norm + 1e-6)), 1.0f) / (float)h.world;     // the 1 / world averages the summed gradient
@@ -349,6 +377,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* prm, float* m, float* 
     }
 }
 __global__ void finish_step_kernel(int* step, double* acc, const int* stop) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (stop && *stop) return;
     *step += 1;
     acc[8] = 0.0;
@@ -359,6 +389,8 @@ __global__ void finish_step_kernel(int* step, double* acc, const int* stop) {
 struct SpecSeg { float* w; int rows, cols; float* v; double* sigma; };
 struct SpecParams { SpecSeg seg[kMaxHiddenL + 1]; int n_seg; float lipschitz; int max_iter; const int* stop; };
 __global__ void __launch_bounds__(512) spectral_kernel(const SpecParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (p.stop && *p.stop) return;
     const SpecSeg& S = p.seg[blockIdx.x];
     __shared__ float v[256], u[256], part[2][256];
@@ -433,6 +465,8 @@ __global__ void __launch_bounds__(512) spectral_kernel(const SpecParams p) {
 struct PackSeg { const float* w; int out, in; bf16* wb; int ld_w; bf16* wt; int ld_t; int rows_t; };
 struct PackParams { PackSeg seg[2 * (kMaxHiddenL + 1)]; int n_seg; const int* stop; };
 __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (p.stop && *p.stop) return;
     const PackSeg& S = p.seg[blockIdx.y];
     const long long nw = (long long)S.out * S.ld_w, ntr = (long long)S.rows_t * S.ld_t;
@@ -450,6 +484,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackParams p) {
 // LSTM: Wcat [256][96] = [W_hh | W_ih | b_hi b_lo | 0] and W_hh^T [64][256]
 __global__ void __launch_bounds__(256) pack_lstm_kernel(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int in_dim, int ld_u,
                                                         bf16* wcat, bf16* whh_t, const int* stop) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (stop && *stop) return;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < kG * ld_u + kH * kG; e += gridDim.x * blockDim.x) {
         if (e < kG * ld_u) {
@@ -491,6 +527,7 @@ struct MlpNet {
     // K-major maps (forward / dX GEMMs) and MN-major maps of the same batch-major tensors (dW = dZ^T X reads both transposed)
     CUtensorMap m_x_bm[kMaxHiddenL + 1], m_x_mn[kMaxHiddenL + 1], m_w[kMaxHiddenL + 1], m_wt[kMaxHiddenL + 1];
     CUtensorMap m_dz_bm[kMaxHiddenL + 2], m_dz_mn[kMaxHiddenL + 2];
+    CUtensorMap m_partial[kMaxHiddenL + 1]; bool partial_tma[kMaxHiddenL + 1];   // split-K partials as [splits * out][ld_p] fp32 (TMA-stored when out % 128 == 0)
 };
 
 struct TacoPPO {
@@ -505,7 +542,7 @@ struct TacoPPO {
     bf16 *wcat = nullptr, *whh_t = nullptr, *u_bm = nullptr, *gates = nullptr, *dg_bm = nullptr;     // dg_bm: [seq*B][256], all time steps
     float *c_state = nullptr, *dh = nullptr, *dc = nullptr, *lstm_partial = nullptr, *colsum_partial = nullptr;
     int lstm_splits = 1;
-    CUtensorMap m_u_bm, m_u_mn, m_wcat, m_whh_t, m_dg_bm, m_dg_mn;
+    CUtensorMap m_u_bm, m_u_mn, m_wcat, m_whh_t, m_dg_bm, m_dg_mn, m_lstm_partial, m_dh;
     // heads / side arrays
     float *mean = nullptr, *value = nullptr, *g_act = nullptr, *g_logp = nullptr, *g_adv = nullptr, *g_ret = nullptr;
     // bookkeeping
@@ -529,7 +566,22 @@ static cudaError_t dev_alloc(TacoPPO* t, T** p, size_t count) {
     return e;
 }
 
-static int launch_gemm(TacoPPO* t, const CUtensorMap& a, const CUtensorMap& b, GemmParams p, cudaStream_t s) {
+// launch with programmatic stream serialization: the kernel may be scheduled while its predecessor in the stream drains; every
+// kernel launched this way starts with pdl_wait() (gemm_tc.cuh)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    TACO_LAUNCHED();
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// c: tensor map of the output when the epilogue stores through TMA (p.tma_store is set from it)
+static int launch_gemm(TacoPPO* t, const CUtensorMap& a, const CUtensorMap& b, GemmParams p, cudaStream_t s, const CUtensorMap* c = nullptr) {
     const int kb_total = (p.k + BK - 1) / BK;
     if (p.splits < 1) p.splits = 1;
     if (p.splits > kb_total) p.splits = kb_total;
@@ -538,8 +590,8 @@ static int launch_gemm(TacoPPO* t, const CUtensorMap& a, const CUtensorMap& b, G
     p.stop = t->stop;
     const int total = ((p.m + BM - 1) / BM) * p.splits;
     const int grid = total < t->num_sms ? total : t->num_sms;
-    gemm_tc_kernel<<<grid, kGemmThreads, kGemmSmem, s>>>(a, b, p); TACO_LAUNCHED();
-    return cudaGetLastError() == cudaSuccess ? TACO_OK : ppo_fail(TACO_E_CUDA, "gemm_tc_kernel launch failed");
+    p.tma_store = c != nullptr;
+    return launch_pdl(gemm_tc_kernel, dim3(grid), dim3(kGemmThreads), kGemmSmem, s, a, b, c ? *c : a, p) == cudaSuccess ? TACO_OK : ppo_fail(TACO_E_CUDA, "gemm_tc_kernel launch failed");
 }
 
 static int splits_for(int m, long long k, int num_sms) {
@@ -576,6 +628,8 @@ static int setup_net(TacoPPO* t, MlpNet& n, long long& off, bool actor) {
         ok = ok && make_map(&n.m_wt[l], n.wt[l], in, pad8(out) < 16 ? 16 : out, n.ld_t[l], pad16(in));   // B operand of the dX GEMM
         ok = ok && make_map(&n.m_dz_bm[lz], n.dz_bm[lz], B, n.ld_dz[lz], n.ld_dz[lz], BM);   // A operand of the dX GEMM
         ok = ok && make_map(&n.m_dz_mn[lz], n.dz_bm[lz], B, n.ld_dz[lz], n.ld_dz[lz], BK);   // A operand of the dW GEMM (MN-major)
+        n.partial_tma[l] = out % BM == 0;
+        if (n.partial_tma[l]) ok = ok && make_map_f32(&n.m_partial[l], n.partial[l], (long long)n.splits[l] * out, n.ld_p[l], n.ld_p[l]);
         if (!ok) return ppo_fail(TACO_E_CUDA, "cuTensorMapEncodeTiled failed");
     }
     (void)actor;
@@ -675,6 +729,8 @@ int taco_ppo_create(int device, const TacoPPOCfg* cfg, TacoPPO** out) {
     ok = ok && make_map(&t->m_whh_t, t->whh_t, kH, kG, kG, kH);
     ok = ok && make_map(&t->m_dg_bm, t->dg_bm, SB, kG, kG, BM);
     ok = ok && make_map(&t->m_dg_mn, t->dg_bm, SB, kG, kG, BK);
+    ok = ok && make_map_f32(&t->m_lstm_partial, t->lstm_partial, (long long)t->lstm_splits * kG, t->ld_u, t->ld_u);
+    ok = ok && make_map_f32(&t->m_dh, t->dh, B, kH, kH);
     if (!ok) return bail(TACO_E_CUDA, "taco_ppo_create: cuTensorMapEncodeTiled failed");
     if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem) != cudaSuccess)
         return bail(TACO_E_CUDA, "taco_ppo_create: cudaFuncSetAttribute failed");
@@ -752,10 +808,10 @@ static int repack(TacoPPO* t, cudaStream_t s, bool honour_stop, int which = 0) {
         }
     }
     pp.stop = honour_stop ? t->stop : nullptr;
-    pack_kernel<<<dim3(32, pp.n_seg), 256, 0, s>>>(pp); TACO_LAUNCHED();
+    launch_pdl(pack_kernel, dim3(32, pp.n_seg), dim3(256), 0, s, pp);
     if (which != 1) {
-        pack_lstm_kernel<<<64, 256, 0, s>>>(t->prm + t->off_wih, t->prm + t->off_whh, t->prm + t->off_bih, t->prm + t->off_bhh, t->sd, t->ld_u, t->wcat,
-                                            t->whh_t, honour_stop ? t->stop : nullptr); TACO_LAUNCHED();
+        launch_pdl(pack_lstm_kernel, dim3(64), dim3(256), 0, s, (const float*)(t->prm + t->off_wih), (const float*)(t->prm + t->off_whh), (const float*)(t->prm + t->off_bih),
+                   (const float*)(t->prm + t->off_bhh), t->sd, t->ld_u, t->wcat, t->whh_t, (const int*)(honour_stop ? t->stop : nullptr));
     }
     return cudaGetLastError() == cudaSuccess ? TACO_OK : ppo_fail(TACO_E_CUDA, "pack kernels failed");
 }
@@ -795,14 +851,13 @@ static int mlp_forward(TacoPPO* t, MlpNet& n, bool actor, cudaStream_t s) {
         p.bias = t->prm + n.b_off[l];
         if (l + 1 < n.L) {
             p.epi = EPI_BIAS_RELU; p.n_valid = pad8(n.s[l + 1]);
-            p.out_bm = n.x_bm[l + 1]; p.ld_bm = n.ld_x[l + 1];
             p.mask_out = n.relu_mask[l + 1]; p.ld_mask = t->B;
         } else if (actor) {
             p.epi = EPI_TANH_F32; p.n_valid = t->A; p.out_f32 = t->mean; p.ldc = t->A;
         } else {
             p.epi = EPI_F32; p.n_valid = 1; p.out_f32 = t->value; p.ldc = 1;
         }
-        const int rc = launch_gemm(t, n.m_x_bm[l], n.m_w[l], p, s);
+        const int rc = launch_gemm(t, n.m_x_bm[l], n.m_w[l], p, s, l + 1 < n.L ? &n.m_x_bm[l + 1] : nullptr);   // X_{l+1} leaves through its own (operand) map
         if (rc != TACO_OK) return rc;
     }
     return TACO_OK;
@@ -819,7 +874,7 @@ static int mlp_backward(TacoPPO* t, MlpNet& n, float* dx_out, cudaStream_t s) {
             p.epi = EPI_F32; p.n_valid = pad16(in);
             p.out_f32 = n.partial[l]; p.ldc = n.ld_p[l]; p.split_stride = (long long)out * n.ld_p[l];
             p.mn_major = 1;
-            const int rc = launch_gemm(t, n.m_dz_mn[lz], n.m_x_mn[l], p, s);
+            const int rc = launch_gemm(t, n.m_dz_mn[lz], n.m_x_mn[l], p, s, n.partial_tma[l] ? &n.m_partial[l] : nullptr);
             if (rc != TACO_OK) return rc;
         }
         if (l > 0 || dx_out) {   // dX_{l-1} = dZ W_l: M = batch, N = in, K = out
@@ -829,11 +884,10 @@ static int mlp_backward(TacoPPO* t, MlpNet& n, float* dx_out, cudaStream_t s) {
             if (l > 0) {
                 p.epi = EPI_RELUBWD; p.n_valid = pad8(in);
                 p.mask_in = n.relu_mask[l]; p.ld_mask = t->B;
-                p.out_bm = n.dz_bm[l]; p.ld_bm = n.ld_dz[l];
             } else {
                 p.epi = EPI_F32; p.n_valid = in; p.out_f32 = dx_out; p.ldc = in;
             }
-            const int rc = launch_gemm(t, n.m_dz_bm[lz], n.m_wt[l], p, s);
+            const int rc = launch_gemm(t, n.m_dz_bm[lz], n.m_wt[l], p, s, l > 0 ? &n.m_dz_bm[l] : (dx_out == t->dh ? &t->m_dh : nullptr));
             if (rc != TACO_OK) return rc;
         }
     }
@@ -854,7 +908,7 @@ int taco_ppo_forward_loss(TacoPPO* t, const TacoPPOHyper* hyper, const float* ob
     g.x0_bm = t->actor.x_bm[0]; g.ld_x0 = t->actor.ld_x[0];
     g.u_bm = t->u_bm; g.ld_u = t->ld_u;
     g.g_act = t->g_act; g.g_logp = t->g_logp; g.g_adv = t->g_adv; g.g_ret = t->g_ret; g.stop = t->stop;
-    gather_kernel<<<(B + 31) / 32, 256, 0, s>>>(g); TACO_LAUNCHED();
+    launch_pdl(gather_kernel, dim3((B + 31) / 32), dim3(256), 0, s, g);
     int rc = TACO_OK;
     // critic first: seq LSTM steps, each one GEMM [h_{t-1} | x_t | 1 1] Wcat^T with the gate math in the epilogue, then its MLP.  The
     // previous optimiser step's projection + re-pack of the ACTOR may still be running on the side stream under these launches.
@@ -886,7 +940,7 @@ int taco_ppo_forward_loss(TacoPPO* t, const TacoPPOHyper* hyper, const float* ob
     L.dz_bm = t->actor.dz_bm[t->actor.L];
     L.dv_bm = t->critic.dz_bm[t->critic.L];
     L.acc = t->acc; L.stop = t->stop;
-    loss_kernel<<<(B + 255) / 256, 256, 0, s>>>(L); TACO_LAUNCHED();
+    launch_pdl(loss_kernel, dim3((B + 255) / 256), dim3(256), 0, s, L);
     PPO_CUDA(cudaGetLastError());
     return TACO_OK;
 }
@@ -908,7 +962,7 @@ int taco_ppo_decide(TacoPPO* t, const TacoPPOHyper* hyper, void* stream) {
     d.acc = t->acc; d.log = t->log; d.n_logged = t->n_logged; d.stop = t->stop; d.max_log = t->max_log;
     d.log_std = t->prm + t->off_log_std; d.act_dim = t->A; d.B = t->B; d.h = to_hyper(hyper);
     d.grad_log_std = t->grad + t->off_log_std;
-    decide_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d); TACO_LAUNCHED();
+    launch_pdl(decide_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, d);
     PPO_CUDA(cudaGetLastError());
     return TACO_OK;
 }
@@ -930,12 +984,12 @@ int taco_ppo_backward(TacoPPO* t, void* stream) {
         b.dh = t->dh; b.dc = t->dc; b.gates = t->gates + (size_t)k * B * kG;
         b.c_prev = k > 0 ? t->c_state + (size_t)(k - 1) * B * kH : nullptr; b.c_cur = t->c_state + (size_t)k * B * kH;
         b.dg_bm = t->dg_bm + (size_t)k * B * kG; b.B = B; b.first = (k == t->seq - 1); b.stop = t->stop;
-        lstm_bwd_kernel<<<(B + 3) / 4, 256, 0, s>>>(b); TACO_LAUNCHED();
+        launch_pdl(lstm_bwd_kernel, dim3((B + 3) / 4), dim3(256), 0, s, b);
         if (k > 0) {   // dh_{t-1} = dgates_t W_hh: M = batch, N = 64, K = 256
             GemmParams p;
             memset(&p, 0, sizeof(p));
             p.m = B; p.n = kH; p.k = kG; p.n_tile = kH; p.splits = 1; p.a_row0 = k * B; p.epi = EPI_F32; p.n_valid = kH; p.out_f32 = t->dh; p.ldc = kH;
-            rc = launch_gemm(t, t->m_dg_bm, t->m_whh_t, p, s);
+            rc = launch_gemm(t, t->m_dg_bm, t->m_whh_t, p, s, &t->m_dh);
             if (rc != TACO_OK) return rc;
         }
     }
@@ -946,7 +1000,7 @@ int taco_ppo_backward(TacoPPO* t, void* stream) {
         p.out_f32 = t->lstm_partial; p.ldc = t->ld_u; p.split_stride = (long long)kG * t->ld_u;
         if (p.n_valid > t->ld_u) p.n_valid = t->ld_u;
         p.mn_major = 1;
-        rc = launch_gemm(t, t->m_dg_mn, t->m_u_mn, p, s);
+        rc = launch_gemm(t, t->m_dg_mn, t->m_u_mn, p, s, &t->m_lstm_partial);
         if (rc != TACO_OK) return rc;
     }
     // bias gradients = column sums of the batch-major dZ: partial rows here, summed by the assembly kernel below
@@ -961,7 +1015,7 @@ int taco_ppo_backward(TacoPPO* t, void* stream) {
         }
     }
     cs.B = B; cs.partial = t->colsum_partial; cs.stop = t->stop;
-    colsum_kernel<<<dim3(col_chunks, cs.n_seg), 256, 0, s>>>(cs); TACO_LAUNCHED();
+    launch_pdl(colsum_kernel, dim3(col_chunks, cs.n_seg), dim3(256), 0, s, cs);
     // weight gradients from the split-K partials
     GradParams gp;
     memset(&gp, 0, sizeof(gp));
@@ -995,7 +1049,7 @@ int taco_ppo_backward(TacoPPO* t, void* stream) {
         add(t->lstm_partial, sp, stride, t->ld_u, kH + t->sd, kG, 1, t->off_bhh);
     }
     gp.grad = t->grad; gp.acc = t->acc; gp.stop = t->stop;
-    grad_assemble_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, s>>>(gp); TACO_LAUNCHED();
+    launch_pdl(grad_assemble_kernel, dim3((unsigned)((elems + 255) / 256)), dim3(256), 0, s, gp);
     PPO_CUDA(cudaGetLastError());
     return TACO_OK;
 }
@@ -1006,9 +1060,10 @@ int taco_ppo_apply(TacoPPO* t, const TacoPPOHyper* hyper, void* stream) {
     DevGuard guard(t->device);
     cudaStream_t s = (cudaStream_t)stream;
     const Hyper h = to_hyper(hyper);
-    grad_norm_kernel<<<64, 256, 0, s>>>(t->grad, t->n_params, 1.0f / (float)h.world, t->acc, t->stop); TACO_LAUNCHED();
-    adam_kernel<<<t->num_sms, 256, 0, s>>>(t->prm, t->adam_m, t->adam_v, t->grad, t->n_params, h, t->step, t->acc, t->log, t->n_logged, t->max_log, t->stop); TACO_LAUNCHED();
-    finish_step_kernel<<<1, 1, 0, s>>>(t->step, t->acc, t->stop); TACO_LAUNCHED();
+    launch_pdl(grad_norm_kernel, dim3(64), dim3(256), 0, s, (const float*)t->grad, t->n_params, 1.0f / (float)h.world, t->acc, (const int*)t->stop);
+    launch_pdl(adam_kernel, dim3(t->num_sms), dim3(256), 0, s, t->prm, t->adam_m, t->adam_v, (const float*)t->grad, t->n_params, h, t->step, t->acc, t->log, (const int*)t->n_logged,
+               t->max_log, (const int*)t->stop);
+    launch_pdl(finish_step_kernel, dim3(1), dim3(1), 0, s, t->step, t->acc, (const int*)t->stop);
     if (h.use_lipschitz) {
         SpecParams sp;
         memset(&sp, 0, sizeof(sp));
@@ -1101,7 +1156,10 @@ static int gemm_selftest_impl(int device, const void* a_bf16, const void* b_bf16
     cudaDeviceProp prop;
     PPO_CUDA(cudaGetDeviceProperties(&prop, device));
     const int total = ((m + BM - 1) / BM) * sp;
-    gemm_tc_kernel<<<total < prop.multiProcessorCount ? total : prop.multiProcessorCount, kGemmThreads, kGemmSmem, s>>>(ma, mb, p); TACO_LAUNCHED();
+    CUtensorMap mc = ma;
+    p.tma_store = (m % BM == 0 && n % 4 == 0) ? 1 : 0;      // exercise the TMA-store epilogue where its shape rule holds
+    if (p.tma_store && !make_map_f32(&mc, part, (long long)sp * m, n, n)) return ppo_fail(TACO_E_CUDA, "tensor map");
+    gemm_tc_kernel<<<total < prop.multiProcessorCount ? total : prop.multiProcessorCount, kGemmThreads, kGemmSmem, s>>>(ma, mb, mc, p); TACO_LAUNCHED();
     GradParams gp;
     memset(&gp, 0, sizeof(gp));
     gp.n_seg = 1;
