@@ -1149,6 +1149,9 @@ static int gemm_selftest_impl(int device, const void* a_bf16, const void* b_bf16
     sp = (kb_total + per - 1) / per;
     float* part = nullptr;
     PPO_CUDA(cudaMalloc(&part, (size_t)sp * m * n * sizeof(float)));
+    // (compute-sanitizer's initcheck does not observe writes made by cp.async.bulk.tensor stores: without this the partials the
+    // TMA-store epilogue writes read as uninitialised in the assembly kernel below)
+    PPO_CUDA(cudaMemsetAsync(part, 0, (size_t)sp * m * n * sizeof(float), s));
     GemmParams p;
     memset(&p, 0, sizeof(p));
     p.m = m; p.n = n; p.k = k; p.n_tile = pad16(n); p.splits = sp; p.kb_per_split = per; p.epi = EPI_F32; p.n_valid = n; p.mn_major = mn ? 1 : 0;

@@ -76,6 +76,10 @@ def ppo_part():
         a = (torch.randn(m, k, device="cuda") * 0.5).bfloat16()
         b = (torch.randn(n, k, device="cuda") * 0.5).bfloat16()
         gemm_selftest(a, b, sp)
+    for (m, n, k, sp) in ((256, 64, 1024, 3), (48, 256, 640, 2)):          # transposed (MN-major) operands; the first shape stores through TMA
+        at = (torch.randn(k, m, device="cuda") * 0.5).bfloat16()
+        bt = (torch.randn(k, n, device="cuda") * 0.5).bfloat16()
+        gemm_selftest(at, bt, sp, transposed=True)
     agent = TorchActorCritic(26, 4, [64, 48], 26, 64, [32]).cuda()
     H, N = 4, 128
     g = torch.Generator(device="cuda").manual_seed(0)
