@@ -55,10 +55,40 @@ __device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
 }
 
 // TU:175-196 get_euler_xyz_v1, roll component (the only one the hot path consumes)
+// atan2 for finite arguments in ~23 instructions (libdevice's atan2f: ~43): t = min / max of the magnitudes by a reciprocal and
+// one Newton correction, atan(t) on [0, 1] as an odd degree-17 minimax polynomial (8 coefficients in t^2, FMA Horner), then the
+// octant fix-ups.  Max error 2.4 ulp over 4 M random arguments (tools/atan2_poly_check.py; numpy's float32 arctan2: 3.3 ulp on
+// the same set, libdevice documents 2 ulp) -- the same accuracy class as the function it replaces; atan2(0, 0) = 0 like libm.
+// The flip task evaluates the roll angle 11 times per RL step (refresh_state in every control iteration, fpv_asymmetry.py:334-360).
+__device__ __forceinline__ float atan2_poly(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(fmaxf(ax, ay), 1e-30f), mn = fminf(ax, ay);
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
+    float t = mn * rc;
+    t = __fmaf_rn(__fmaf_rn(-mx, t, mn), rc, t);
+    const float s = t * t;
+    float p = 0.00282363896258175373077393f;
+    p = __fmaf_rn(p, s, -0.0159569028764963150024414f);
+    p = __fmaf_rn(p, s, 0.0425049886107444763183594f);
+    p = __fmaf_rn(p, s, -0.0748900920152664184570312f);
+    p = __fmaf_rn(p, s, 0.106347933411598205566406f);
+    p = __fmaf_rn(p, s, -0.142027363181114196777344f);
+    p = __fmaf_rn(p, s, 0.199926957488059997558594f);
+    p = __fmaf_rn(p, s, -0.333331018686294555664062f);
+    float r = __fmaf_rn(p * s, t, t);
+    if (ay > ax) r = kHalfPi - r;
+    if (x < 0.0f) r = kPi - r;
+    return copysignf(r, y);
+}
 __device__ __forceinline__ float roll_of(Q4 q) {
     const float sinr = 2.0f * (q.w * q.x + q.y * q.z);
     const float cosr = q.w * q.w - q.x * q.x - q.y * q.y + q.z * q.z;
+#ifdef TACO_ATAN2_LIBM                  // tuning / A-B builds only: libdevice's atan2f (5 % slower flip step, profiles/README.md)
     return atan2f(sinr, cosr);
+#else
+    return atan2_poly(sinr, cosr);
+#endif
 }
 
 // sin/cos for |x| <= pi/2 by Horner evaluation of the degree-13/14 Taylor polynomials (oracle/leaf_math.py

@@ -23,7 +23,7 @@
 #include "../../include/taco_b200.h"
 
 #ifndef TACO_MIN_BLOCKS
-#define TACO_MIN_BLOCKS 6     // resident CTAs per SM the register allocation targets: 80 regs, 24 warps/SM (measured best of 4/5/6/8)
+#define TACO_MIN_BLOCKS 6     // resident CTAs per SM the register allocation targets: 80 regs, 24 warps/SM (measured best of 4/5/6/7/8)
 #endif
 #ifndef TACO_VARIANT
 #error "define TACO_VARIANT (fast / strict) before including fpv_step_kernel.cuh"
@@ -81,11 +81,52 @@ __device__ __forceinline__ void write_rows_impl(const float* __restrict__ in, fl
         if (FULL || e < nv) out2[e * row2 + keep2 + j] = make_float2(fr[0], fr[1]);
     }
 }
+// The same copy for a full CTA and a compile-time L, with no index arithmetic in the instruction stream: warp w owns the 32
+// consecutive rows [32 w, 32 w + 32) and its lanes run ALONG a row, so every load / store is `base + immediate` (the row and
+// column offsets are compile-time constants of the unrolled loops).  Kept part: lanes 0..31 and 32..keep2-1 of each row;
+// newest frame: two rows per store instruction (13 float2 each, lanes 26..31 idle).  Same bytes touched as the generic walk,
+// a third of its instructions (8 per element there: division by keep2, address, bounds predicate).
+template <int LC>
+__device__ __forceinline__ void write_rows_full(const float* __restrict__ in, float* __restrict__ out, const float* frames,
+                                                size_t blk_env0, int tid) {
+    constexpr int row2 = 13 * LC, keep2 = 13 * (LC - 1);
+    constexpr int NJ = (keep2 + 31) / 32;                       // column chunks of 32 lanes per row
+    constexpr int NJ1 = NJ > 0 ? NJ : 1;
+    constexpr int EB = NJ1 <= 2 ? 8 : (NJ1 <= 4 ? 4 : 2);       // rows per batch: <= 16 loads in flight per thread
+    const int w = tid >> 5, lane = tid & 31;
+    const float2* src = reinterpret_cast<const float2*>(in) + (blk_env0 + 32 * w) * row2 + 13 + lane;
+    float2* dst = reinterpret_cast<float2*>(out) + (blk_env0 + 32 * w) * row2 + lane;
+    if (keep2 > 0) {
+#pragma unroll
+        for (int e0 = 0; e0 < 32; e0 += EB) {
+            float2 v[EB][NJ1];
+#pragma unroll
+            for (int e = 0; e < EB; ++e)
+#pragma unroll
+                for (int c = 0; c < NJ; ++c)
+                    if ((c + 1) * 32 <= keep2 || c * 32 + lane < keep2) v[e][c] = __ldg(src + (e0 + e) * row2 + c * 32);
+#pragma unroll
+            for (int e = 0; e < EB; ++e)
+#pragma unroll
+                for (int c = 0; c < NJ; ++c)
+                    if ((c + 1) * 32 <= keep2 || c * 32 + lane < keep2) dst[(e0 + e) * row2 + c * 32] = v[e][c];
+        }
+    }
+    if (lane < 26) {
+        const int sub = lane >= 13 ? 1 : 0, j = lane - 13 * sub;
+        const float* fr = frames + (32 * w + sub) * kFramePad + 2 * j;
+        float2* d = dst - lane + sub * row2 + keep2 + j;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) d[e * row2] = make_float2(fr[e * kFramePad], fr[e * kFramePad + 1]);
+    }
+}
 template <int LC>
 __device__ __forceinline__ void write_rows(const float* __restrict__ in, float* __restrict__ out, const float* frames,
                                            int L_rt, size_t blk_env0, int tid, int nv) {
-    if (nv == kBlock) write_rows_impl<LC, true>(in, out, frames, L_rt, blk_env0, tid, nv);     // every CTA but (at most) the last
-    else write_rows_impl<LC, false>(in, out, frames, L_rt, blk_env0, tid, nv);
+    if (nv == kBlock) {                                                                        // every CTA but (at most) the last
+        if constexpr (LC > 0) write_rows_full<LC>(in, out, frames, blk_env0, tid);
+        else write_rows_impl<LC, true>(in, out, frames, L_rt, blk_env0, tid, nv);
+    } else write_rows_impl<LC, false>(in, out, frames, L_rt, blk_env0, tid, nv);
 }
 
 // TASK: task_mode (mix = per-env task from the global env id).  DR: per-env randomised model parameters live in the
@@ -622,15 +663,27 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
         for (int j = 0; j < 26; ++j) { fc[j] = 0.f; fn[j] = 0.f; }
     }
 
-    // ---------------------------------------------------------------------- rollout statistics: warp shuffle -> smem -> 1 atomic / block / stat
+    // ---------------------------------------------------------------------- rollout statistics: warp reduction -> smem -> 1 atomic / block / stat
+    // (the 0 / 1 flags as a ballot + popc, the episode lengths as an integer redux: 2 instructions each instead of a 10-instruction
+    // shuffle tree; the two float sums keep their butterfly order, so every statistic has the value it had)
     {
-        float sv[7] = {st_rew, st_done, st_tout, st_epret, st_eplen, st_nonfin, st_ovf};
+        float sv[2] = {st_rew, st_epret};
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-            float v = sv[j];
+        for (int j = 0; j < 2; ++j) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((tid & 31) == 0 && v != 0.f) atomicAdd(&s_stats[j], (double)v);
+            for (int o = 16; o > 0; o >>= 1) sv[j] += __shfl_xor_sync(0xffffffffu, sv[j], o);
+        }
+        const uint32_t b_done = __ballot_sync(0xffffffffu, st_done != 0.f), b_tout = __ballot_sync(0xffffffffu, st_tout != 0.f);
+        const uint32_t b_nonfin = __ballot_sync(0xffffffffu, st_nonfin != 0.f), b_ovf = __ballot_sync(0xffffffffu, st_ovf != 0.f);
+        const int len_sum = __reduce_add_sync(0xffffffffu, (int)st_eplen);       // episode lengths are integers <= max_len
+        if ((tid & 31) == 0) {
+            if (sv[0] != 0.f) atomicAdd(&s_stats[0], (double)sv[0]);
+            if (b_done) atomicAdd(&s_stats[1], (double)__popc(b_done));
+            if (b_tout) atomicAdd(&s_stats[2], (double)__popc(b_tout));
+            if (sv[1] != 0.f) atomicAdd(&s_stats[3], (double)sv[1]);
+            if (len_sum) atomicAdd(&s_stats[4], (double)len_sum);
+            if (b_nonfin) atomicAdd(&s_stats[5], (double)__popc(b_nonfin));
+            if (b_ovf) atomicAdd(&s_stats[6], (double)__popc(b_ovf));
         }
     }
     __syncthreads();   // frames + stats visible
