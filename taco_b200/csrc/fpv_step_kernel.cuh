@@ -25,6 +25,9 @@
 #ifndef TACO_MIN_BLOCKS
 #define TACO_MIN_BLOCKS 6     // resident CTAs per SM the register allocation targets: 80 regs, 24 warps/SM (measured best of 4/5/6/7/8)
 #endif
+#ifndef TACO_MIN_BLOCKS_DR
+#define TACO_MIN_BLOCKS_DR 5  // the DR variants keep 14 more per-env model parameters live through the control loop: 96 regs, 20 warps/SM (mix + DR: -2 %, profiles/ab_r02w.txt)
+#endif
 #ifndef TACO_VARIANT
 #error "define TACO_VARIANT (fast / strict) before including fpv_step_kernel.cuh"
 #endif
@@ -64,7 +67,7 @@ __device__ __forceinline__ void write_rows_impl(const float* __restrict__ in, fl
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int k = k0 + u * kBlock;
-                const int e = k / keep2, j = k - e * keep2;
+                const int e = k / (keep2 > 0 ? keep2 : 1), j = k - e * keep2;
                 dst[u] = e * row2 + j;
                 v[u] = (k < total) ? __ldg(in2 + dst[u] + 13) : make_float2(0.f, 0.f);
             }
@@ -134,9 +137,9 @@ __device__ __forceinline__ void write_rows(const float* __restrict__ in, float* 
 // SUB: physics sub-steps per simulate call (1 / 2 unrolled; 0 = runtime p.substeps).
 // DEVDIFF: graph-mode variant (difficulty scalars from device memory; costs two spilled registers, so eager launches do not use it).
 template <int TASK, bool DR, int SUB, bool DEVDIFF = false>
-__global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const StepParams p) {
-    __shared__ float s_clean[kBlock * kFramePad];
-    __shared__ float s_noisy[kBlock * kFramePad];
+__global__ void __launch_bounds__(kBlock, DR ? TACO_MIN_BLOCKS_DR : TACO_MIN_BLOCKS) fpv_step_kernel(const StepParams p) {
+    __shared__ __align__(16) float s_clean[kBlock * kFramePad];
+    __shared__ __align__(16) float s_noisy[kBlock * kFramePad];
     __shared__ double s_stats[kNumStats];
 
     const int tid = threadIdx.x;
@@ -151,6 +154,8 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
     float st_rew = 0.f, st_done = 0.f, st_tout = 0.f, st_epret = 0.f, st_eplen = 0.f, st_nonfin = 0.f, st_ovf = 0.f;
     float* fc = s_clean + tid * kFramePad;
     float* fn = s_noisy + tid * kFramePad;
+
+    const uint32_t vmask = __ballot_sync(0xffffffffu, valid);  // only the last CTA of a ragged shard has partial warps
 
     if (valid) {
         // ------------------------------------------------------------------ load
@@ -206,14 +211,39 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
         int q_len = (int)((qm >> QM_LEN_SHIFT) & 2047u);
         uint32_t q_ovf = (qm >> QM_OVF_SHIFT) & 1u;
 
+        // ------------------------------------------------------------------ reset draws, generated by the WARP for its resetting envs
+        // In steady state ~1 % of the envs reset per step, i.e. ~29 % of the warps hold one or two resetting lanes, and such a warp
+        // used to run the whole draw sequence (6 .. 11 Philox blocks, ~90 instructions each) for those lanes alone.  Here the lanes
+        // of the warp compute the blocks side by side instead -- lanes 0..15 the blocks of the first resetting env, lanes 16..31 those
+        // of the second (block c = lane & 15: reset stream blocks 0..9, block 10 = the command stream's block 0) -- and post them in a
+        // mailbox in the warp's own rows of s_clean (not written before the frame at the end of the step; no other warp touches
+        // them before the CTA barrier).  The resetting lane reads the blocks where the sequential code computed them: same counters,
+        // same keys, same words.  Warps with 3+ resetting lanes (the first step, synchronised time-outs) and partial warps keep the
+        // per-lane path.
+        bool coop = false;
+        const uint4* mbox = reinterpret_cast<const uint4*>(s_clean + (tid & ~31) * kFramePad);
+        if (vmask == 0xffffffffu) {
+            const uint32_t rmask = __ballot_sync(0xffffffffu, R);
+            const int nres = __popc(rmask);
+            if (nres == 1 || nres == 2) {
+                const int lane = tid & 31, first = __ffs(rmask) - 1, last = 31 - __clz(rmask);
+                const uint32_t gs = __shfl_sync(0xffffffffu, g, (lane & 16) ? last : first);
+                const uint32_t c = (uint32_t)(lane & 15);
+                if (c <= 10u) {
+                    const uint4 blk4 = philox4x32_10(gs, t_rl, c < 10u ? c : 0u, c < 10u ? (uint32_t)STREAM_RESET : (uint32_t)STREAM_COMMAND, k0, k1);
+                    const_cast<uint4*>(mbox)[lane] = blk4;
+                }
+                __syncwarp();
+                coop = true;
+                if (nres == 2 && lane == last) mbox += 16;
+            }
+        }
+        auto reset_block = [&](uint32_t c) -> uint4 { return coop ? mbox[c] : philox4x32_10(g, t_rl, c, STREAM_RESET, k0, k1); };
+
         // ------------------------------------------------------------------ lazy reset (fpv_asymmetry.py:475-517)
         if (R) {
             const float d = TACO_DIFF(difficulty, 0);          // read where it is used: no register held across the step
-            const uint4 b0 = philox4x32_10(g, t_rl, 0, STREAM_RESET, k0, k1);
-            const uint4 b1 = philox4x32_10(g, t_rl, 1, STREAM_RESET, k0, k1);
-            const uint4 b2 = philox4x32_10(g, t_rl, 2, STREAM_RESET, k0, k1);
-            const uint4 b3 = philox4x32_10(g, t_rl, 3, STREAM_RESET, k0, k1);
-            const uint4 b4 = philox4x32_10(g, t_rl, 4, STREAM_RESET, k0, k1);
+            const uint4 b0 = reset_block(0), b1 = reset_block(1), b2 = reset_block(2), b3 = reset_block(3), b4 = reset_block(4);
             const bool flip_env = (task == TACO_TASK_FLIP);
             // copter position (:730-737, :788-793, :855-861, :993-1036)
             if (flags & TACO_F_RANDOM_COPTER_POS) {
@@ -260,10 +290,7 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
             bu1 = 0.f; bt = 0.f;
             bec = (flags & TACO_F_RANDOM_VOLTAGE) ? rr(2.2f, 0.0f, u01(b2.w)) : 0.f;
             if (DR) {
-                const uint4 b5 = philox4x32_10(g, t_rl, 5, STREAM_RESET, k0, k1);
-                const uint4 b6 = philox4x32_10(g, t_rl, 6, STREAM_RESET, k0, k1);
-                const uint4 b7 = philox4x32_10(g, t_rl, 7, STREAM_RESET, k0, k1);
-                const uint4 b8 = philox4x32_10(g, t_rl, 8, STREAM_RESET, k0, k1);
+                const uint4 b5 = reset_block(5), b6 = reset_block(6), b7 = reset_block(7), b8 = reset_block(8);
                 if (flags & TACO_F_RANDOM_ROTORDYNAMIC_COE) {     // thrust_dynamics.py:117-122
                     poly[0] = kPolyNom[0] * rr(TACO_DIFF(dr_rng, 5), TACO_DIFF(dr_lo, 6), u01(b5.x));
                     poly[1] = kPolyNom[1] * rr(TACO_DIFF(dr_rng, 5), TACO_DIFF(dr_lo, 6), u01(b5.y));
@@ -299,7 +326,7 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
                 p.D[3][i] = make_float4(lag[0], lag[1], lag[2], lag[3]);
             }
             if (flags & TACO_F_RANDOM_ROTOR_SPEED) {              // thrust_dynamics.py:143-146
-                const uint4 b9 = philox4x32_10(g, t_rl, 9, STREAM_RESET, k0, k1);
+                const uint4 b9 = reset_block(9);
                 om[0] = rr(400.0f, 0.0f, u01(b9.x)); om[1] = rr(400.0f, 0.0f, u01(b9.y));
                 om[2] = rr(400.0f, 0.0f, u01(b9.z)); om[3] = rr(400.0f, 0.0f, u01(b9.w));
             } else { om[0] = om[1] = om[2] = om[3] = 0.f; }
@@ -323,13 +350,18 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
             sincos_draw(yaw * 0.5f, &tq.z, &tq.w);
         }
         // ------------------------------------------------------------------ command (:587-603, :758, :814-821, :886-917, :1058-1112)
+        // (the command stream's block is drawn only where a word of it is consumed: rotate with random_command, flip at progress 500)
         if (R || at500) {
-            const uint4 cb = philox4x32_10(g, t_rl, 0, STREAM_COMMAND, k0, k1);
             if (task == TACO_TASK_POS) cmd = 0.f;
-            else if (task == TACO_TASK_ROTATE) cmd = (flags & TACO_F_RANDOM_COMMAND) ? rr(12.0f, -6.0f, u01(cb.y)) : 1.0f;
+            else if (task == TACO_TASK_ROTATE) {
+                if (flags & TACO_F_RANDOM_COMMAND) {
+                    const uint4 cb = (coop && R) ? mbox[10] : philox4x32_10(g, t_rl, 0, STREAM_COMMAND, k0, k1);
+                    cmd = rr(12.0f, -6.0f, u01(cb.y));
+                } else cmd = 1.0f;
+            } else if (R) cmd = (wld.x > 5.0f) ? kTwoPi : -kTwoPi;   // a reset overrides the redraw at 500 (:886-917)
             else {
-                if (at500) cmd = cmd + kTwoPi * kTurns[cb.x >> 29];
-                if (R) cmd = (wld.x > 5.0f) ? kTwoPi : -kTwoPi;
+                const uint4 cb = philox4x32_10(g, t_rl, 0, STREAM_COMMAND, k0, k1);
+                cmd = cmd + kTwoPi * kTurns[cb.x >> 29];
             }
         }
         if (R) progress = 0;                                       // :510-511
@@ -447,7 +479,8 @@ __global__ void __launch_bounds__(kBlock, TACO_MIN_BLOCKS) fpv_step_kernel(const
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const float x = TACO_DIVC(thr[r], 1000.0f);
-                    const float tgt = ((((poly[0] + poly[1] * x) + poly[2] * y) + poly[3] * (x * x)) + poly[4] * x * y) * 100.0f;
+                    const float p01 = DR ? poly[0] + poly[1] * x : poly[1] * x;    // nominal poly[0] = +0 and poly[1] * x > 0: 0 + a == a bit for bit
+                    const float tgt = (((p01 + poly[2] * y) + poly[3] * (x * x)) + poly[4] * x * y) * 100.0f;
                     om[r] = om[r] + lag[r] * (tgt - om[r]);
                 }
                 if (flags & TACO_F_ROTOR_NOISE) {
