@@ -326,6 +326,10 @@ int taco_gae_normalize(int device, float* adv_dev, int64_t count, const double* 
 /* -- self-test: exhaustive comparison (all float bit patterns with |x| in [2^-60, 2^60]) of the kernel's 3-instruction
  * division-by-constant against IEEE division, for every divisor the step kernel uses; writes the mismatch count. */
 int taco_selftest_divc(int device, float dt, uint64_t* n_mismatch);
+/* atan2_poly of the step kernel (roll angle of refresh_state, fpv_asymmetry.py:334-360 / torch_utils.py:175-196: torch.atan2 in
+ * the reference) against double-precision atan2 on n_angles directions x 9 radii, the four axes and the origin:
+ * *max_ulp = largest error in units in the last place of the exact result, *n_nonfinite = NaN / Inf results (must be 0). */
+int taco_selftest_atan2(int device, uint32_t n_angles, float* max_ulp, uint32_t* n_nonfinite);
 
 /* number of CUDA kernels this library has launched in this process so far (every <<<>>> of libtaco_b200.so; captured launches
  * count once, at capture) */

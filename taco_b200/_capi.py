@@ -84,6 +84,7 @@ def lib():
         "taco_env_import_state": (C.c_int, [vp, vp]),
         "taco_env_debug_delay": (C.c_int, [vp, vp]),
         "taco_selftest_divc": (C.c_int, [C.c_int, f32, C.POINTER(u64)]),
+        "taco_selftest_atan2": (C.c_int, [C.c_int, C.c_uint32, C.POINTER(f32), C.POINTER(C.c_uint32)]),
         "taco_actor_create": (C.c_int, [C.c_int, C.POINTER(i32), i32, C.POINTER(vp)]),
         "taco_actor_destroy": (C.c_int, [vp]),
         "taco_actor_load": (C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), f32, vp]),

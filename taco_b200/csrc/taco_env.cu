@@ -239,6 +239,37 @@ __global__ void selftest_divc_kernel(unsigned long long* bad, float dt, uint32_t
     if (local) atomicAdd(bad, local);
 }
 
+// atan2_poly (fpv_math.cuh) against double-precision atan2 on a dense sweep of the circle at many radii, plus the axes and the
+// origin: out[0] = max error in ulp of the exact result (as float bits of the largest value seen), out[1] = non-finite results
+__global__ void selftest_atan2_kernel(uint32_t* out, uint32_t n_angles) {
+    float worst = 0.0f;
+    uint32_t nonfinite = 0;
+    for (uint32_t a = blockIdx.x * blockDim.x + threadIdx.x; a < n_angles; a += gridDim.x * blockDim.x) {
+        const double ang = -3.14159265358979323846 + 6.28318530717958647692 * ((double)a + 0.5) / (double)n_angles;
+#pragma unroll 1
+        for (int e = -12; e <= 4; e += 2) {                    // radii 2^-12 .. 2^4: the roll arguments have radius <= 2
+            const double rad = exp2((double)e) * (1.0 + 0.37 * (double)(a & 7u) / 8.0);
+            const float y = (float)(rad * sin(ang)), x = (float)(rad * cos(ang));
+            const float got = atan2_poly(y, x);
+            const double ref = atan2((double)y, (double)x);
+            const float ulp = __uint_as_float(__float_as_uint(fabsf((float)ref)) + 1u) - fabsf((float)ref);
+            if (!isfinite(got)) nonfinite += 1;
+            else worst = fmaxf(worst, (float)(fabs((double)got - ref) / (double)ulp));
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                  // axes and origin: exact values expected
+        const float ys[5] = {0.0f, 1.0f, 0.0f, -1.0f, 0.0f}, xs[5] = {1.0f, 0.0f, -1.0f, 0.0f, 0.0f};
+        const float want[5] = {0.0f, kHalfPi, kPi, -kHalfPi, 0.0f};
+        for (int k = 0; k < 5; ++k) {
+            const float got = atan2_poly(ys[k], xs[k]);
+            if (!isfinite(got)) nonfinite += 1;
+            else worst = fmaxf(worst, fabsf(got - want[k]) / 1.1920929e-7f);
+        }
+    }
+    atomicMax(out, __float_as_uint(worst));                     // non-negative floats order like their bit patterns
+    if (nonfinite) atomicAdd(out + 1, nonfinite);
+}
+
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace taco
@@ -267,6 +298,21 @@ int taco_selftest_divc(int device, float dt, uint64_t* n_mismatch) {
         for (unsigned long long i = 0; i < h[0] && i < 32; ++i) { char buf[64]; snprintf(buf, sizeof(buf), " (0x%08x,%u)", rec[2 * i], rec[2 * i + 1]); msg += buf; }
         g_err = msg;
     }
+    return TACO_OK;
+}
+int taco_selftest_atan2(int device, uint32_t n_angles, float* max_ulp, uint32_t* n_nonfinite) {
+    if (!max_ulp || !n_nonfinite || n_angles == 0) return fail(TACO_E_INVALID, "taco_selftest_atan2: null / empty argument");
+    DeviceGuard guard(device);
+    uint32_t* d = nullptr;
+    TACO_CUDA(cudaMalloc(&d, 2 * sizeof(uint32_t)));
+    TACO_CUDA(cudaMemset(d, 0, 2 * sizeof(uint32_t)));
+    selftest_atan2_kernel<<<148 * 4, 256>>>(d, n_angles); TACO_LAUNCHED();
+    TACO_CUDA(cudaGetLastError());
+    uint32_t h[2] = {0, 0};
+    TACO_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    memcpy(max_ulp, &h[0], sizeof(float));
+    *n_nonfinite = h[1];
     return TACO_OK;
 }
 int taco_abi_version(void) { return TACO_ABI_VERSION; }
