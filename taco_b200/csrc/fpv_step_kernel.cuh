@@ -89,19 +89,19 @@ __device__ __forceinline__ void write_rows_impl(const float* __restrict__ in, fl
 // column offsets are compile-time constants of the unrolled loops).  Kept part: lanes 0..31 and 32..keep2-1 of each row;
 // newest frame: two rows per store instruction (13 float2 each, lanes 26..31 idle).  Same bytes touched as the generic walk,
 // a third of its instructions (8 per element there: division by keep2, address, bounds predicate).
-template <int LC>
-__device__ __forceinline__ void write_rows_full(const float* __restrict__ in, float* __restrict__ out, const float* frames,
-                                                size_t blk_env0, int tid) {
+// kept part of rows [row0, row0 + NR) of the CTA by ONE warp (lanes along the row)
+template <int LC, int NR>
+__device__ __forceinline__ void copy_kept_rows(const float* __restrict__ in, float* __restrict__ out, size_t blk_env0, int row0, int lane) {
     constexpr int row2 = 13 * LC, keep2 = 13 * (LC - 1);
     constexpr int NJ = (keep2 + 31) / 32;                       // column chunks of 32 lanes per row
     constexpr int NJ1 = NJ > 0 ? NJ : 1;
     constexpr int EB = NJ1 <= 2 ? 8 : (NJ1 <= 4 ? 4 : 2);       // rows per batch: <= 16 loads in flight per thread
-    const int w = tid >> 5, lane = tid & 31;
-    const float2* src = reinterpret_cast<const float2*>(in) + (blk_env0 + 32 * w) * row2 + 13 + lane;
-    float2* dst = reinterpret_cast<float2*>(out) + (blk_env0 + 32 * w) * row2 + lane;
+    static_assert(NR % EB == 0, "rows per warp must be a multiple of the batch");
     if (keep2 > 0) {
-#pragma unroll
-        for (int e0 = 0; e0 < 32; e0 += EB) {
+        const float2* src = reinterpret_cast<const float2*>(in) + (blk_env0 + row0) * row2 + 13 + lane;
+        float2* dst = reinterpret_cast<float2*>(out) + (blk_env0 + row0) * row2 + lane;
+#pragma unroll (NR <= 32 ? NR / EB : 4)
+        for (int e0 = 0; e0 < NR; e0 += EB) {
             float2 v[EB][NJ1];
 #pragma unroll
             for (int e = 0; e < EB; ++e)
@@ -115,13 +115,25 @@ __device__ __forceinline__ void write_rows_full(const float* __restrict__ in, fl
                     if ((c + 1) * 32 <= keep2 || c * 32 + lane < keep2) dst[(e0 + e) * row2 + c * 32] = v[e][c];
         }
     }
+}
+// newest frame of the 32 rows [32 w, 32 w + 32) by warp w: two rows per store instruction (13 float2 each, lanes 26..31 idle)
+template <int LC>
+__device__ __forceinline__ void write_newest_rows(float* __restrict__ out, const float* frames, size_t blk_env0, int tid) {
+    constexpr int row2 = 13 * LC, keep2 = 13 * (LC - 1);
+    const int w = tid >> 5, lane = tid & 31;
     if (lane < 26) {
         const int sub = lane >= 13 ? 1 : 0, j = lane - 13 * sub;
         const float* fr = frames + (32 * w + sub) * kFramePad + 2 * j;
-        float2* d = dst - lane + sub * row2 + keep2 + j;
+        float2* d = reinterpret_cast<float2*>(out) + (blk_env0 + 32 * w + sub) * row2 + keep2 + j;
 #pragma unroll
         for (int e = 0; e < 32; e += 2) d[e * row2] = make_float2(fr[e * kFramePad], fr[e * kFramePad + 1]);
     }
+}
+template <int LC>
+__device__ __forceinline__ void write_rows_full(const float* __restrict__ in, float* __restrict__ out, const float* frames,
+                                                size_t blk_env0, int tid) {
+    copy_kept_rows<LC, 32>(in, out, blk_env0, 32 * (tid >> 5), tid & 31);
+    write_newest_rows<LC>(out, frames, blk_env0, tid);
 }
 template <int LC>
 __device__ __forceinline__ void write_rows(const float* __restrict__ in, float* __restrict__ out, const float* frames,
@@ -136,8 +148,13 @@ __device__ __forceinline__ void write_rows(const float* __restrict__ in, float* 
 // D planes; when false the rotor polynomial / aero coefficients fold into instruction immediates.
 // SUB: physics sub-steps per simulate call (1 / 2 unrolled; 0 = runtime p.substeps).
 // DEVDIFF: graph-mode variant (difficulty scalars from device memory; costs two spilled registers, so eager launches do not use it).
-template <int TASK, bool DR, int SUB, bool DEVDIFF = false>
-__global__ void __launch_bounds__(kBlock, DR ? TACO_MIN_BLOCKS_DR : TACO_MIN_BLOCKS) fpv_step_kernel(const StepParams p) {
+// CW: extra warps of the CTA (threads >= 128) that do nothing but the kept-history copy of the states buffer, from the first cycle of
+// the CTA -- the copy depends on nothing the step computes.  CW = 4 for launches of at most one CTA per SM (the 4096-env scale of
+// the reference: one env's instruction stream is latency-bound there, and the copy's four load -> store round trips were a third of
+// the kernel's time when they ran after it: 14.4 -> 13.1 us); CW = 0 otherwise (the copy warps' registers cost resident compute
+// warps: one copy warp per CTA at 2 Mi envs measured 0.636 against 0.609 ms, profiles/ab_r02y.txt).
+template <int TASK, bool DR, int SUB, bool DEVDIFF = false, int CW = 0>
+__global__ void __launch_bounds__(kBlock + 32 * CW, CW ? 1 : (DR ? TACO_MIN_BLOCKS_DR : TACO_MIN_BLOCKS)) fpv_step_kernel(const StepParams p) {
     __shared__ __align__(16) float s_clean[kBlock * kFramePad];
     __shared__ __align__(16) float s_noisy[kBlock * kFramePad];
     __shared__ double s_stats[kNumStats];
@@ -145,11 +162,19 @@ __global__ void __launch_bounds__(kBlock, DR ? TACO_MIN_BLOCKS_DR : TACO_MIN_BLO
     const int tid = threadIdx.x;
     const int blk = blockIdx.x + p.block0;                      // a launch covers CTAs [block0, block0 + gridDim.x): chunked host pipeline
     const int i = blk * kBlock + tid;
-    const bool valid = i < p.n;
+    const bool is_copy = CW > 0 && tid >= kBlock;              // copy warps: no env of their own
+    const bool valid = !is_copy && i < p.n;
+    // split copy: else the compute warps copy after the step, as with CW = 0 (where nothing of this is kept live across the step)
+    const bool split_copy = CW > 0 && min(kBlock, p.n - blk * kBlock) == kBlock && p.len_states == 5;
     const uint32_t flags = p.flags;
     const bool obs_noise = (flags & TACO_F_OBSERVATION_NOISE) != 0;
     if (tid < kNumStats) s_stats[tid] = 0.0;
     __syncthreads();
+
+    if (CW > 0 && is_copy) {
+        if (split_copy) copy_kept_rows<5, kBlock / (CW ? CW : 1)>(p.states_in, p.states_out, (size_t)blk * kBlock, ((tid - kBlock) >> 5) * (kBlock / (CW ? CW : 1)), tid & 31);
+        return;                                                 // (the compute warps meet at a named barrier of their own)
+    }
 
     float st_rew = 0.f, st_done = 0.f, st_tout = 0.f, st_epret = 0.f, st_eplen = 0.f, st_nonfin = 0.f, st_ovf = 0.f;
     float* fc = s_clean + tid * kFramePad;
@@ -719,7 +744,8 @@ __global__ void __launch_bounds__(kBlock, DR ? TACO_MIN_BLOCKS_DR : TACO_MIN_BLO
             if (b_ovf) atomicAdd(&s_stats[6], (double)__popc(b_ovf));
         }
     }
-    __syncthreads();   // frames + stats visible
+    if (CW > 0) asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");   // the compute warps only: the copy warps may be gone
+    else __syncthreads();   // frames + stats visible
     if (tid < 7) {
         const double v = s_stats[tid];
         if (v != 0.0) atomicAdd(p.stats + (size_t)(blk % kStatSlots) * kStatStride + tid, v);
@@ -731,34 +757,37 @@ __global__ void __launch_bounds__(kBlock, DR ? TACO_MIN_BLOCKS_DR : TACO_MIN_BLO
     // ---------------------------------------------------------------------- history shift + newest frame (:392,:413)
     // out[e][f][:] = in[e][f+1][:] for f < L-1, newest frame last; ping-pong buffers, so no in-place hazard.
     const size_t blk_env0 = (size_t)blk * kBlock;
-    const int nv = min(kBlock, p.n - blk * kBlock);
-    if (p.len_states == 5) write_rows<5>(p.states_in, p.states_out, s_clean, 5, blk_env0, tid, nv);
+    const int nv = min(kBlock, p.n - blk * kBlock);             // valid rows of this CTA
+    if (CW > 0 && split_copy) write_newest_rows<5>(p.states_out, s_clean, blk_env0, tid);   // the copy warps moved the kept part
+    else if (p.len_states == 5) write_rows<5>(p.states_in, p.states_out, s_clean, 5, blk_env0, tid, nv);
     else write_rows<0>(p.states_in, p.states_out, s_clean, p.len_states, blk_env0, tid, nv);
     const float* sf = obs_noise ? s_noisy : s_clean;
     if (p.len_obs == 1) write_rows<1>(p.obs_in, p.obs_out, sf, 1, blk_env0, tid, nv);
     else write_rows<0>(p.obs_in, p.obs_out, sf, p.len_obs, blk_env0, tid, nv);
 }
 
+#ifndef TACO_COPY_WARPS_SMALL
+#define TACO_COPY_WARPS_SMALL 4     // copy warps per CTA for launches of <= kSmallGrid CTAs (0 = off)
+#endif
+constexpr int kSmallGrid = 148;     // one CTA per SM
+
+template <int TASK, bool DR, bool DEVDIFF>
+static void launch_variant(const StepParams& p, int grid, cudaStream_t stream) {
+    if (p.substeps == 2) {
+        if (TACO_COPY_WARPS_SMALL > 0 && grid <= kSmallGrid)
+            fpv_step_kernel<TASK, DR, 2, DEVDIFF, TACO_COPY_WARPS_SMALL><<<grid, kBlock + 32 * TACO_COPY_WARPS_SMALL, 0, stream>>>(p);
+        else fpv_step_kernel<TASK, DR, 2, DEVDIFF><<<grid, kBlock, 0, stream>>>(p);
+    } else if (p.substeps == 1 && !DEVDIFF) fpv_step_kernel<TASK, DR, 1, DEVDIFF><<<grid, kBlock, 0, stream>>>(p);
+    else fpv_step_kernel<TASK, DR, 0, DEVDIFF><<<grid, kBlock, 0, stream>>>(p);
+}
 template <int TASK>
 static void launch_task(const StepParams& p, cudaStream_t stream) {
     const int grid = p.nblocks > 0 ? p.nblocks : p.n_pad / kBlock - p.block0;
     if (p.diff_dev != nullptr) {                       // graph mode (taco_env_graph_begin .. _end)
-        if (p.has_dr) {
-            if (p.substeps == 2) fpv_step_kernel<TASK, true, 2, true><<<grid, kBlock, 0, stream>>>(p);
-            else fpv_step_kernel<TASK, true, 0, true><<<grid, kBlock, 0, stream>>>(p);
-        } else {
-            if (p.substeps == 2) fpv_step_kernel<TASK, false, 2, true><<<grid, kBlock, 0, stream>>>(p);
-            else fpv_step_kernel<TASK, false, 0, true><<<grid, kBlock, 0, stream>>>(p);
-        }
-    } else if (p.has_dr) {
-        if (p.substeps == 2) fpv_step_kernel<TASK, true, 2><<<grid, kBlock, 0, stream>>>(p);
-        else if (p.substeps == 1) fpv_step_kernel<TASK, true, 1><<<grid, kBlock, 0, stream>>>(p);
-        else fpv_step_kernel<TASK, true, 0><<<grid, kBlock, 0, stream>>>(p);
-    } else {
-        if (p.substeps == 2) fpv_step_kernel<TASK, false, 2><<<grid, kBlock, 0, stream>>>(p);
-        else if (p.substeps == 1) fpv_step_kernel<TASK, false, 1><<<grid, kBlock, 0, stream>>>(p);
-        else fpv_step_kernel<TASK, false, 0><<<grid, kBlock, 0, stream>>>(p);
-    }
+        if (p.has_dr) launch_variant<TASK, true, true>(p, grid, stream);
+        else launch_variant<TASK, false, true>(p, grid, stream);
+    } else if (p.has_dr) launch_variant<TASK, true, false>(p, grid, stream);
+    else launch_variant<TASK, false, false>(p, grid, stream);
     TACO_LAUNCHED();
 }
 

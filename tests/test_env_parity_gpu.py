@@ -164,6 +164,36 @@ def test_shard_invariance_single_gpu():
     full.close(); shard.close()
 
 
+@pytest.mark.parametrize("task,dr", [("flip", False), ("mix", True)])
+def test_large_grid_launch_matches_small_grid_shards(task, dr):
+    """The step kernel has two launch shapes: grids of at most one CTA per SM (<= 148 x 128 envs: the 4096-env scale every oracle
+    comparison in this file runs at) add four copy warps per CTA that move the kept state history while the step computes; larger
+    grids -- the benchmarked shape -- copy after the step.  One 24 001-env handle (188 CTAs, ragged tail) against 4096-env shards
+    of the same global envs: states, observations, rewards, masks and the exported env state must be bit-identical, step after
+    step, so the oracle parity of the small shape carries over to the large one."""
+    import taco_b200
+    from taco_b200 import make_cfg
+    n = 24_001
+    full = taco_b200.FpvVecTask(make_cfg(task, n, domain_randomization=dr), "cuda:0", "cuda:0", -1, True, seed=11)
+    offs = [0, 8192, n - 4096]
+    shards = [taco_b200.FpvVecTask(make_cfg(task, 4096, domain_randomization=dr), "cuda:0", "cuda:0", -1, True,
+                                   env_offset=o, num_envs_global=n, seed=11) for o in offs]
+    for t in range(40):
+        af = full.random_actions(t)
+        o_f, r_f, x_f, e_f = full.step(af)
+        for o, sh in zip(offs, shards):
+            o_s, r_s, x_s, e_s = sh.step(af[o:o + 4096].contiguous())
+            assert torch.equal(o_f["states"][o:o + 4096], o_s["states"]), (t, o)
+            assert torch.equal(o_f["obs"][o:o + 4096], o_s["obs"]), (t, o)
+            assert torch.equal(r_f[o:o + 4096], r_s) and torch.equal(x_f[o:o + 4096], x_s)
+            assert torch.equal(e_f["time_outs"][o:o + 4096], e_s["time_outs"])
+    st = full.export_state()
+    for o, sh in zip(offs, shards):
+        assert np.array_equal(st[o:o + 4096, :34], sh.export_state()[:, :34])
+        sh.close()
+    full.close()
+
+
 @pytest.mark.parametrize("mode", ["mapped", "copy", "pageable"])
 @pytest.mark.parametrize("n", [3000, 200_003])     # one chunk / three pipelined chunks; neither a multiple of 128 (tail block)
 def test_host_buffer_entry_point_matches_device_path(n, mode, monkeypatch):
