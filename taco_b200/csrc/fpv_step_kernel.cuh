@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(kBlock + 32 * CW, CW ? 1 : (DR ? TACO_MIN_BLOC
                 cmd = cmd + kTwoPi * kTurns[cb.x >> 29];
             }
         }
+        if (coop) __syncwarp();                                    // mailbox reads done before any lane writes its frame over those rows
         if (R) progress = 0;                                       // :510-511
 
         // ------------------------------------------------------------------ pre_physics_step (:321-332): enqueue the action

@@ -24,6 +24,15 @@ def step_part():
         env.stats()
         torch.cuda.synchronize()
         env.close()
+    # natural, sparse resets (episodes end at different steps -> one or two resetting lanes per warp: the warp-generated reset draws
+    # through the shared-memory mailbox) in both launch shapes: <= 148 CTAs (copy warps) and a larger grid (copy after the step)
+    for n, steps in ((4096, 70), (148 * 128 + 999, 45)):
+        env = taco_b200.FpvVecTask(make_cfg("flip", n), "cuda:0", "cuda:0", -1, True, seed=5)
+        for t in range(steps):
+            env.step(env.random_actions(t))
+        st = env.stats().cpu().tolist()
+        assert st[1] > 0, "no episode ended: the sparse-reset path was not exercised"
+        env.close()
     print("step ok")
 
 
