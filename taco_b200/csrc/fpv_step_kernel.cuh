@@ -129,17 +129,47 @@ __device__ __forceinline__ void write_newest_rows(float* __restrict__ out, const
         for (int e = 0; e < 32; e += 2) d[e * row2] = make_float2(fr[e * kFramePad], fr[e * kFramePad + 1]);
     }
 }
-template <int LC>
+// A full CTA with a compile-time L.  Newest frame: write_newest_rows.  Kept part, two forms, chosen per kernel variant by
+// measurement (tools/step_ab.py, profiles/ab_r02ab.txt / ab_r02ac.txt):
+//   FLAT = false  lanes along the rows (copy_kept_rows): a third of the instructions, but the second column chunk of a 52-element row
+//                 fills 20 of 32 lanes -- best for the DR variants (96 registers, 5 CTAs per SM: mix + DR 0.719 against 0.731 ms)
+//   FLAT = true   the flat walk over the CTA's kept elements (every request 256 contiguous bytes, 13 loads in flight per thread):
+//                 best for the variants at 80 registers / 6 CTAs per SM (flip: 0.560 against 0.584 ms over the first synchronised
+//                 steps, 0.602 against 0.607 in steady state)
+template <int LC, bool FLAT>
 __device__ __forceinline__ void write_rows_full(const float* __restrict__ in, float* __restrict__ out, const float* frames,
                                                 size_t blk_env0, int tid) {
-    copy_kept_rows<LC, 32>(in, out, blk_env0, 32 * (tid >> 5), tid & 31);
+    if constexpr (FLAT) {
+        constexpr int row2 = 13 * LC, keep2 = 13 * (LC - 1);
+        const float2* in2 = reinterpret_cast<const float2*>(in) + blk_env0 * row2;
+        float2* out2 = reinterpret_cast<float2*>(out) + blk_env0 * row2;
+        if constexpr (keep2 > 0) {
+            constexpr int total = kBlock * keep2, U = 13;
+            for (int k0 = tid; k0 < total; k0 += kBlock * U) {
+                float2 v[U];
+                int dst[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int k = k0 + u * kBlock;
+                    const int e = k / keep2, j = k - e * keep2;
+                    dst[u] = e * row2 + j;
+                    v[u] = (k < total) ? __ldg(in2 + dst[u] + 13) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (k0 + u * kBlock < total) out2[dst[u]] = v[u];
+            }
+        }
+    } else {
+        copy_kept_rows<LC, 32>(in, out, blk_env0, 32 * (tid >> 5), tid & 31);
+    }
     write_newest_rows<LC>(out, frames, blk_env0, tid);
 }
-template <int LC>
+template <int LC, bool FLAT>
 __device__ __forceinline__ void write_rows(const float* __restrict__ in, float* __restrict__ out, const float* frames,
                                            int L_rt, size_t blk_env0, int tid, int nv) {
     if (nv == kBlock) {                                                                        // every CTA but (at most) the last
-        if constexpr (LC > 0) write_rows_full<LC>(in, out, frames, blk_env0, tid);
+        if constexpr (LC > 0) write_rows_full<LC, FLAT>(in, out, frames, blk_env0, tid);
         else write_rows_impl<LC, true>(in, out, frames, L_rt, blk_env0, tid, nv);
     } else write_rows_impl<LC, false>(in, out, frames, L_rt, blk_env0, tid, nv);
 }
@@ -760,11 +790,11 @@ __global__ void __launch_bounds__(kBlock + 32 * CW, CW ? 1 : (DR ? TACO_MIN_BLOC
     const size_t blk_env0 = (size_t)blk * kBlock;
     const int nv = min(kBlock, p.n - blk * kBlock);             // valid rows of this CTA
     if (CW > 0 && split_copy) write_newest_rows<5>(p.states_out, s_clean, blk_env0, tid);   // the copy warps moved the kept part
-    else if (p.len_states == 5) write_rows<5>(p.states_in, p.states_out, s_clean, 5, blk_env0, tid, nv);
-    else write_rows<0>(p.states_in, p.states_out, s_clean, p.len_states, blk_env0, tid, nv);
+    else if (p.len_states == 5) write_rows<5, !DR>(p.states_in, p.states_out, s_clean, 5, blk_env0, tid, nv);
+    else write_rows<0, false>(p.states_in, p.states_out, s_clean, p.len_states, blk_env0, tid, nv);
     const float* sf = obs_noise ? s_noisy : s_clean;
-    if (p.len_obs == 1) write_rows<1>(p.obs_in, p.obs_out, sf, 1, blk_env0, tid, nv);
-    else write_rows<0>(p.obs_in, p.obs_out, sf, p.len_obs, blk_env0, tid, nv);
+    if (p.len_obs == 1) write_rows<1, !DR>(p.obs_in, p.obs_out, sf, 1, blk_env0, tid, nv);
+    else write_rows<0, false>(p.obs_in, p.obs_out, sf, p.len_obs, blk_env0, tid, nv);
 }
 
 #ifndef TACO_COPY_WARPS_SMALL

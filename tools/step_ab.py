@@ -6,6 +6,8 @@ import json, os, statistics, subprocess, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rounds = int(sys.argv[1]); libs = sys.argv[2:]
 work = [("flip", ["flip", "2097152", "10", "25"]), ("mixdr", ["mix", "2097152", "8", "25", "--dr"]), ("flip4096", ["flip", "4096", "6", "200"])]
+if os.environ.get("AB_WORK"):
+    work = [w for w in work if w[0] in os.environ["AB_WORK"].split(",")]
 res = {}
 for r in range(rounds):
     for lib in libs:
@@ -18,5 +20,7 @@ for r in range(rounds):
                 print("FAILED", lib, name, out.stderr[-500:]); continue
             late = [x["ms_per_step"] for x in w if x["steps"][0] >= 100] or [w[-1]["ms_per_step"]]
             res.setdefault((lib, name), []).append(statistics.median(late))
+            if len(w) > 2:                           # the synchronised early steps (no resets yet, boost clocks): the driver's 20-step burst
+                res.setdefault((lib, name + ":steps25-50"), []).append(w[1]["ms_per_step"])
 for (lib, name), v in sorted(res.items(), key=lambda kv: (kv[0][1], kv[0][0])):
     print(json.dumps({"workload": name, "lib": lib, "ms_per_step": v}))
