@@ -41,6 +41,7 @@ struct CriticTcParams {
     float* value;          // (n_rows) f32
     int in_dim, seq_len, n_rows, num_tiles;
     int tiles_per_cta;     // 2 (a CTA keeps a pair of tiles in flight) or 1
+    int stagger;           // cycles by which tile 1's LSTM chain trails tile 0's (0 = strictly alternating issue order)
     int lstm_hidden;       // H: multiple of 16, <= 64
     int n_hidden;          // MLP hidden layers, 1..3
     const uint8_t* wimg;   // pre-swizzled bf16 chunk images: LSTM [W_hh | W_ih] (gate-permuted rows), MLP layers, output (16 rows)
@@ -63,6 +64,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// non-blocking phase test of an mbarrier
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+constexpr int kCriticStagger = 1200;      // default of CriticTcParams::stagger (TACO_CRITIC_STAGGER in the environment overrides it: tuning)
 __device__ __forceinline__ float tanh_mufu(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // TACO_CRITIC_GATES (tuning builds): 0 (default) = tanh.approx.f32; 1 = MUFU.TANH on packed half pairs (tanh.approx.f16x2: the same
@@ -273,7 +281,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) critic_tc_kernel(const CriticTc
         mbar_wait(bar_lstm, 0u);                                       // the resident LSTM image
         for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
             const int nt = min(tps, p.num_tiles - tps * pair);
-            for (int s = 0; s < n_sched; ++s) {
+            // ---- LSTM steps: the weights are resident, so the two tiles' chains need not advance in lock step.  Their parts are
+            // issued as the tiles become ready (the epilogue side is unchanged: per tile, wait bar_d / arrive bar_a), and tile 1's
+            // chain is started p.stagger cycles after tile 0's, so that one tile's gate math (MUFU-bound: 4 warps per
+            // scheduler when both tiles are in it) falls into the other's accumulator / frame-load / staging waits.
+            int s_first = 0;
+            if (p.stagger > 0 && nt == 2) {
+                const int n = p.layer[0].n, parts = (n + kPartN - 1) / kPartN, total_parts = T * parts;
+                int done0 = 0, done1 = 0;
+                long long t0_start = 0;
+                while (done0 < total_parts || done1 < total_parts) {
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const int dn = t == 0 ? done0 : done1;
+                        if (dn >= total_parts) continue;
+                        if (t == 1 && dn == 0 && (done0 == 0 || clock64() - t0_start < (long long)p.stagger)) continue;
+                        if (!mbar_test(bar_a + 8 * t, (a_phase >> t) & 1u)) continue;
+                        a_phase ^= (1u << t);
+                        const int h0 = (dn % parts) * kPartN;
+                        const uint32_t idesc = umma_idesc_bf16(kTileM, min(kPartN, n - h0));
+                        const uint64_t bdesc = bdesc0 + (uint64_t)((kRing * kSlotBytes + (h0 / kPartN) * 2 * kChunkBytes) >> 4);
+                        tc_fence_after();
+                        TACO_DBG(0, dbg_n, 0x20 | t);
+                        if (elect_one_sync()) {
+                            const uint32_t a_addr = tmem0 + (uint32_t)(t * kTmemSlot);
+                            const uint32_t d_addr = a_addr + (uint32_t)kTmemD;
+                            for (int c = 0; c < p.layer[0].kchunks; ++c) {
+                                const uint64_t b_c = bdesc + (uint64_t)(c * (kChunkBytes >> 4));
+                                const uint32_t a_c = a_addr + (uint32_t)(c * (kKC / 2));
+                                umma_bf16_ts(d_addr, a_c, b_c, idesc, (uint32_t)(c != 0));
+                                umma_bf16_ts(d_addr, a_c + 8u, b_c + 2u, idesc, 1u);
+                                if (c == 0) {                          // the x_t chunk of an LSTM step holds only 32 K values (26 + 2 bias + pad)
+                                    umma_bf16_ts(d_addr, a_c + 16u, b_c + 4u, idesc, 1u);
+                                    umma_bf16_ts(d_addr, a_c + 24u, b_c + 6u, idesc, 1u);
+                                }
+                            }
+                            umma_commit(bar_d + 8 * t);
+                        }
+                        __syncwarp();
+                        TACO_DBG(0, dbg_n, 0x30 | t);
+                        if (t == 0) { if (done0 == 0) t0_start = clock64(); ++done0; } else ++done1;
+                    }
+                    __nanosleep(20);
+                }
+                s_first = T;
+            }
+            for (int s = s_first; s < n_sched; ++s) {
                 const int l = s < T ? 0 : s - T + 1;
                 const int n = p.layer[l].n, kch = p.layer[l].kchunks;
                 for (int h0 = 0; h0 < n; h0 += kPartN) {

@@ -383,6 +383,8 @@ int taco_critic_forward(TacoCritic* c, const float* states_dev, float* value_dev
         p.wimg = c->wimg; p.bias = c->bias_pad; p.b_out = c->b_out;
         for (int l = 0; l <= p.n_hidden + 1; ++l) p.layer[l] = c->tc_layer[l];
         p.tiles_per_cta = p.num_tiles <= c->num_sms ? 1 : 2;
+        static const int stagger = [] { const char* e = getenv("TACO_CRITIC_STAGGER"); return e ? atoi(e) : taco::critic::kCriticStagger; }();
+        p.stagger = stagger;
         const int num_pairs = (p.num_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
         const int grid = num_pairs < c->num_sms ? num_pairs : c->num_sms;
         // developer aid: TACO_CRITIC_TIMELINE=<file> records clock64 stamps of CTA 0's MMA issuer / epilogue (synchronous)
