@@ -428,7 +428,7 @@ def shard_point(torch, dist, taco_b200, dev, rank, world, task, n, dr, strict_fp
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "algorithmic_bytes_per_env_step": algo}}
 
 
-def policy_loop_point(torch, dist, taco_b200, dev, rank, world, n, hidden, horizon, strict_fp, reps=3):
+def policy_loop_point(torch, dist, taco_b200, dev, rank, world, n, hidden, horizon, strict_fp, reps=5):
     """north_star "random-init-policy rollouts at 1, 2, 4, 8 GPUs": the whole collection loop of PPO.run on every rank's env shard
     -- horizon x (actor sample + LSTM critic value + env.step, zero-copy store), GAE, then the two small all-reduces (advantage
     moments, episode statistics) -- timed per rollout, max over ranks."""
@@ -458,13 +458,16 @@ def policy_loop_point(torch, dist, taco_b200, dev, rank, world, n, hidden, horiz
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
+    # every rollout timed on its own and the MEDIAN reported: the loop is eager (101 launches per rollout), so one host hiccup
+    # (a 90 ms stall of the launching thread was seen once in r02ak) would otherwise triple the mean of three; all values are in the line
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for e0, e1 in evs:
+        e0.record()
         stats = run()
-    e1.record()
+        e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    per_rollout = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
+    ms = per_rollout[len(per_rollout) // 2]
     if world > 1:
         tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
@@ -474,6 +477,7 @@ def policy_loop_point(torch, dist, taco_b200, dev, rank, world, n, hidden, horiz
                         f"{'x'.join(map(str, cs))} (tcgen05 kernels; sizes are OUR stated default) + env.step every step, zero-copy store, GAE, "
                         "2 small all-reduces per rollout; random-init spectral-normalised policy",
             "value": float(world) * n * horizon / (ms * 1e-3), "unit": "env-steps/s", "ms_per_rollout": ms, "ms_per_step": ms / horizon,
+            "ms_per_rollout_all": [round(x, 3) for x in per_rollout], "statistic": f"median of {reps} rollouts",
             "n_gpus": world, "gpu_launches_per_rollout": 3 * horizon + 5,
             "episodes_finished_last_rollout": float(stats[1].item())}
 

@@ -183,11 +183,15 @@ __device__ __forceinline__ void write_rows(const float* __restrict__ in, float* 
 // the reference: one env's instruction stream is latency-bound there, and the copy's four load -> store round trips were a third of
 // the kernel's time when they ran after it: 14.4 -> 13.1 us); CW = 0 otherwise (the copy warps' registers cost resident compute
 // warps: one copy warp per CTA at 2 Mi envs measured 0.636 against 0.609 ms, profiles/ab_r02y.txt).
-template <int TASK, bool DR, int SUB, bool DEVDIFF = false, int CW = 0>
+// HB: variant for the mapped host-buffer step (taco_env_step_host with pinned buffers): the one-byte results (time-outs, compact
+// flags) leave as one 128-byte run per CTA.  A separate instantiation, so that the device-resident step carries none of it
+// (as run-time branches it cost that step 1 % over the first synchronised steps, profiles/ab_r02aj.txt).
+template <int TASK, bool DR, int SUB, bool DEVDIFF = false, int CW = 0, bool HB = false>
 __global__ void __launch_bounds__(kBlock + 32 * CW, CW ? 1 : (DR ? TACO_MIN_BLOCKS_DR : TACO_MIN_BLOCKS)) fpv_step_kernel(const StepParams p) {
     __shared__ __align__(16) float s_clean[kBlock * kFramePad];
     __shared__ __align__(16) float s_noisy[kBlock * kFramePad];
     __shared__ double s_stats[kNumStats];
+    __shared__ __align__(16) uint8_t s_hostb[HB ? kBlock : 16];  // byte-wide host results of the CTA (mapped host-buffer step)
 
     const int tid = threadIdx.x;
     const int blk = blockIdx.x + p.block0;                      // a launch covers CTAs [block0, block0 + gridDim.x): chunked host pipeline
@@ -745,8 +749,14 @@ __global__ void __launch_bounds__(kBlock + 32 * CW, CW ? 1 : (DR ? TACO_MIN_BLOC
         // mapped host-buffer step (taco_env_step_host): results are posted straight into the caller's pinned host memory
         if (p.host_reset) p.host_reset[i] = done ? 1ll : 0ll;
         if (p.host_rew) p.host_rew[i] = rew;
-        if (p.host_tout) p.host_tout[i] = tout ? 1 : 0;
-        if (p.host_flags) p.host_flags[i] = (uint8_t)((done ? 1 : 0) | (tout ? 2 : 0));
+        // the one-byte results go out as ONE 128-byte run per CTA after the barrier below (a warp's 32 single bytes are a 32-byte PCIe
+        // write with as much header as payload: the time-out column alone cost 0.07 ms of the 0.82 ms host-buffer step)
+        if (HB) {
+            if (p.host_tout || p.host_flags) s_hostb[tid] = p.host_flags ? (uint8_t)((done ? 1 : 0) | (tout ? 2 : 0)) : (uint8_t)(tout ? 1 : 0);
+        } else {
+            if (p.host_tout) p.host_tout[i] = tout ? 1 : 0;
+            if (p.host_flags) p.host_flags[i] = (uint8_t)((done ? 1 : 0) | (tout ? 2 : 0));
+        }
     } else {
 #pragma unroll
         for (int j = 0; j < 26; ++j) { fc[j] = 0.f; fn[j] = 0.f; }
@@ -777,6 +787,13 @@ __global__ void __launch_bounds__(kBlock + 32 * CW, CW ? 1 : (DR ? TACO_MIN_BLOC
     }
     if (CW > 0) asm volatile("bar.sync 1, %0;" ::"n"(kBlock) : "memory");   // the compute warps only: the copy warps may be gone
     else __syncthreads();   // frames + stats visible
+    if (HB && (p.host_tout || p.host_flags)) {                  // blk * 128 keeps the 4-byte alignment of a pinned buffer
+        uint8_t* hb = (p.host_flags ? p.host_flags : p.host_tout) + (size_t)blk * kBlock;
+        const int nvb = min(kBlock, p.n - blk * kBlock);
+        if (nvb == kBlock && (reinterpret_cast<uintptr_t>(hb) & 3u) == 0) {
+            if (tid < kBlock / 4) reinterpret_cast<uint32_t*>(hb)[tid] = reinterpret_cast<const uint32_t*>(s_hostb)[tid];
+        } else if (tid < nvb) hb[tid] = s_hostb[tid];
+    }
     if (tid < 7) {
         const double v = s_stats[tid];
         if (v != 0.0) atomicAdd(p.stats + (size_t)(blk % kStatSlots) * kStatStride + tid, v);
@@ -807,6 +824,7 @@ static void launch_variant(const StepParams& p, int grid, cudaStream_t stream) {
     if (p.substeps == 2) {
         if (TACO_COPY_WARPS_SMALL > 0 && grid <= kSmallGrid)
             fpv_step_kernel<TASK, DR, 2, DEVDIFF, TACO_COPY_WARPS_SMALL><<<grid, kBlock + 32 * TACO_COPY_WARPS_SMALL, 0, stream>>>(p);
+        else if (!DEVDIFF && (p.host_tout || p.host_flags)) fpv_step_kernel<TASK, DR, 2, false, 0, true><<<grid, kBlock, 0, stream>>>(p);
         else fpv_step_kernel<TASK, DR, 2, DEVDIFF><<<grid, kBlock, 0, stream>>>(p);
     } else if (p.substeps == 1 && !DEVDIFF) fpv_step_kernel<TASK, DR, 1, DEVDIFF><<<grid, kBlock, 0, stream>>>(p);
     else fpv_step_kernel<TASK, DR, 0, DEVDIFF><<<grid, kBlock, 0, stream>>>(p);
