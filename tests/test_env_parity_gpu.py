@@ -164,8 +164,8 @@ def test_shard_invariance_single_gpu():
     full.close(); shard.close()
 
 
-@pytest.mark.parametrize("task,dr", [("flip", False), ("mix", True)])
-def test_large_grid_launch_matches_small_grid_shards(task, dr):
+@pytest.mark.parametrize("task,dr,n,steps", [("flip", False, 24_001, 40), ("mix", True, 24_001, 40), ("flip", False, 2_097_152, 12)])
+def test_large_grid_launch_matches_small_grid_shards(task, dr, n, steps):
     """The step kernel has two launch shapes: grids of at most one CTA per SM (<= 148 x 128 envs: the 4096-env scale every oracle
     comparison in this file runs at) add four copy warps per CTA that move the kept state history while the step computes; larger
     grids -- the benchmarked shape -- copy after the step.  One 24 001-env handle (188 CTAs, ragged tail) against 4096-env shards
@@ -173,12 +173,12 @@ def test_large_grid_launch_matches_small_grid_shards(task, dr):
     step, so the oracle parity of the small shape carries over to the large one."""
     import taco_b200
     from taco_b200 import make_cfg
-    n = 24_001
+    # (the third case is bench.py's own workload: BASELINE configs[1] at 2 Mi envs per GPU)
     full = taco_b200.FpvVecTask(make_cfg(task, n, domain_randomization=dr), "cuda:0", "cuda:0", -1, True, seed=11)
-    offs = [0, 8192, n - 4096]
+    offs = [0, (n // 2 // 128) * 128 + 128, n - 4096]
     shards = [taco_b200.FpvVecTask(make_cfg(task, 4096, domain_randomization=dr), "cuda:0", "cuda:0", -1, True,
                                    env_offset=o, num_envs_global=n, seed=11) for o in offs]
-    for t in range(40):
+    for t in range(steps):
         af = full.random_actions(t)
         o_f, r_f, x_f, e_f = full.step(af)
         for o, sh in zip(offs, shards):
